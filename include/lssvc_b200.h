@@ -1,0 +1,233 @@
+/*
+ * lssvc_b200 — C-ABI of the B200-native LSSVC two-layer coding forward pass.
+ *
+ * Every entry point takes plain pointers and sizes (device pointers unless a
+ * parameter is marked "host"), a cudaStream_t passed as void*, and returns 0 on
+ * success or a negative lssvc_status.  No torch types cross this boundary.
+ *
+ * Activations are NHWC fp32 ("pixel-major": all channels of one pixel are
+ * contiguous).  A view is a window of `C` channels inside a buffer whose
+ * pixels are `pitch` floats apart, so channel-concatenation of the reference
+ * (torch.cat(dim=1)) is a matter of pointing producers at slices of one buffer.
+ *
+ * The reference is a PyTorch code drop with no FFI of its own on this path
+ * except the pybind11 entropy coder; each entry point below cites the reference
+ * operator (file:line under /root/reference) it replaces.
+ */
+#ifndef LSSVC_B200_H
+#define LSSVC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  LSSVC_OK = 0,
+  LSSVC_ERR_ARG = -1,        /* bad shape / alignment / unsupported configuration */
+  LSSVC_ERR_CUDA = -2,       /* a CUDA runtime / driver call failed               */
+  LSSVC_ERR_NO_DEVICE = -3,  /* no sm_100 device                                   */
+  LSSVC_ERR_STREAM = -4      /* rANS stream exhausted / malformed                  */
+} lssvc_status;
+
+/* NHWC fp32 window: element (y, x, c) lives at ptr[(y * W + x) * pitch + c]. */
+typedef struct {
+  float *ptr;
+  int32_t H, W, C;
+  int32_t pitch;
+} lssvc_view;
+
+#define LSSVC_MAX_SRC 3
+
+#define LSSVC_ACT_NONE 0
+#define LSSVC_ACT_LRELU 1 /* x > 0 ? x : slope * x (ReLU is slope 0) */
+
+#define LSSVC_IN_NONE 0
+#define LSSVC_IN_SQUARE 1 /* x*x, used by GDN's norm pool */
+#define LSSVC_IN_LRELU 2
+
+#define LSSVC_EPI_PLAIN 0
+#define LSSVC_EPI_GDN 1  /* out = gdn_x * rsqrt(acc + bias)   (gdn.py:29-44, video_net_component.py:83-105) */
+#define LSSVC_EPI_IGDN 2 /* out = gdn_x * sqrt(acc + bias)                                               */
+
+/*
+ * One convolution with its fused epilogue.  Replaces nn.Conv2d / nn.ConvTranspose2d(stride 1)
+ * + nn.LeakyReLU / nn.ReLU + residual adds + nn.PixelShuffle(2) as they occur in
+ * src/IntraModules/layers.py, src/InterModules/{video_net_component,lssvc_modules}.py,
+ * src/models/{dmc_net,LSSVC_net,IntraSS,priors}.py.
+ *
+ *   acc  = sum over sources, taps, channels  in(src) * weight          (+ bias)
+ *   v    = act(acc) * out_scale
+ *   v   += res1 + res2                      (either may be absent: ptr == NULL)
+ *   out  = v                                (optionally through PixelShuffle(2))
+ *   out2 = lrelu(v, slope2)                 (optional second copy, same addressing mode)
+ *
+ * weight is packed [kh*kw][n_pad][cin_total] (K-major rows), bias is [n_pad];
+ * cin_total = sum of src[i].C, n_pad = cout rounded up to 16.
+ * With pixel_shuffle the packed output-channel order is (2*i + j) * (cout/4) + c for
+ * reference channel 4*c + 2*i + j, so that each sub-pixel's channels are contiguous.
+ */
+typedef struct {
+  int32_t n_src;
+  lssvc_view src[LSSVC_MAX_SRC];
+  const float *weight;
+  const float *bias;
+  int32_t kh, kw, stride, pad;
+  int32_t cout, n_pad, cin_total;
+  int32_t in_transform;
+  float in_slope;
+  int32_t epi;
+  int32_t act;
+  float slope;
+  float out_scale;
+  int32_t pixel_shuffle;
+  lssvc_view out;
+  lssvc_view res1, res2;
+  lssvc_view out2;
+  float slope2;
+  lssvc_view gdn_x;
+} lssvc_conv;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int32_t lssvc_abi_version(void);
+/* 0 when device `dev` is sm_100-class and the driver entry points needed for TMA resolve. */
+int32_t lssvc_device_check(int32_t dev);
+const char *lssvc_last_error(void);
+/* number of kernels this library launched since load (bench.py's gpu_launches) */
+int64_t lssvc_launch_count(void);
+
+/* ---- convolutions ------------------------------------------------------------------------ */
+/* tcgen05 / TMEM / TMA implicit-GEMM (TF32 operands, fp32 accumulate). */
+int32_t lssvc_conv_tc(const lssvc_conv *c, void *stream);
+/* fp32 CUDA-core implicit GEMM: any shape, also hosts the GDN epilogue and input transforms. */
+int32_t lssvc_conv_simt(const lssvc_conv *c, void *stream);
+/* depthwise 3x3, pad 1 (lssvc_modules.py:23-24): weight [9][C], bias [C] */
+int32_t lssvc_dwconv3x3(const lssvc_view *in, const float *weight, const float *bias,
+                        const lssvc_view *out, void *stream);
+/* nn.ConvTranspose2d(k=3, stride=2, padding=1, output_padding=1) (dmc_net.py:198-246):
+ * weight packed [9][cin][cout]; act/slope as above. */
+int32_t lssvc_deconv3x3_s2(const lssvc_view *in, const float *weight, const float *bias,
+                           int32_t act, float slope, const lssvc_view *out, void *stream);
+
+/* ---- layout ------------------------------------------------------------------------------ */
+/* NCHW contiguous [C][H][W] -> NHWC view (channels C..out.C-1 of the view are zero filled) */
+int32_t lssvc_nchw_to_nhwc(const float *src, int32_t C, const lssvc_view *out, void *stream);
+int32_t lssvc_nhwc_to_nchw(const lssvc_view *in, float *dst, void *stream);
+/* out = lrelu(in, slope) (slope 1 = copy) on views */
+int32_t lssvc_lrelu_copy(const lssvc_view *in, float slope, const lssvc_view *out, void *stream);
+/* out = a*wa + b*wb (wa/wb: 1-channel views or NULL for plain add) — hybrid context blend,
+ * LSSVC_net.py:253-255 with the 2-way softmax of lssvc_modules.py:133-153 folded in:
+ * logits is the 2-channel generator output, wa = sigmoid(l0 - l1), wb = 1 - wa. */
+int32_t lssvc_softmax2_blend(const lssvc_view *logits, const lssvc_view *a, const lssvc_view *b,
+                             const lssvc_view *out, void *stream);
+
+/* ---- warping / resampling ---------------------------------------------------------------- */
+/* flow_warp (video_net_component.py:329-352): bilinear, border clamp, align_corners=True,
+ * flow in pixels, channel 0 = x.  flow_scale multiplies the flow first. */
+int32_t lssvc_flow_warp(const lssvc_view *src, const lssvc_view *flow, float flow_scale,
+                        const lssvc_view *out, void *stream);
+/* F.interpolate(mode='bilinear', align_corners=False) to out.H x out.W, times `scale`
+ * (video_net_component.py:355-368, lssvc_modules.py:360,393,425, layers.py:269,284) */
+int32_t lssvc_bilinear_resize(const lssvc_view *in, float scale, const lssvc_view *out, void *stream);
+int32_t lssvc_avgpool2(const lssvc_view *in, const lssvc_view *out, void *stream);
+int32_t lssvc_maxpool2(const lssvc_view *in, const lssvc_view *out, void *stream);
+/* One SpyNet level prologue (video_net_component.py:241-246 / :319-324):
+ * flow_up = 2 * bilinear_x2(flow_coarse); out8 = cat(im1, flow_warp(im2, flow_up), flow_up).
+ * flow_coarse may be NULL (level 0: zero flow). */
+int32_t lssvc_spynet_prep(const lssvc_view *im1, const lssvc_view *im2, const lssvc_view *flow_coarse,
+                          const lssvc_view *out8, const lssvc_view *flow_up, void *stream);
+/* OffsetDiversity tail (lssvc_modules.py:95-110): `off` is conv_offset's output at half
+ * resolution (3*G*O channels = o1 | o2 | mask); it is bilinearly x2-upsampled on the fly,
+ * offset = mag * tanh(o) + flow, the feature is warped per (group, offset) and multiplied by
+ * sigmoid(mask); result is the (C * O)-channel tensor fed to the grouped 1x1 fusion conv,
+ * which is applied here too: out[g*cg + k] = sum_{j<2cg} w[g*cg+k][j] * warped[g*2cg + j] + b. */
+int32_t lssvc_offset_diversity(const lssvc_view *x, const lssvc_view *off, const lssvc_view *flow,
+                               const float *fusion_w, const float *fusion_b, int32_t groups,
+                               int32_t offset_num, float magnitude, const lssvc_view *out, void *stream);
+
+/* ---- entropy models ---------------------------------------------------------------------- */
+/* Laplace branch (LSSVC_net.py:154-161, 466-473; dmc_net.py:370-377, 429-449):
+ *   q = round(y - mean); y_hat = q + mean; bits += clamp(-log2(P(q; scale) + 1e-5), 0, 50)
+ * mean may be NULL (zero).  Any of y_q / y_hat / index may be NULL.  bits is a device double
+ * accumulator.  index (int32, NCHW order [C][H][W]) and sym (int32, NCHW) feed the rANS coder:
+ * index = GaussianEncoder.build_indexes(scale) through `thresholds[n_thr]`
+ * (video_entropy_models.py:309-313). */
+int32_t lssvc_laplace_quant(const lssvc_view *y, const lssvc_view *mean, const lssvc_view *scale,
+                            const lssvc_view *y_q, const lssvc_view *y_hat, double *bits,
+                            int32_t *sym_nchw, int32_t *index_nchw, const float *thresholds,
+                            int32_t n_thr, void *stream);
+/* One step of the 4-step checkerboard/channel-quarter prior (LSSVC_net.py:288-296, 338-443).
+ * params8: 8 chunks (4 scales | 4 means) of C/4 channels; step in 0..3 selects the mask pattern
+ * (quarter k is coded on checkerboard phase {0123, 3210, 2301, 1032}[step][k], phase = 2*(y&1) + (x&1)).
+ * Writes the step's positions of y_hat (y_hat_so_far), y_q, scales_hat; step 0 also zeroes the rest.
+ * bits accumulates the Laplace bits of the step's symbols.  sym/index (optional) receive the step's
+ * reduced C/4-channel tensors y_q_w_k / build_indexes(scales_w_k) in NCHW order (write=True branch). */
+int32_t lssvc_four_part_step(const lssvc_view *y, const lssvc_view *params8, int32_t step,
+                             const lssvc_view *y_hat, const lssvc_view *y_q, const lssvc_view *scales_hat,
+                             double *bits, int32_t *sym_nchw, int32_t *index_nchw,
+                             const float *thresholds, int32_t n_thr, void *stream);
+/* Decoder side (LSSVC_net_extend.py:200-263): CDF rows of the step's scales_r ... */
+int32_t lssvc_four_part_index(const lssvc_view *params8, int32_t step, int32_t *index_nchw,
+                              const float *thresholds, int32_t n_thr, void *stream);
+/* ... and y_hat_so_far += (decoded y_q_r + means) on the step's mask */
+int32_t lssvc_four_part_dec_step(const int32_t *sym_nchw, const lssvc_view *params8, int32_t step,
+                                 const lssvc_view *y_hat, void *stream);
+/* GaussianEncoder.build_indexes / GaussianConditional.build_indexes of a whole tensor, NCHW order */
+int32_t lssvc_scale_index(const lssvc_view *scale, int32_t *index_nchw, const float *thresholds,
+                          int32_t n_thr, void *stream);
+/* decoded int32 NCHW symbols -> NHWC fp32 view, optionally + add (means / medians): the
+ * `.to(device)` + `y_q + means_hat` of LSSVC_net_extend.py:108-123, dmc_net_extend.py:112-135 */
+int32_t lssvc_symbols_to_view(const int32_t *sym_nchw, const lssvc_view *add, const lssvc_view *out,
+                              void *stream);
+/* Gaussian-conditional branch of the I-frame models (img_entropy_models.py:650-685):
+ * y_hat = round(y - mean) + mean; lik = max(Phi(.5-|v|)/s - Phi(-.5-|v|)/s, 1e-9), s = max(scale, .11);
+ * bits += -log2(lik).  index uses GaussianConditional.build_indexes (:687-691). */
+int32_t lssvc_gaussian_quant(const lssvc_view *y, const lssvc_view *mean, const lssvc_view *scale,
+                             const lssvc_view *y_hat, double *bits, int32_t *sym_nchw,
+                             int32_t *index_nchw, const float *thresholds, int32_t n_thr, void *stream);
+/* Factorised prior of the P-frame models, BitEstimator (video_entropy_models.py:110-166):
+ * z_hat = round(z); p = F(z_hat + .5) - F(z_hat - .5); bits += clamp(-log2(p + 1e-5), 0, 50).
+ * coef is [C][11] = softplus(h1..4), b1..4, tanh(a1..3) per channel. */
+int32_t lssvc_bitparm_quant(const lssvc_view *z, const float *coef, const lssvc_view *z_hat,
+                            double *bits, int32_t *sym_nchw, void *stream);
+/* Factorised prior of the I-frame models, EntropyBottleneck (img_entropy_models.py:483-554):
+ * z_hat = round(z - med) + med, likelihood through the 1-3-3-3-3-1 logistic MLP.
+ * coef is [C][59]: softplus(matrices) 3,9,9,9,3 | biases 3,3,3,3,1 | tanh(factors) 3,3,3,3 | median. */
+int32_t lssvc_eb_quant(const lssvc_view *z, const float *coef, const lssvc_view *z_hat,
+                       double *bits, int32_t *sym_nchw, void *stream);
+/* sum of squared error between two views (PSNR statistics gathered over NCCL) */
+int32_t lssvc_sse(const lssvc_view *a, const lssvc_view *b, double *out, void *stream);
+
+/* ---- rANS entropy coder (host code; src/cpp/rans/rans_interface.cpp, src/cpp/ops/ops.cpp) --- */
+typedef struct lssvc_rans_encoder lssvc_rans_encoder;
+typedef struct lssvc_rans_decoder lssvc_rans_decoder;
+
+/* MLCodec_CXX.pmf_to_quantized_cdf (ops.cpp:24-82): cdf_out has n + 1 entries. host pointers. */
+int32_t lssvc_pmf_to_quantized_cdf(const float *pmf, int32_t n, int32_t precision, uint32_t *cdf_out);
+
+/* BufferedRansEncoder (rans_interface.cpp:85-172). All pointers are host pointers;
+ * cdfs is row-major [n_rows][cdf_stride]. */
+lssvc_rans_encoder *lssvc_rans_encoder_new(void);
+void lssvc_rans_encoder_free(lssvc_rans_encoder *e);
+void lssvc_rans_encoder_reset(lssvc_rans_encoder *e);
+int32_t lssvc_rans_encode_with_indexes(lssvc_rans_encoder *e, const int32_t *symbols,
+                                       const int32_t *indexes, int64_t n, const int32_t *cdfs,
+                                       int32_t cdf_stride, const int32_t *cdf_sizes,
+                                       const int32_t *offsets);
+/* Finishes the stream; returns its size in bytes and a pointer valid until the next
+ * reset/flush/free.  Clears the symbol buffer like the reference's flush(). */
+int64_t lssvc_rans_encoder_flush(lssvc_rans_encoder *e, const uint8_t **data);
+
+/* RansDecoder (rans_interface.cpp:176-244) */
+lssvc_rans_decoder *lssvc_rans_decoder_new(void);
+void lssvc_rans_decoder_free(lssvc_rans_decoder *d);
+int32_t lssvc_rans_decoder_set_stream(lssvc_rans_decoder *d, const uint8_t *data, int64_t nbytes);
+int32_t lssvc_rans_decode_stream(lssvc_rans_decoder *d, const int32_t *indexes, int64_t n,
+                                 const int32_t *cdfs, int32_t cdf_stride, const int32_t *cdf_sizes,
+                                 const int32_t *offsets, int32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSSVC_B200_H */

@@ -1,0 +1,458 @@
+// Memory-bound image-space kernels: layout conversion, flow warping, bilinear resampling, pooling,
+// the SpyNet level prologue and the OffsetDiversity tail.  All operate on NHWC fp32 views and are
+// written for coalesced, 128-bit accesses along the channel axis.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+inline int blocks_for(long long total) { return static_cast<int>((total + TPB - 1) / TPB); }
+
+// ---- layout ------------------------------------------------------------------------------
+// src [C][H][W] -> dst NHWC (pitch), zero fill channels C..Cv-1. Tile transpose through smem so both
+// sides are coalesced: block = 32 pixels x all channels.
+__global__ void nchw_to_nhwc_kernel(const float *__restrict__ src, int C, float *__restrict__ dst, int Cv, int pitch,
+                                    long long HW) {
+  extern __shared__ float tile[];  // [Cv][33]
+  const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+  for (int i = threadIdx.x; i < Cv * 32; i += blockDim.x) {
+    const int c = i / 32, px = i % 32;
+    const long long pp = p0 + px;
+    tile[c * 33 + px] = (c < C && pp < HW) ? src[static_cast<long long>(c) * HW + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cv * 32; i += blockDim.x) {
+    const int px = i / Cv, c = i % Cv;
+    const long long pp = p0 + px;
+    if (pp < HW) dst[pp * pitch + c] = tile[c * 33 + px];
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float *__restrict__ src, int C, int pitch, float *__restrict__ dst,
+                                    long long HW) {
+  extern __shared__ float tile[];  // [C][33]
+  const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+  for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
+    const int px = i / C, c = i % C;
+    const long long pp = p0 + px;
+    tile[c * 33 + px] = pp < HW ? src[pp * pitch + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
+    const int c = i / 32, px = i % 32;
+    const long long pp = p0 + px;
+    if (pp < HW) dst[static_cast<long long>(c) * HW + pp] = tile[c * 33 + px];
+  }
+}
+
+__global__ void lrelu_copy_kernel(const float *__restrict__ in, int in_pitch, float slope, float *__restrict__ out,
+                                  int out_pitch, int C, long long pixels) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= pixels * C) return;
+  const long long pix = idx / C;
+  const int c = static_cast<int>(idx - pix * C);
+  out[pix * out_pitch + c] = lrelu(in[pix * in_pitch + c], slope);
+}
+
+__global__ void softmax2_blend_kernel(const float *__restrict__ logits, int l_pitch, const float *__restrict__ a,
+                                      int a_pitch, const float *__restrict__ b, int b_pitch, float *__restrict__ out,
+                                      int o_pitch, int C, long long pixels) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= pixels * C) return;
+  const long long pix = idx / C;
+  const int c = static_cast<int>(idx - pix * C);
+  // softmax over two logits, computed the way torch does (subtract the max, exp, normalise)
+  const float l0 = logits[pix * l_pitch], l1 = logits[pix * l_pitch + 1];
+  const float mx = fmaxf(l0, l1);
+  const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+  const float inv = 1.f / (e0 + e1);
+  out[pix * o_pitch + c] = a[pix * a_pitch + c] * (e0 * inv) + b[pix * b_pitch + c] * (e1 * inv);
+}
+
+// ---- warping -----------------------------------------------------------------------------
+// grid_sample(bilinear, border, align_corners=True) on grid = base + flow / ((W-1)/2): the sample
+// position in pixels is x + fx (up to the fp32 normalise/denormalise round trip the reference does,
+// reproduced here so that results track the reference to the last bits that matter).
+__device__ __forceinline__ float linspace_pm1(int i, int n) {
+  // torch.linspace(-1, 1, n)[i]: symmetric evaluation from both ends
+  const float step = 2.f / static_cast<float>(n - 1);
+  return (i < n / 2) ? (-1.f + step * static_cast<float>(i)) : (1.f - step * static_cast<float>(n - 1 - i));
+}
+
+__device__ __forceinline__ void warp_coords(int x, int y, float fx, float fy, int W, int H, int &x0, int &x1, int &y0,
+                                            int &y1, float &wx, float &wy) {
+  // reference: g = linspace(-1,1,W)[x] + fx / ((W-1)/2); ATen: ix = ((g + 1) / 2) * (W - 1), clipped to [0, W-1]
+  const float sx = (W > 1) ? linspace_pm1(x, W) : -1.f;
+  const float sy = (H > 1) ? linspace_pm1(y, H) : -1.f;
+  const float gx = sx + fx / ((static_cast<float>(W) - 1.f) / 2.f);
+  const float gy = sy + fy / ((static_cast<float>(H) - 1.f) / 2.f);
+  float ix = ((gx + 1.f) / 2.f) * static_cast<float>(W - 1);
+  float iy = ((gy + 1.f) / 2.f) * static_cast<float>(H - 1);
+  ix = fminf(fmaxf(ix, 0.f), static_cast<float>(W - 1));
+  iy = fminf(fmaxf(iy, 0.f), static_cast<float>(H - 1));
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  x0 = static_cast<int>(fx0);
+  y0 = static_cast<int>(fy0);
+  x1 = min(x0 + 1, W - 1);
+  y1 = min(y0 + 1, H - 1);
+  wx = ix - fx0;
+  wy = iy - fy0;
+}
+
+__device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v11, float wx, float wy) {
+  // ATen grid_sampler_2d corner weights: nw = (x_se - ix)(y_se - iy), ne = (ix - x_sw)(y_sw - iy), ...
+  const float ex = 1.f - wx, ey = 1.f - wy;
+  return v00 * (ex * ey) + v01 * (wx * ey) + v10 * (ex * wy) + v11 * (wx * wy);
+}
+
+template <int VEC>
+__global__ void flow_warp_kernel(const float *__restrict__ src, int s_pitch, const float *__restrict__ flow,
+                                 int f_pitch, float fscale, float *__restrict__ out, int o_pitch, int H, int W, int C) {
+  const int cv = C / VEC;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(H) * W * cv) return;
+  const int c = static_cast<int>(idx % cv) * VEC;
+  const long long pix = idx / cv;
+  const int x = static_cast<int>(pix % W), y = static_cast<int>(pix / W);
+  const float fx = flow[pix * f_pitch] * fscale, fy = flow[pix * f_pitch + 1] * fscale;
+  int x0, x1, y0, y1;
+  float wx, wy;
+  warp_coords(x, y, fx, fy, W, H, x0, x1, y0, y1, wx, wy);
+  const float *p00 = src + (static_cast<long long>(y0) * W + x0) * s_pitch + c;
+  const float *p01 = src + (static_cast<long long>(y0) * W + x1) * s_pitch + c;
+  const float *p10 = src + (static_cast<long long>(y1) * W + x0) * s_pitch + c;
+  const float *p11 = src + (static_cast<long long>(y1) * W + x1) * s_pitch + c;
+  float *o = out + pix * o_pitch + c;
+  if (VEC == 4) {
+    const float4 a = *reinterpret_cast<const float4 *>(p00), b = *reinterpret_cast<const float4 *>(p01);
+    const float4 d = *reinterpret_cast<const float4 *>(p10), e = *reinterpret_cast<const float4 *>(p11);
+    *reinterpret_cast<float4 *>(o) = make_float4(bilerp(a.x, b.x, d.x, e.x, wx, wy), bilerp(a.y, b.y, d.y, e.y, wx, wy),
+                                                 bilerp(a.z, b.z, d.z, e.z, wx, wy), bilerp(a.w, b.w, d.w, e.w, wx, wy));
+  } else {
+    o[0] = bilerp(p00[0], p01[0], p10[0], p11[0], wx, wy);
+  }
+}
+
+// ---- bilinear resize, align_corners=False -----------------------------------------------------
+__device__ __forceinline__ void resize_coord(int d, float scale, int in_size, int &i0, int &i1, float &w1) {
+  // ATen area_pixel_compute_source_index(align_corners=False): max((d + .5) * scale - .5, 0)
+  float s = (static_cast<float>(d) + 0.5f) * scale - 0.5f;
+  s = s < 0.f ? 0.f : s;
+  i0 = static_cast<int>(s);
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  w1 = s - static_cast<float>(i0);
+}
+
+template <int VEC>
+__global__ void bilinear_resize_kernel(const float *__restrict__ in, int i_pitch, int Hi, int Wi,
+                                       float *__restrict__ out, int o_pitch, int Ho, int Wo, int C, float rh, float rw,
+                                       float mul) {
+  const int cv = C / VEC;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(Ho) * Wo * cv) return;
+  const int c = static_cast<int>(idx % cv) * VEC;
+  const long long pix = idx / cv;
+  const int x = static_cast<int>(pix % Wo), y = static_cast<int>(pix / Wo);
+  int x0, x1, y0, y1;
+  float wx, wy;
+  resize_coord(x, rw, Wi, x0, x1, wx);
+  resize_coord(y, rh, Hi, y0, y1, wy);
+  const float hx = 1.f - wx, hy = 1.f - wy;
+  const float *p00 = in + (static_cast<long long>(y0) * Wi + x0) * i_pitch + c;
+  const float *p01 = in + (static_cast<long long>(y0) * Wi + x1) * i_pitch + c;
+  const float *p10 = in + (static_cast<long long>(y1) * Wi + x0) * i_pitch + c;
+  const float *p11 = in + (static_cast<long long>(y1) * Wi + x1) * i_pitch + c;
+  float *o = out + pix * o_pitch + c;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    // ATen upsample_bilinear2d: h0l * (w0l * v00 + w1l * v01) + h1l * (w0l * v10 + w1l * v11)
+    const float v = hy * (hx * p00[e] + wx * p01[e]) + wy * (hx * p10[e] + wx * p11[e]);
+    o[e] = v * mul;
+  }
+}
+
+template <bool MAX>
+__global__ void pool2_kernel(const float *__restrict__ in, int i_pitch, int Wi, float *__restrict__ out, int o_pitch,
+                             int Ho, int Wo, int C) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(Ho) * Wo * C) return;
+  const int c = static_cast<int>(idx % C);
+  const long long pix = idx / C;
+  const int x = static_cast<int>(pix % Wo), y = static_cast<int>(pix / Wo);
+  const float *p = in + (static_cast<long long>(2 * y) * Wi + 2 * x) * i_pitch + c;
+  const float a = p[0], b = p[i_pitch], d = p[static_cast<long long>(Wi) * i_pitch],
+              e = p[static_cast<long long>(Wi) * i_pitch + i_pitch];
+  out[pix * o_pitch + c] = MAX ? fmaxf(fmaxf(a, b), fmaxf(d, e)) : (a + b + d + e) * 0.25f;
+}
+
+// ---- SpyNet level prologue --------------------------------------------------------------------
+__global__ void spynet_prep_kernel(const float *__restrict__ im1, int p1, const float *__restrict__ im2, int p2,
+                                   const float *__restrict__ fc, int pc, float *__restrict__ out8, int p8,
+                                   float *__restrict__ fup, int pf, int H, int W) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= static_cast<long long>(H) * W) return;
+  const int x = static_cast<int>(pix % W), y = static_cast<int>(pix / W);
+  float fx = 0.f, fy = 0.f;
+  if (fc) {
+    const int Hc = H / 2, Wc = W / 2;
+    int x0, x1, y0, y1;
+    float wx, wy;
+    resize_coord(x, 0.5f, Wc, x0, x1, wx);
+    resize_coord(y, 0.5f, Hc, y0, y1, wy);
+    const float hx = 1.f - wx, hy = 1.f - wy;
+    const float *q00 = fc + (static_cast<long long>(y0) * Wc + x0) * pc, *q01 = fc + (static_cast<long long>(y0) * Wc + x1) * pc;
+    const float *q10 = fc + (static_cast<long long>(y1) * Wc + x0) * pc, *q11 = fc + (static_cast<long long>(y1) * Wc + x1) * pc;
+    fx = (hy * (hx * q00[0] + wx * q01[0]) + wy * (hx * q10[0] + wx * q11[0])) * 2.0f;
+    fy = (hy * (hx * q00[1] + wx * q01[1]) + wy * (hx * q10[1] + wx * q11[1])) * 2.0f;
+  }
+  int x0, x1, y0, y1;
+  float wx, wy;
+  warp_coords(x, y, fx, fy, W, H, x0, x1, y0, y1, wx, wy);
+  const float *a = im2 + (static_cast<long long>(y0) * W + x0) * p2, *b = im2 + (static_cast<long long>(y0) * W + x1) * p2;
+  const float *d = im2 + (static_cast<long long>(y1) * W + x0) * p2, *e = im2 + (static_cast<long long>(y1) * W + x1) * p2;
+  const float *i1 = im1 + pix * p1;
+  float *o = out8 + pix * p8;
+  const float4 lo = make_float4(i1[0], i1[1], i1[2], bilerp(a[0], b[0], d[0], e[0], wx, wy));
+  const float4 hi = make_float4(bilerp(a[1], b[1], d[1], e[1], wx, wy), bilerp(a[2], b[2], d[2], e[2], wx, wy), fx, fy);
+  *reinterpret_cast<float4 *>(o) = lo;
+  *reinterpret_cast<float4 *>(o + 4) = hi;
+  fup[pix * pf] = fx;
+  fup[pix * pf + 1] = fy;
+}
+
+// ---- OffsetDiversity tail ----------------------------------------------------------------------
+// One thread per (pixel, group).  cg = C / groups channels per group; `off` holds, at half resolution,
+// [G*O offsets-x/y interleaved as the reference's (o1 | o2) chunks][G*O masks].
+// Reference layout (lssvc_modules.py:96-109): offset = cat(o1, o2) viewed as (G*O, 2): warp n uses
+// channels (2n, 2n+1) of the 2*G*O-channel tensor; mask n is channel n of the mask chunk; warp n acts on
+// x-group (n mod G) ("x.repeat(offset_num)") and its output lands in channels n*cg .. n*cg+cg-1 of the
+// (C*O)-channel tensor, which the grouped 1x1 fusion conv (groups=G, 2*cg inputs per group) consumes.
+template <int CG, int O>
+__global__ void offset_diversity_kernel(const float *__restrict__ xin, int xp, const float *__restrict__ off, int op,
+                                        const float *__restrict__ flow, int fp, const float *__restrict__ fw,
+                                        const float *__restrict__ fb, int G, float mag, float *__restrict__ out,
+                                        int outp, int H, int W) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(H) * W * G) return;
+  const int g = static_cast<int>(idx % G);
+  const long long pix = idx / G;
+  const int x = static_cast<int>(pix % W), y = static_cast<int>(pix / W);
+  const int Hc = H / 2, Wc = W / 2;
+  const int n_off = G * O;
+  int bx0, bx1, by0, by1;
+  float bwx, bwy;
+  resize_coord(x, 0.5f, Wc, bx0, bx1, bwx);
+  resize_coord(y, 0.5f, Hc, by0, by1, bwy);
+  const float hx = 1.f - bwx, hy = 1.f - bwy;
+  const float *q00 = off + (static_cast<long long>(by0) * Wc + bx0) * op, *q01 = off + (static_cast<long long>(by0) * Wc + bx1) * op;
+  const float *q10 = off + (static_cast<long long>(by1) * Wc + bx0) * op, *q11 = off + (static_cast<long long>(by1) * Wc + bx1) * op;
+  auto up = [&](int ch) { return hy * (hx * q00[ch] + bwx * q01[ch]) + bwy * (hx * q10[ch] + bwx * q11[ch]); };
+  const float flx = flow[pix * fp], fly = flow[pix * fp + 1];
+
+  // fusion group g consumes channels [g*2cg, (g+1)*2cg) of the warped tensor, i.e. warps
+  // n = (g*2cg + j) / cg for j in [0, 2cg): n = 2g and 2g + 1 when O == 2.
+  float acc[CG];
+#pragma unroll
+  for (int k = 0; k < CG; ++k) acc[k] = fb[g * CG + k];
+#pragma unroll
+  for (int t = 0; t < O; ++t) {
+    const int n = g * O + t;          // warp index in the (C*O)-channel tensor
+    const int xg = n % G;             // which x group it warps (x.repeat(offset_num, ...))
+    const float ox = mag * tanhf(up(2 * n)) + flx;
+    const float oy = mag * tanhf(up(2 * n + 1)) + fly;
+    const float mk = 1.f / (1.f + expf(-up(2 * n_off + n)));
+    int x0, x1, y0, y1;
+    float wx, wy;
+    warp_coords(x, y, ox, oy, W, H, x0, x1, y0, y1, wx, wy);
+    const float *a = xin + (static_cast<long long>(y0) * W + x0) * xp + xg * CG;
+    const float *b = xin + (static_cast<long long>(y0) * W + x1) * xp + xg * CG;
+    const float *d = xin + (static_cast<long long>(y1) * W + x0) * xp + xg * CG;
+    const float *e = xin + (static_cast<long long>(y1) * W + x1) * xp + xg * CG;
+#pragma unroll
+    for (int j = 0; j < CG; ++j) {
+      const float v = bilerp(a[j], b[j], d[j], e[j], wx, wy) * mk;
+#pragma unroll
+      for (int k = 0; k < CG; ++k) acc[k] = fmaf(fw[(g * CG + k) * (O * CG) + t * CG + j], v, acc[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < CG; ++k) out[pix * outp + g * CG + k] = acc[k];
+}
+
+__global__ void sse_kernel(const float *__restrict__ a, int ap, const float *__restrict__ b, int bp, int C,
+                           long long pixels, double *__restrict__ out) {
+  double local = 0.0;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < pixels * C;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = idx / C;
+    const int c = static_cast<int>(idx - pix * C);
+    const float d = a[pix * ap + c] - b[pix * bp + c];
+    local += static_cast<double>(d) * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  __shared__ double warp_sums[TPB / 32];
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < TPB / 32; ++i) s += warp_sums[i];
+    atomicAdd(out, s);
+  }
+}
+
+bool aligned4(const lssvc_view *v) { return v->C % 4 == 0 && v->pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0; }
+
+}  // namespace
+
+extern "C" int32_t lssvc_nchw_to_nhwc(const float *src, int32_t C, const lssvc_view *out, void *stream) {
+  LSSVC_REQUIRE(src && lssvc::view_ok(out) && C >= 1 && C <= out->C, "nchw_to_nhwc: bad arguments");
+  LSSVC_REQUIRE(out->C <= 1024, "nchw_to_nhwc: too many channels");
+  const long long HW = static_cast<long long>(out->H) * out->W;
+  const int blocks = static_cast<int>((HW + 31) / 32);
+  nchw_to_nhwc_kernel<<<blocks, TPB, out->C * 33 * sizeof(float), lssvc::as_stream(stream)>>>(src, C, out->ptr, out->C,
+                                                                                               out->pitch, HW);
+  LSSVC_LAUNCHED();
+  return LSSVC_OK;
+}
+
+extern "C" int32_t lssvc_nhwc_to_nchw(const lssvc_view *in, float *dst, void *stream) {
+  LSSVC_REQUIRE(dst && lssvc::view_ok(in), "nhwc_to_nchw: bad arguments");
+  LSSVC_REQUIRE(in->C <= 1024, "nhwc_to_nchw: too many channels");
+  const long long HW = static_cast<long long>(in->H) * in->W;
+  const int blocks = static_cast<int>((HW + 31) / 32);
+  nhwc_to_nchw_kernel<<<blocks, TPB, in->C * 33 * sizeof(float), lssvc::as_stream(stream)>>>(in->ptr, in->C, in->pitch,
+                                                                                              dst, HW);
+  LSSVC_LAUNCHED();
+  return LSSVC_OK;
+}
+
+extern "C" int32_t lssvc_lrelu_copy(const lssvc_view *in, float slope, const lssvc_view *out, void *stream) {
+  LSSVC_REQUIRE(lssvc::view_ok(in) && lssvc::view_ok(out), "lrelu_copy: bad view");
+  LSSVC_REQUIRE(in->H == out->H && in->W == out->W && in->C == out->C, "lrelu_copy: shape mismatch");
+  const long long pixels = static_cast<long long>(in->H) * in->W;
+  lrelu_copy_kernel<<<blocks_for(pixels * in->C), TPB, 0, lssvc::as_stream(stream)>>>(in->ptr, in->pitch, slope, out->ptr,
+                                                                                       out->pitch, in->C, pixels);
+  LSSVC_LAUNCHED();
+  return LSSVC_OK;
+}
+
+extern "C" int32_t lssvc_softmax2_blend(const lssvc_view *logits, const lssvc_view *a, const lssvc_view *b,
+                                        const lssvc_view *out, void *stream) {
+  LSSVC_REQUIRE(lssvc::view_ok(logits) && lssvc::view_ok(a) && lssvc::view_ok(b) && lssvc::view_ok(out),
+                "softmax2_blend: bad view");
+  LSSVC_REQUIRE(logits->C == 2 && a->C == b->C && a->C == out->C, "softmax2_blend: channel mismatch");
+  LSSVC_REQUIRE(a->H == out->H && b->H == out->H && logits->H == out->H && a->W == out->W && b->W == out->W &&
+                    logits->W == out->W,
+                "softmax2_blend: size mismatch");
+  const long long pixels = static_cast<long long>(out->H) * out->W;
+  softmax2_blend_kernel<<<blocks_for(pixels * out->C), TPB, 0, lssvc::as_stream(stream)>>>(
+      logits->ptr, logits->pitch, a->ptr, a->pitch, b->ptr, b->pitch, out->ptr, out->pitch, out->C, pixels);
+  LSSVC_LAUNCHED();
+  return LSSVC_OK;
+}
+
+extern "C" int32_t lssvc_flow_warp(const lssvc_view *src, const lssvc_view *flow, float flow_scale,
+                                   const lssvc_view *out, void *stream) {
+  LSSVC_REQUIRE(lssvc::view_ok(src) && lssvc::view_ok(flow) && lssvc::view_ok(out), "flow_warp: bad view");
+  LSSVC_REQUIRE(flow->C >= 2 && src->H == out->H && src->W == out->W && flow->H == out->H && flow->W == out->W &&
+                    src->C == out->C,
+                "flow_warp: shape mismatch");
+  const long long pixels = static_cast<long long>(out->H) * out->W;
+  cudaStream_t s = lssvc::as_stream(stream);
+  if (aligned4(src) && aligned4(out)) {
+    flow_warp_kernel<4><<<blocks_for(pixels * (src->C / 4)), TPB, 0, s>>>(src->ptr, src->pitch, flow->ptr, flow->pitch,
+                                                                         flow_scale, out->ptr, out->pitch, out->H, out->W,
+                                                                         src->C);
+  } else {
+    flow_warp_kernel<1><<<blocks_for(pixels * src->C), TPB, 0, s>>>(src->ptr, src->pitch, flow->ptr, flow->pitch,
+                                                                   flow_scale, out->ptr, out->pitch, out->H, out->W, src->C);
+  }
+  LSSVC_LAUNCHED();
+  return LSSVC_OK;
+}
+
+extern "C" int32_t lssvc_bilinear_resize(const lssvc_view *in, float scale, const lssvc_view *out, void *stream) {
+  LSSVC_REQUIRE(lssvc::view_ok(in) && lssvc::view_ok(out) && in->C == out->C, "bilinear_resize: bad view");
+  const float rh = static_cast<float>(in->H) / static_cast<float>(out->H);
+  const float rw = static_cast<float>(in->W) / static_cast<float>(out->W);
+  const long long pixels = static_cast<long long>(out->H) * out->W;
+  cudaStream_t s = lssvc::as_stream(stream);
+  if (aligned4(in) && aligned4(out)) {
+    bilinear_resize_kernel<4><<<blocks_for(pixels * (in->C / 4)), TPB, 0, s>>>(in->ptr, in->pitch, in->H, in->W, out->ptr,
+                                                                              out->pitch, out->H, out->W, in->C, rh, rw, scale);
+  } else {
+    bilinear_resize_kernel<1><<<blocks_for(pixels * in->C), TPB, 0, s>>>(in->ptr, in->pitch, in->H, in->W, out->ptr,
+                                                                        out->pitch, out->H, out->W, in->C, rh, rw, scale);
+  }
+  LSSVC_LAUNCHED();
+  return LSSVC_OK;
+}
+
+static int32_t pool2(const lssvc_view *in, const lssvc_view *out, void *stream, bool is_max) {
+  LSSVC_REQUIRE(lssvc::view_ok(in) && lssvc::view_ok(out) && in->C == out->C, "pool2: bad view");
+  LSSVC_REQUIRE(out->H == in->H / 2 && out->W == in->W / 2, "pool2: output must be half the input");
+  const long long total = static_cast<long long>(out->H) * out->W * out->C;
+  cudaStream_t s = lssvc::as_stream(stream);
+  if (is_max) pool2_kernel<true><<<blocks_for(total), TPB, 0, s>>>(in->ptr, in->pitch, in->W, out->ptr, out->pitch, out->H, out->W, out->C);
+  else pool2_kernel<false><<<blocks_for(total), TPB, 0, s>>>(in->ptr, in->pitch, in->W, out->ptr, out->pitch, out->H, out->W, out->C);
+  LSSVC_LAUNCHED();
+  return LSSVC_OK;
+}
+extern "C" int32_t lssvc_avgpool2(const lssvc_view *in, const lssvc_view *out, void *stream) { return pool2(in, out, stream, false); }
+extern "C" int32_t lssvc_maxpool2(const lssvc_view *in, const lssvc_view *out, void *stream) { return pool2(in, out, stream, true); }
+
+extern "C" int32_t lssvc_spynet_prep(const lssvc_view *im1, const lssvc_view *im2, const lssvc_view *flow_coarse,
+                                     const lssvc_view *out8, const lssvc_view *flow_up, void *stream) {
+  LSSVC_REQUIRE(lssvc::view_ok(im1) && lssvc::view_ok(im2) && lssvc::view_ok(out8) && lssvc::view_ok(flow_up),
+                "spynet_prep: bad view");
+  LSSVC_REQUIRE(im1->C >= 3 && im2->C >= 3 && out8->C == 8 && flow_up->C >= 2, "spynet_prep: channel counts");
+  LSSVC_REQUIRE(out8->pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(out8->ptr) & 15) == 0, "spynet_prep: out8 alignment");
+  const int H = im1->H, W = im1->W;
+  LSSVC_REQUIRE(im2->H == H && im2->W == W && out8->H == H && out8->W == W && flow_up->H == H && flow_up->W == W,
+                "spynet_prep: size mismatch");
+  const float *fc = nullptr;
+  int pc = 0;
+  if (lssvc::view_present(flow_coarse)) {
+    LSSVC_REQUIRE(flow_coarse->H * 2 == H && flow_coarse->W * 2 == W && flow_coarse->C >= 2, "spynet_prep: coarse flow size");
+    fc = flow_coarse->ptr;
+    pc = flow_coarse->pitch;
+  }
+  spynet_prep_kernel<<<blocks_for(static_cast<long long>(H) * W), TPB, 0, lssvc::as_stream(stream)>>>(
+      im1->ptr, im1->pitch, im2->ptr, im2->pitch, fc, pc, out8->ptr, out8->pitch, flow_up->ptr, flow_up->pitch, H, W);
+  LSSVC_LAUNCHED();
+  return LSSVC_OK;
+}
+
+extern "C" int32_t lssvc_offset_diversity(const lssvc_view *x, const lssvc_view *off, const lssvc_view *flow,
+                                          const float *fusion_w, const float *fusion_b, int32_t groups,
+                                          int32_t offset_num, float magnitude, const lssvc_view *out, void *stream) {
+  LSSVC_REQUIRE(lssvc::view_ok(x) && lssvc::view_ok(off) && lssvc::view_ok(flow) && lssvc::view_ok(out),
+                "offset_diversity: bad view");
+  LSSVC_REQUIRE(groups > 0 && x->C % groups == 0 && x->C / groups == 3 && offset_num == 2,
+                "offset_diversity: only 3 channels per group and 2 offsets are built (C=%d G=%d O=%d)", x->C, groups,
+                offset_num);
+  LSSVC_REQUIRE(off->C == 3 * groups * offset_num && off->H * 2 == x->H && off->W * 2 == x->W,
+                "offset_diversity: offset tensor shape");
+  LSSVC_REQUIRE(flow->C >= 2 && flow->H == x->H && flow->W == x->W && out->H == x->H && out->W == x->W && out->C == x->C,
+                "offset_diversity: size mismatch");
+  const long long total = static_cast<long long>(x->H) * x->W * groups;
+  offset_diversity_kernel<3, 2><<<blocks_for(total), TPB, 0, lssvc::as_stream(stream)>>>(
+      x->ptr, x->pitch, off->ptr, off->pitch, flow->ptr, flow->pitch, fusion_w, fusion_b, groups, magnitude, out->ptr,
+      out->pitch, x->H, x->W);
+  LSSVC_LAUNCHED();
+  return LSSVC_OK;
+}
+
+extern "C" int32_t lssvc_sse(const lssvc_view *a, const lssvc_view *b, double *out, void *stream) {
+  LSSVC_REQUIRE(lssvc::view_ok(a) && lssvc::view_ok(b) && out, "sse: bad arguments");
+  LSSVC_REQUIRE(a->H == b->H && a->W == b->W && a->C == b->C, "sse: shape mismatch");
+  const long long pixels = static_cast<long long>(a->H) * a->W;
+  int blocks = blocks_for(pixels * a->C);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sse_kernel<<<blocks, TPB, 0, lssvc::as_stream(stream)>>>(a->ptr, a->pitch, b->ptr, b->pitch, a->C, pixels, out);
+  LSSVC_LAUNCHED();
+  return LSSVC_OK;
+}

@@ -1,0 +1,302 @@
+"""Host-side operator layer: NHWC views over torch-owned device memory and thin wrappers that hand raw
+pointers to the C-ABI kernels.  torch is used for allocation and stream handles only."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import CConv, CView, byref
+
+_NULL_VIEW = CView(None, 0, 0, 0, 0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class View:
+    """A window of C channels of an NHWC fp32 buffer with `pitch` floats per pixel."""
+
+    __slots__ = ("buf", "H", "W", "C", "pitch", "coff")
+
+    def __init__(self, buf, H, W, C, pitch, coff=0):
+        self.buf, self.H, self.W, self.C, self.pitch, self.coff = buf, H, W, C, pitch, coff
+
+    @staticmethod
+    def alloc(H, W, C, device, pitch=None, zero=False):
+        pitch = pitch or round_up(C, 4)
+        fn = torch.zeros if zero else torch.empty
+        return View(fn(H * W * pitch, dtype=torch.float32, device=device), H, W, C, pitch)
+
+    def slice(self, c0, c1):
+        assert 0 <= c0 < c1 <= self.C, (c0, c1, self.C)
+        return View(self.buf, self.H, self.W, c1 - c0, self.pitch, self.coff + c0)
+
+    def widen(self, C):
+        """Same window start, C channels wide (to expose zeroed pad channels to a conv)."""
+        assert self.coff + C <= self.pitch
+        return View(self.buf, self.H, self.W, C, self.pitch, self.coff)
+
+    @property
+    def device(self):
+        return self.buf.device
+
+    def c(self):
+        return CView(self.buf.data_ptr() + 4 * self.coff, self.H, self.W, self.C, self.pitch)
+
+    def as_tensor(self):
+        """[H, W, C] strided torch view (tests / debugging)."""
+        return self.buf.view(self.H, self.W, self.pitch)[:, :, self.coff:self.coff + self.C]
+
+    def to_nchw(self):
+        out = torch.empty(1, self.C, self.H, self.W, dtype=torch.float32, device=self.device)
+        lib = _lib.load()
+        _lib.check(lib.lssvc_nhwc_to_nchw(byref(self.c()), _ptr(out), _stream()), "nhwc_to_nchw")
+        return out
+
+    @staticmethod
+    def from_nchw(t, C_view=None, out=None):
+        """[1, C, H, W] (or [C, H, W]) contiguous fp32 -> NHWC view with C_view >= C channels (rest zero)."""
+        if t.dim() == 4:
+            assert t.shape[0] == 1, "batch 1 only"
+            t = t[0]
+        t = t.contiguous()
+        assert t.dtype == torch.float32 and t.is_cuda
+        C, H, W = t.shape
+        if out is None:
+            out = View.alloc(H, W, C_view or C, t.device)
+        lib = _lib.load()
+        _lib.check(lib.lssvc_nchw_to_nhwc(_ptr(t), C, byref(out.c()), _stream()), "nchw_to_nhwc")
+        return out
+
+
+def _cv(v):
+    return v.c() if v is not None else _NULL_VIEW
+
+
+class PackedConv:
+    """Weights of one Conv2d repacked for the kernels: [kh*kw][n_pad][cin_total] + bias[n_pad]."""
+
+    __slots__ = ("weight", "bias", "kh", "kw", "stride", "pad", "cout", "n_pad", "cin_total", "src_c", "pixel_shuffle")
+
+    def __init__(self, w, b, stride=1, pad=None, src_channels=None, pixel_shuffle=False, transposed=False, device=None):
+        """w: [Cout, Cin, kh, kw] (Conv2d) or, with transposed=True, a stride-1 ConvTranspose2d weight
+        [Cin, Cout, kh, kw] (turned into the equivalent flipped Conv2d).  src_channels: list of
+        (real, view) channel counts per source when sources are padded; default one unpadded source."""
+        w = w.detach().to(torch.float32).cpu()
+        if transposed:
+            w = w.permute(1, 0, 2, 3).flip(2, 3)
+        cout, cin, kh, kw = w.shape
+        b = torch.zeros(cout) if b is None else b.detach().to(torch.float32).cpu()
+        if src_channels is None:
+            src_channels = [(cin, cin)]
+        assert sum(r for r, _ in src_channels) == cin, (src_channels, cin)
+        if pixel_shuffle:
+            assert cout % 4 == 0
+            cq = cout // 4
+            # packed channel (2i+j)*cq + c  <-  reference channel 4c + 2i + j
+            perm = torch.tensor([4 * c + s for s in range(4) for c in range(cq)])
+            w, b = w[perm], b[perm]
+        n_pad = round_up(cout, 16)
+        cin_total = sum(v for _, v in src_channels)
+        packed = torch.zeros(kh * kw, n_pad, cin_total)
+        wt = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+        ci = co = 0
+        for real, view in src_channels:
+            packed[:, :cout, co:co + real] = wt[:, :, ci:ci + real]
+            ci += real
+            co += view
+        bias = torch.zeros(n_pad)
+        bias[:cout] = b
+        self.weight = packed.contiguous().to(device)
+        self.bias = bias.to(device)
+        self.kh, self.kw, self.stride = kh, kw, stride
+        self.pad = kh // 2 if pad is None else pad
+        self.cout, self.n_pad, self.cin_total = cout, n_pad, cin_total
+        self.src_c = [v for _, v in src_channels]
+        self.pixel_shuffle = pixel_shuffle
+
+
+_FORCE_SIMT = False
+
+
+def force_simt(flag):
+    """Route every convolution through the fp32 CUDA-core kernel (on-device cross-check of tcgen05)."""
+    global _FORCE_SIMT
+    _FORCE_SIMT = bool(flag)
+
+
+def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, out_scale=1.0,
+         in_transform=_lib.IN_NONE, in_slope=0.0, epi=_lib.EPI_PLAIN, gdn_x=None, engine=None):
+    """Run one packed convolution.  act: None or the LeakyReLU slope (0.0 = ReLU).
+    engine: None (auto), 'tc' or 'simt'."""
+    if isinstance(srcs, View):
+        srcs = [srcs]
+    assert len(srcs) == len(pc.src_c), (len(srcs), pc.src_c)
+    d = CConv()
+    d.n_src = len(srcs)
+    for i, s in enumerate(srcs):
+        assert s.C == pc.src_c[i], f"source {i} has {s.C} channels, packed for {pc.src_c[i]}"
+        d.src[i] = s.c()
+    d.weight, d.bias = pc.weight.data_ptr(), pc.bias.data_ptr()
+    d.kh, d.kw, d.stride, d.pad = pc.kh, pc.kw, pc.stride, pc.pad
+    d.cout, d.n_pad, d.cin_total = pc.cout, pc.n_pad, pc.cin_total
+    d.in_transform, d.in_slope, d.epi = in_transform, in_slope, epi
+    d.act = _lib.ACT_NONE if act is None else _lib.ACT_LRELU
+    d.slope = 0.0 if act is None else float(act)
+    d.out_scale = float(out_scale)
+    d.pixel_shuffle = 1 if pc.pixel_shuffle else 0
+    d.out = out.c()
+    d.res1, d.res2, d.out2, d.gdn_x = _cv(res1), _cv(res2), _cv(out2), _cv(gdn_x)
+    d.slope2 = float(slope2)
+    lib = _lib.load()
+    if engine is None:
+        tc_ok = (not _FORCE_SIMT and in_transform == _lib.IN_NONE and epi == _lib.EPI_PLAIN
+                 and all(s.C % 8 == 0 and s.pitch % 4 == 0 and (s.coff % 4 == 0) for s in srcs)
+                 and pc.stride in (1, 2))
+        engine = "tc" if tc_ok else "simt"
+    if engine == "tc":
+        _lib.check(lib.lssvc_conv_tc(byref(d), _stream()), "conv_tc")
+    else:
+        _lib.check(lib.lssvc_conv_simt(byref(d), _stream()), "conv_simt")
+    return out
+
+
+def dwconv3x3(x, weight9c, bias, out):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_dwconv3x3(byref(x.c()), _ptr(weight9c), _ptr(bias), byref(out.c()), _stream()), "dwconv3x3")
+    return out
+
+
+def deconv3x3_s2(x, weight, bias, out, act=None):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_deconv3x3_s2(byref(x.c()), _ptr(weight), _ptr(bias), 0 if act is None else 1,
+                                      0.0 if act is None else float(act), byref(out.c()), _stream()), "deconv3x3_s2")
+    return out
+
+
+def lrelu_copy(x, slope, out):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_lrelu_copy(byref(x.c()), float(slope), byref(out.c()), _stream()), "lrelu_copy")
+    return out
+
+
+def softmax2_blend(logits, a, b, out):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_softmax2_blend(byref(logits.c()), byref(a.c()), byref(b.c()), byref(out.c()), _stream()),
+               "softmax2_blend")
+    return out
+
+
+def flow_warp(src, flow, out, flow_scale=1.0):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_flow_warp(byref(src.c()), byref(flow.c()), float(flow_scale), byref(out.c()), _stream()),
+               "flow_warp")
+    return out
+
+
+def bilinear_resize(x, out, scale=1.0):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_bilinear_resize(byref(x.c()), float(scale), byref(out.c()), _stream()), "bilinear_resize")
+    return out
+
+
+def avgpool2(x, out):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_avgpool2(byref(x.c()), byref(out.c()), _stream()), "avgpool2")
+    return out
+
+
+def maxpool2(x, out):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_maxpool2(byref(x.c()), byref(out.c()), _stream()), "maxpool2")
+    return out
+
+
+def spynet_prep(im1, im2, flow_coarse, out8, flow_up):
+    lib = _lib.load()
+    fc = byref(flow_coarse.c()) if flow_coarse is not None else None
+    _lib.check(lib.lssvc_spynet_prep(byref(im1.c()), byref(im2.c()), fc, byref(out8.c()), byref(flow_up.c()), _stream()),
+               "spynet_prep")
+
+
+def offset_diversity(x, off, flow, fusion_w, fusion_b, groups, offset_num, magnitude, out):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_offset_diversity(byref(x.c()), byref(off.c()), byref(flow.c()), _ptr(fusion_w), _ptr(fusion_b),
+                                          groups, offset_num, float(magnitude), byref(out.c()), _stream()),
+               "offset_diversity")
+    return out
+
+
+def _opt(v):
+    return byref(v.c()) if v is not None else None
+
+
+def laplace_quant(y, mean, scale, y_q=None, y_hat=None, bits=None, sym=None, index=None, thresholds=None):
+    lib = _lib.load()
+    n_thr = 0 if thresholds is None else thresholds.numel()
+    _lib.check(lib.lssvc_laplace_quant(byref(y.c()), _opt(mean), byref(scale.c()), _opt(y_q), _opt(y_hat), _ptr(bits),
+                                       _ptr(sym), _ptr(index), _ptr(thresholds), n_thr, _stream()), "laplace_quant")
+
+
+def four_part_step(y, params8, step, y_hat, y_q=None, scales_hat=None, bits=None, sym=None, index=None, thresholds=None):
+    lib = _lib.load()
+    n_thr = 0 if thresholds is None else thresholds.numel()
+    _lib.check(lib.lssvc_four_part_step(byref(y.c()), byref(params8.c()), step, byref(y_hat.c()), _opt(y_q),
+                                        _opt(scales_hat), _ptr(bits), _ptr(sym), _ptr(index), _ptr(thresholds), n_thr,
+                                        _stream()), "four_part_step")
+
+
+def four_part_index(params8, step, index, thresholds):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_four_part_index(byref(params8.c()), step, _ptr(index), _ptr(thresholds), thresholds.numel(),
+                                         _stream()), "four_part_index")
+
+
+def four_part_dec_step(sym, params8, step, y_hat):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_four_part_dec_step(_ptr(sym), byref(params8.c()), step, byref(y_hat.c()), _stream()),
+               "four_part_dec_step")
+
+
+def scale_index(scale, index, thresholds):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_scale_index(byref(scale.c()), _ptr(index), _ptr(thresholds), thresholds.numel(), _stream()),
+               "scale_index")
+
+
+def symbols_to_view(sym, add, out):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_symbols_to_view(_ptr(sym), _opt(add), byref(out.c()), _stream()), "symbols_to_view")
+    return out
+
+
+def gaussian_quant(y, mean, scale, y_hat=None, bits=None, sym=None, index=None, thresholds=None):
+    lib = _lib.load()
+    n_thr = 0 if thresholds is None else thresholds.numel()
+    _lib.check(lib.lssvc_gaussian_quant(byref(y.c()), byref(mean.c()), byref(scale.c()), _opt(y_hat), _ptr(bits),
+                                        _ptr(sym), _ptr(index), _ptr(thresholds), n_thr, _stream()), "gaussian_quant")
+
+
+def bitparm_quant(z, coef, z_hat=None, bits=None, sym=None):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_bitparm_quant(byref(z.c()), _ptr(coef), _opt(z_hat), _ptr(bits), _ptr(sym), _stream()),
+               "bitparm_quant")
+
+
+def eb_quant(z, coef, z_hat=None, bits=None, sym=None):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_eb_quant(byref(z.c()), _ptr(coef), _opt(z_hat), _ptr(bits), _ptr(sym), _stream()), "eb_quant")
+
+
+def sse(a, b, out):
+    lib = _lib.load()
+    _lib.check(lib.lssvc_sse(byref(a.c()), byref(b.c()), _ptr(out), _stream()), "sse")

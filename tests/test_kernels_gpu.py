@@ -1,0 +1,410 @@
+"""Kernel-level parity: every CUDA kernel against the PyTorch op it replaces, on identical seeded inputs.
+Tolerances are stated per test: fp32 CUDA-core kernels 1e-5 relative to the output scale (summation order only),
+tcgen05 TF32 kernels 2e-3 relative to the output scale (10-bit operand mantissas, fp32 accumulation)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from lssvc_b200 import ops
+    return ops
+
+
+def rel_err(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def make_view(t_nchw, ops, C_view=None):
+    return ops.View.from_nchw(t_nchw, C_view=C_view)
+
+
+def ref_conv(xs, w, b, stride, pad, act=None, ps=False, res=None, out_scale=1.0):
+    x = torch.cat(xs, 1)
+    y = F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=pad)
+    if act is not None:
+        y = F.leaky_relu(y, act)
+    y = y * out_scale
+    if ps:
+        y = F.pixel_shuffle(y, 2)
+    if res is not None:
+        for r in res:
+            y = y + r.double()
+    return y.float()
+
+
+CONV_CASES = [
+    # (name, src channels(real), view channels, cout, k, stride, H, W, ps)
+    ("3x3_64_64", [64], [64], 64, 3, 1, 40, 56, False),
+    ("3x3_48_48_kc16", [48], [48], 48, 3, 1, 24, 40, False),
+    ("3x3_s2_64_96", [64], [64], 96, 3, 2, 48, 64, False),
+    ("7x7_8_32_kc8", [8], [8], 32, 7, 1, 24, 32, False),
+    ("7x7_16_2", [16], [16], 2, 7, 1, 16, 32, False),
+    ("1x1_64_256", [64], [64], 256, 1, 1, 16, 48, False),
+    ("1x1_288_1152_ntiles", [288], [288], 1152, 1, 1, 9, 15, False),
+    ("cat_64_64", [64, 64], [64, 64], 64, 3, 1, 18, 30, False),
+    ("cat_3_48_pad", [3, 48], [8, 48], 64, 3, 2, 32, 48, False),
+    ("ps_96_256", [96], [96], 256, 3, 1, 18, 30, True),
+    ("ps_64_12", [64], [64], 12, 3, 1, 16, 16, True),
+    ("odd_170_149", [170], [176], 149, 3, 1, 12, 20, False),
+    ("1x1_s2_down", [64], [64], 64, 1, 2, 32, 32, False),
+]
+
+
+def _run_conv_case(case, engine, device, with_extras):
+    ops = _ops()
+    name, creal, cview, cout, k, stride, H, W, ps = case
+    g = torch.Generator(device="cpu").manual_seed(hash(name) % 10000)
+    xs = [torch.randn(1, c, H, W, generator=g).to(device) for c in creal]
+    cin = sum(creal)
+    w = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(device)
+    b = torch.randn(cout, generator=g).to(device)
+    pad = k // 2 if k > 1 else 0
+    pc = ops.PackedConv(w, b, stride=stride, pad=pad, src_channels=list(zip(creal, cview)), pixel_shuffle=ps,
+                        device=device)
+    srcs = [make_view(x, ops, C_view=cv) for x, cv in zip(xs, cview)]
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    f = 2 if ps else 1
+    c_out = cout // 4 if ps else cout
+    out = ops.View.alloc(Ho * f, Wo * f, c_out, device, zero=True)
+    res = None
+    kw = {}
+    act = None
+    if with_extras:
+        act = 0.1
+        r1 = torch.randn(1, c_out, Ho * f, Wo * f, generator=g).to(device)
+        r2 = torch.randn(1, c_out, Ho * f, Wo * f, generator=g).to(device)
+        res = [r1, r2]
+        kw = dict(res1=make_view(r1, ops), res2=make_view(r2, ops), out2=ops.View.alloc(Ho * f, Wo * f, c_out, device),
+                  slope2=0.2, out_scale=1.5)
+    ops.conv(pc, srcs, out, act=act, engine=engine, **kw)
+    torch.cuda.synchronize()
+    ref = ref_conv(xs, w, b, stride, pad, act=act, ps=ps, res=res, out_scale=1.5 if with_extras else 1.0)
+    got = out.to_nchw()
+    err = rel_err(got, ref)
+    if with_extras:
+        got2 = kw["out2"].to_nchw()
+        err = max(err, rel_err(got2, F.leaky_relu(ref, 0.2)))
+    return err
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("extras", [False, True], ids=["plain", "epilogue"])
+def test_conv_simt(case, extras, cuda_device):
+    err = _run_conv_case(case, "simt", cuda_device, extras)
+    assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("extras", [False, True], ids=["plain", "epilogue"])
+def test_conv_tc(case, extras, cuda_device):
+    err = _run_conv_case(case, "tc", cuda_device, extras)
+    print(f"tcgen05 conv {case[0]} rel err {err:.3e}")
+    assert err < 2e-3, err
+
+
+def test_conv_tc_large_persistent(cuda_device):
+    """More tiles than SMs: exercises the persistent loop, TMEM double buffering and barrier phase wrap."""
+    err = _run_conv_case(("big", [64], [64], 64, 3, 1, 256, 320, False), "tc", cuda_device, True)
+    assert err < 2e-3, err
+    err = _run_conv_case(("big48", [48, 48], [48, 48], 48, 3, 1, 200, 312, False), "tc", cuda_device, False)
+    assert err < 2e-3, err
+
+
+def test_gdn_epilogue(cuda_device):
+    ops = _ops()
+    from lssvc_b200 import _lib
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    C, H, W = 64, 20, 28
+    x = torch.randn(1, C, H, W, generator=g).to(dev)
+    gamma = (torch.rand(C, C, generator=g) * 0.1).to(dev)
+    beta = (torch.rand(C, generator=g) + 0.5).to(dev)
+    res = torch.randn(1, C, H, W, generator=g).to(dev)
+    pc = ops.PackedConv(gamma.view(C, C, 1, 1), beta, pad=0, device=dev)
+    xv = make_view(x, ops)
+    for inverse in (False, True):
+        out = ops.View.alloc(H, W, C, dev)
+        ops.conv(pc, xv, out, in_transform=_lib.IN_SQUARE, epi=_lib.EPI_IGDN if inverse else _lib.EPI_GDN, gdn_x=xv,
+                 res1=make_view(res, ops), engine="simt")
+        norm = F.conv2d(x.double() ** 2, gamma.double().view(C, C, 1, 1), beta.double())
+        ref = (x.double() * (norm.sqrt() if inverse else norm.rsqrt()) + res.double()).float()
+        assert rel_err(out.to_nchw(), ref) < 1e-5
+
+
+def test_dwconv_and_deconv(cuda_device):
+    ops = _ops()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(4)
+    C, H, W = 48, 18, 30
+    x = torch.randn(1, C, H, W, generator=g).to(dev)
+    w = torch.randn(C, 1, 3, 3, generator=g).to(dev)
+    b = torch.randn(C, generator=g).to(dev)
+    out = ops.View.alloc(H, W, C, dev)
+    ops.dwconv3x3(make_view(x, ops), w.view(C, 9).t().contiguous(), b, out)
+    ref = F.conv2d(x, w, b, padding=1, groups=C)
+    assert rel_err(out.to_nchw(), ref) < 1e-5
+
+    cin, cout = 64, 96
+    x = torch.randn(1, cin, 9, 15, generator=g).to(dev)
+    w = (torch.randn(cin, cout, 3, 3, generator=g) / 10).to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    out = ops.View.alloc(18, 30, cout, dev)
+    wp = w.permute(2, 3, 0, 1).reshape(9, cin, cout).contiguous()
+    ops.deconv3x3_s2(make_view(x, ops), wp, b, out, act=0.01)
+    ref = F.leaky_relu(F.conv_transpose2d(x, w, b, stride=2, padding=1, output_padding=1), 0.01)
+    assert rel_err(out.to_nchw(), ref) < 1e-5
+
+    # stride-1 transposed conv through the regular conv path
+    w1 = (torch.randn(cin, cout, 3, 3, generator=g) / 10).to(dev)
+    pc = ops.PackedConv(w1, b, transposed=True, device=dev)
+    out = ops.View.alloc(9, 15, cout, dev)
+    ops.conv(pc, make_view(x, ops), out, engine="simt")
+    ref = F.conv_transpose2d(x, w1, b, stride=1, padding=1)
+    assert rel_err(out.to_nchw(), ref) < 1e-5
+
+
+def torch_warp_ref(feature, flow):
+    N, _, H, W = flow.shape
+    hor = torch.linspace(-1.0, 1.0, W, device=flow.device).view(1, 1, 1, W).expand(N, -1, H, -1)
+    ver = torch.linspace(-1.0, 1.0, H, device=flow.device).view(1, 1, H, 1).expand(N, -1, -1, W)
+    grid = torch.cat([hor, ver], 1)
+    fl = torch.cat([flow[:, 0:1] / ((W - 1.0) / 2.0), flow[:, 1:2] / ((H - 1.0) / 2.0)], 1)
+    return F.grid_sample(feature, (grid + fl).permute(0, 2, 3, 1), mode="bilinear", padding_mode="border",
+                         align_corners=True)
+
+
+def test_flow_warp_resize_pool(cuda_device):
+    ops = _ops()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    for C, H, W in [(48, 32, 48), (3, 24, 40), (64, 18, 30)]:
+        x = torch.rand(1, C, H, W, generator=g).to(dev)
+        flow = (torch.randn(1, 2, H, W, generator=g) * 6).to(dev)
+        out = ops.View.alloc(H, W, C, dev)
+        ops.flow_warp(make_view(x, ops), make_view(flow, ops), out)
+        ref = torch_warp_ref(x, flow)
+        assert (out.to_nchw() - ref).abs().max().item() < 2e-5
+    x = torch.randn(1, 64, 18, 30, generator=g).to(dev)
+    for (Ho, Wo) in [(36, 60), (27, 45), (9, 15)]:
+        out = ops.View.alloc(Ho, Wo, 64, dev)
+        ops.bilinear_resize(make_view(x, ops), out, scale=2.0)
+        ref = F.interpolate(x, size=(Ho, Wo), mode="bilinear", align_corners=False) * 2.0
+        assert (out.to_nchw() - ref).abs().max().item() < 1e-5
+    x2 = torch.randn(1, 2, 18, 30, generator=g).to(dev)
+    out = ops.View.alloc(9, 15, 2, dev)
+    ops.bilinear_resize(make_view(x2, ops), out, scale=0.5)
+    assert (out.to_nchw() - F.avg_pool2d(x2, 2) * 0.5).abs().max().item() < 1e-6
+    out = ops.View.alloc(9, 15, 64, dev)
+    ops.avgpool2(make_view(x, ops), out)
+    assert (out.to_nchw() - F.avg_pool2d(x, 2)).abs().max().item() < 1e-6
+    ops.maxpool2(make_view(x, ops), out)
+    assert (out.to_nchw() - F.max_pool2d(x, 2)).abs().max().item() == 0.0
+
+
+def test_spynet_prep(cuda_device):
+    ops = _ops()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(6)
+    H, W = 24, 40
+    im1 = torch.rand(1, 3, H, W, generator=g).to(dev)
+    im2 = torch.rand(1, 3, H, W, generator=g).to(dev)
+    fc = (torch.randn(1, 2, H // 2, W // 2, generator=g) * 2).to(dev)
+    out8 = ops.View.alloc(H, W, 8, dev)
+    fup = ops.View.alloc(H, W, 2, dev)
+    ops.spynet_prep(make_view(im1, ops, 4), make_view(im2, ops, 4), make_view(fc, ops), out8, fup)
+    up = F.interpolate(fc, size=(H, W), mode="bilinear", align_corners=False) * 2.0
+    ref = torch.cat([im1, torch_warp_ref(im2, up), up], 1)
+    assert (out8.to_nchw() - ref).abs().max().item() < 2e-5
+    assert (fup.to_nchw() - up).abs().max().item() < 1e-5
+    ops.spynet_prep(make_view(im1, ops, 4), make_view(im2, ops, 4), None, out8, fup)
+    ref0 = torch.cat([im1, im2, torch.zeros_like(up)], 1)
+    assert (out8.to_nchw() - ref0).abs().max().item() < 1e-6
+
+
+def test_offset_diversity(cuda_device):
+    ops = _ops()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(7)
+    C, G, O, H, W = 48, 16, 2, 16, 24
+    x = torch.randn(1, C, H, W, generator=g).to(dev)
+    off = torch.randn(1, 3 * G * O, H // 2, W // 2, generator=g).to(dev)
+    flow = (torch.randn(1, 2, H, W, generator=g) * 3).to(dev)
+    fw = torch.randn(C, C * O // G, 1, 1, generator=g).to(dev)
+    fb = torch.randn(C, generator=g).to(dev)
+    out = ops.View.alloc(H, W, C, dev)
+    ops.offset_diversity(make_view(x, ops), make_view(off, ops), make_view(flow, ops), fw.reshape(C, -1).contiguous(), fb,
+                         G, O, 40.0, out)
+    # reference data flow (lssvc_modules.py:92-112)
+    o = F.interpolate(off, size=(H, W), mode="bilinear", align_corners=False)
+    o1, o2, mask = torch.chunk(o, 3, dim=1)
+    mask = torch.sigmoid(mask)
+    offset = 40.0 * torch.tanh(torch.cat((o1, o2), dim=1)) + flow.repeat(1, G * O, 1, 1)
+    offset = offset.view(G * O, 2, H, W)
+    mask = mask.view(G * O, 1, H, W)
+    xx = x.view(G, C // G, H, W).repeat(O, 1, 1, 1)
+    xx = torch_warp_ref(xx, offset) * mask
+    ref = F.conv2d(xx.view(1, C * O, H, W), fw, fb, groups=G)
+    assert rel_err(out.to_nchw(), ref) < 2e-5
+
+
+def test_softmax_blend_and_lrelu(cuda_device):
+    ops = _ops()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(8)
+    H, W, C = 12, 20, 48
+    lg = torch.randn(1, 2, H, W, generator=g).to(dev)
+    a = torch.randn(1, C, H, W, generator=g).to(dev)
+    b = torch.randn(1, C, H, W, generator=g).to(dev)
+    out = ops.View.alloc(H, W, C, dev)
+    ops.softmax2_blend(make_view(lg, ops), make_view(a, ops), make_view(b, ops), out)
+    wmap = torch.softmax(lg, dim=1)
+    ref = a * wmap[:, 0:1] + b * wmap[:, 1:2]
+    assert (out.to_nchw() - ref).abs().max().item() < 1e-6
+    ops.lrelu_copy(make_view(a, ops), 0.1, out)
+    assert (out.to_nchw() - F.leaky_relu(a, 0.1)).abs().max().item() == 0.0
+
+
+def laplace_bits_ref(q, scale):
+    sigma = scale.clamp(1e-5, 1e10)
+    lap = torch.distributions.laplace.Laplace(torch.zeros_like(sigma), sigma)
+    probs = lap.cdf(q + 0.5) - lap.cdf(q - 0.5)
+    return torch.sum(torch.clamp(-1.0 * torch.log(probs + 1e-5) / math.log(2.0), 0, 50))
+
+
+def test_laplace_quant_and_index(cuda_device):
+    ops = _ops()
+    from lssvc_b200.entropy import video_scale_thresholds
+    dev = cuda_device
+    g = torch.Generator().manual_seed(9)
+    C, H, W = 96, 9, 15
+    y = (torch.randn(1, C, H, W, generator=g) * 4).to(dev)
+    mean = torch.randn(1, C, H, W, generator=g).to(dev)
+    scale = torch.exp(torch.randn(1, C, H, W, generator=g) * 2).to(dev)
+    scale[0, 0, 0, :5] = torch.tensor([-1.0, 0.0, 1e-7, 100.0, 0.01])
+    yq, yh = ops.View.alloc(H, W, C, dev), ops.View.alloc(H, W, C, dev)
+    bits = torch.zeros(1, dtype=torch.float64, device=dev)
+    sym = torch.empty(C * H * W, dtype=torch.int32, device=dev)
+    idx = torch.empty(C * H * W, dtype=torch.int32, device=dev)
+    thr = video_scale_thresholds().to(dev)
+    ops.laplace_quant(make_view(y, ops), make_view(mean, ops), make_view(scale, ops), yq, yh, bits, sym, idx, thr)
+    q_ref = torch.round(y - mean)
+    assert torch.equal(yq.to_nchw(), q_ref)
+    assert torch.equal(yh.to_nchw(), q_ref + mean)
+    assert torch.equal(sym.view(1, C, H, W), q_ref.int())
+    ref_bits = laplace_bits_ref(q_ref.cpu(), scale.cpu()).item()
+    assert abs(bits.item() - ref_bits) / ref_bits < 1e-5
+    # build_indexes as the reference computes it on CPU (video_entropy_models.py:309-313)
+    s = torch.maximum(scale.cpu(), torch.zeros_like(scale.cpu()) + 1e-5)
+    log_min, log_max = math.log(0.01), math.log(64.0)
+    ref_idx = ((torch.log(s) - log_min) / ((log_max - log_min) / 255)).clamp_(0, 255).int()
+    assert torch.equal(idx.view(1, C, H, W).cpu(), ref_idx)
+
+
+def test_four_part_steps(cuda_device):
+    ops = _ops()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(10)
+    C, H, W = 128, 8, 12
+    y = (torch.randn(1, C, H, W, generator=g) * 3).to(dev)
+    prm = [torch.randn(1, 2 * C, H, W, generator=g).to(dev) for _ in range(4)]
+    for p in prm:
+        p[:, :C] = torch.exp(p[:, :C])
+    yv = make_view(y, ops)
+    yh, yq, sh = (ops.View.alloc(H, W, C, dev) for _ in range(3))
+    bits = torch.zeros(1, dtype=torch.float64, device=dev)
+    for step in range(4):
+        ops.four_part_step(yv, make_view(prm[step], ops), step, yh, yq, sh, bits)
+    # reference masks (LSSVC_net.py:298-325, 361-413)
+    masks = []
+    for (i, j) in ((0, 0), (0, 1), (1, 0), (1, 1)):
+        m = torch.zeros(1, 1, H, W, device=dev)
+        m[:, :, i::2, j::2] = 1
+        masks.append(m)
+    order = [[0, 1, 2, 3], [3, 2, 1, 0], [2, 3, 0, 1], [1, 0, 3, 2]]
+    cq = C // 4
+    yh_ref = torch.zeros_like(y)
+    yq_ref = torch.zeros_like(y)
+    sh_ref = torch.zeros_like(y)
+    for step in range(4):
+        sc, mn = prm[step][:, :C], prm[step][:, C:]
+        for k in range(4):
+            sl = slice(k * cq, (k + 1) * cq)
+            m = masks[order[step][k]]
+            q = torch.round((y[:, sl] - mn[:, sl] * m) * m)
+            yq_ref[:, sl] += q
+            yh_ref[:, sl] += q + mn[:, sl] * m
+            sh_ref[:, sl] += sc[:, sl] * m
+    assert torch.equal(yq.to_nchw(), yq_ref)
+    assert torch.equal(yh.to_nchw(), yh_ref)
+    assert torch.equal(sh.to_nchw(), sh_ref)
+    ref_bits = laplace_bits_ref(yq_ref.cpu(), sh_ref.cpu()).item()
+    assert abs(bits.item() - ref_bits) / ref_bits < 1e-5
+
+
+def test_gaussian_and_factorized(cuda_device):
+    ops = _ops()
+    from lssvc_b200.entropy import image_scale_thresholds
+    dev = cuda_device
+    g = torch.Generator().manual_seed(11)
+    C, H, W = 96, 9, 15
+    y = (torch.randn(1, C, H, W, generator=g) * 4).to(dev)
+    mean = torch.randn(1, C, H, W, generator=g).to(dev)
+    scale = torch.exp(torch.randn(1, C, H, W, generator=g) * 2).to(dev)
+    yh = ops.View.alloc(H, W, C, dev)
+    bits = torch.zeros(1, dtype=torch.float64, device=dev)
+    idx = torch.empty(C * H * W, dtype=torch.int32, device=dev)
+    sym = torch.empty(C * H * W, dtype=torch.int32, device=dev)
+    thr = image_scale_thresholds().to(dev)
+    ops.gaussian_quant(make_view(y, ops), make_view(mean, ops), make_view(scale, ops), yh, bits, sym, idx, thr)
+    yc, mc, sc = y.cpu(), mean.cpu(), scale.cpu()
+    out = torch.round(yc - mc) + mc
+    assert torch.equal(yh.to_nchw().cpu(), out)
+    v = (out - mc).abs()
+    s = torch.max(sc, torch.tensor(0.11))
+    cum = lambda t: 0.5 * torch.erfc(-(2 ** -0.5) * t)
+    lik = torch.max(cum((0.5 - v) / s) - cum((-0.5 - v) / s), torch.tensor(1e-9))
+    ref_bits = (torch.log(lik).sum() / -math.log(2)).item()
+    assert abs(bits.item() - ref_bits) / ref_bits < 1e-4
+    s2 = torch.maximum(sc, torch.zeros_like(sc) + 1e-5)
+    lmin, lmax = math.log(0.11), math.log(256.0)
+    ref_idx = ((torch.log(s2) - lmin) / ((lmax - lmin) / 63) + 1).clamp_(0, 63).int()
+    assert torch.equal(idx.view(1, C, H, W).cpu(), ref_idx)
+    assert torch.equal(sym.view(1, C, H, W).cpu(), torch.round(yc - mc).int())
+
+    # BitEstimator
+    Cz = 64
+    z = (torch.randn(1, Cz, 5, 7, generator=g) * 3).to(dev)
+    h = torch.randn(4, Cz, generator=g) * 0.5
+    b = torch.randn(4, Cz, generator=g) * 0.5
+    a = torch.randn(3, Cz, generator=g) * 0.5
+    coef = torch.cat([F.softplus(h), b, torch.tanh(a)], 0).t().contiguous().to(dev)  # [C][11]
+    zh = ops.View.alloc(5, 7, Cz, dev)
+    bits.zero_()
+    ops.bitparm_quant(make_view(z, ops), coef, zh, bits)
+
+    def cdf(x):
+        for i in range(3):
+            x = x * F.softplus(h[i]).view(1, -1, 1, 1) + b[i].view(1, -1, 1, 1)
+            x = x + torch.tanh(x) * torch.tanh(a[i]).view(1, -1, 1, 1)
+        return torch.sigmoid(x * F.softplus(h[3]).view(1, -1, 1, 1) + b[3].view(1, -1, 1, 1))
+
+    zq = torch.round(z.cpu())
+    prob = cdf(zq + 0.5) - cdf(zq - 0.5)
+    ref_bits = torch.sum(torch.clamp(-1.0 * torch.log(prob + 1e-5) / math.log(2.0), 0, 50)).item()
+    assert torch.equal(zh.to_nchw().cpu(), zq)
+    assert abs(bits.item() - ref_bits) / ref_bits < 1e-4
+
+
+def test_layout_roundtrip(cuda_device):
+    ops = _ops()
+    dev = cuda_device
+    x = torch.randn(1, 37, 13, 21, device=dev)
+    v = ops.View.from_nchw(x, C_view=40)
+    assert torch.equal(v.slice(0, 37).to_nchw(), x)
+    assert v.slice(37, 40).to_nchw().abs().max().item() == 0.0
