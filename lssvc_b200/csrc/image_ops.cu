@@ -12,39 +12,41 @@ __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? 
 inline int blocks_for(long long total) { return static_cast<int>((total + TPB - 1) / TPB); }
 
 // ---- layout ------------------------------------------------------------------------------
-// src [C][H][W] -> dst NHWC (pitch), zero fill channels C..Cv-1. Tile transpose through smem so both
-// sides are coalesced: block = 32 pixels x all channels.
+// src [C][H][W] -> dst NHWC (pitch), zero fill channels C..Cv-1. 32 pixels x 32 channels tile transposed through
+// smem so both sides are coalesced.  blockDim = (32, 8).
 __global__ void nchw_to_nhwc_kernel(const float *__restrict__ src, int C, float *__restrict__ dst, int Cv, int pitch,
                                     long long HW) {
-  extern __shared__ float tile[];  // [Cv][33]
+  __shared__ float tile[32][33];
   const long long p0 = static_cast<long long>(blockIdx.x) * 32;
-  for (int i = threadIdx.x; i < Cv * 32; i += blockDim.x) {
-    const int c = i / 32, px = i % 32;
-    const long long pp = p0 + px;
-    tile[c * 33 + px] = (c < C && pp < HW) ? src[static_cast<long long>(c) * HW + pp] : 0.f;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i;
+    const long long pp = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && pp < HW) ? src[static_cast<long long>(c) * HW + pp] : 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < Cv * 32; i += blockDim.x) {
-    const int px = i / Cv, c = i % Cv;
-    const long long pp = p0 + px;
-    if (pp < HW) dst[pp * pitch + c] = tile[c * 33 + px];
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const long long pp = p0 + i;
+    const int c = c0 + threadIdx.x;
+    if (pp < HW && c < Cv) dst[pp * pitch + c] = tile[threadIdx.x][i];
   }
 }
 
 __global__ void nhwc_to_nchw_kernel(const float *__restrict__ src, int C, int pitch, float *__restrict__ dst,
                                     long long HW) {
-  extern __shared__ float tile[];  // [C][33]
+  __shared__ float tile[32][33];
   const long long p0 = static_cast<long long>(blockIdx.x) * 32;
-  for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
-    const int px = i / C, c = i % C;
-    const long long pp = p0 + px;
-    tile[c * 33 + px] = pp < HW ? src[pp * pitch + c] : 0.f;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const long long pp = p0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (pp < HW && c < C) ? src[pp * pitch + c] : 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
-    const int c = i / 32, px = i % 32;
-    const long long pp = p0 + px;
-    if (pp < HW) dst[static_cast<long long>(c) * HW + pp] = tile[c * 33 + px];
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i;
+    const long long pp = p0 + threadIdx.x;
+    if (c < C && pp < HW) dst[static_cast<long long>(c) * HW + pp] = tile[threadIdx.x][i];
   }
 }
 
@@ -309,22 +311,18 @@ bool aligned4(const lssvc_view *v) { return v->C % 4 == 0 && v->pitch % 4 == 0 &
 
 extern "C" int32_t lssvc_nchw_to_nhwc(const float *src, int32_t C, const lssvc_view *out, void *stream) {
   LSSVC_REQUIRE(src && lssvc::view_ok(out) && C >= 1 && C <= out->C, "nchw_to_nhwc: bad arguments");
-  LSSVC_REQUIRE(out->C <= 1024, "nchw_to_nhwc: too many channels");
   const long long HW = static_cast<long long>(out->H) * out->W;
-  const int blocks = static_cast<int>((HW + 31) / 32);
-  nchw_to_nhwc_kernel<<<blocks, TPB, out->C * 33 * sizeof(float), lssvc::as_stream(stream)>>>(src, C, out->ptr, out->C,
-                                                                                               out->pitch, HW);
+  dim3 grid(static_cast<unsigned>((HW + 31) / 32), lssvc::ceil_div(out->C, 32));
+  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, lssvc::as_stream(stream)>>>(src, C, out->ptr, out->C, out->pitch, HW);
   LSSVC_LAUNCHED();
   return LSSVC_OK;
 }
 
 extern "C" int32_t lssvc_nhwc_to_nchw(const lssvc_view *in, float *dst, void *stream) {
   LSSVC_REQUIRE(dst && lssvc::view_ok(in), "nhwc_to_nchw: bad arguments");
-  LSSVC_REQUIRE(in->C <= 1024, "nhwc_to_nchw: too many channels");
   const long long HW = static_cast<long long>(in->H) * in->W;
-  const int blocks = static_cast<int>((HW + 31) / 32);
-  nhwc_to_nchw_kernel<<<blocks, TPB, in->C * 33 * sizeof(float), lssvc::as_stream(stream)>>>(in->ptr, in->C, in->pitch,
-                                                                                              dst, HW);
+  dim3 grid(static_cast<unsigned>((HW + 31) / 32), lssvc::ceil_div(in->C, 32));
+  nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, lssvc::as_stream(stream)>>>(in->ptr, in->C, in->pitch, dst, HW);
   LSSVC_LAUNCHED();
   return LSSVC_OK;
 }

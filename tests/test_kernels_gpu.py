@@ -223,8 +223,8 @@ def test_spynet_prep(cuda_device):
     assert (out8.to_nchw() - ref).abs().max().item() < 2e-5
     assert (fup.to_nchw() - up).abs().max().item() < 1e-5
     ops.spynet_prep(make_view(im1, ops, 4), make_view(im2, ops, 4), None, out8, fup)
-    ref0 = torch.cat([im1, im2, torch.zeros_like(up)], 1)
-    assert (out8.to_nchw() - ref0).abs().max().item() < 1e-6
+    ref0 = torch.cat([im1, torch_warp_ref(im2, torch.zeros_like(up)), torch.zeros_like(up)], 1)
+    assert (out8.to_nchw() - ref0).abs().max().item() < 2e-5
 
 
 def test_offset_diversity(cuda_device):
