@@ -332,7 +332,6 @@ extern "C" int32_t lssvc_conv_tc(const lssvc_conv *c, void *stream) {
   LSSVC_REQUIRE(c->in_transform == LSSVC_IN_NONE && c->epi == LSSVC_EPI_PLAIN,
                 "conv_tc: input transforms / GDN epilogue are SIMT-only");
   LSSVC_REQUIRE(c->stride == 1 || c->stride == 2, "conv_tc: stride %d", c->stride);
-  if (int rc = resolve_driver()) return rc;
 
   const int Hin = c->src[0].H, Win = c->src[0].W;
   int kc = 32;
@@ -368,6 +367,15 @@ extern "C" int32_t lssvc_conv_tc(const lssvc_conv *c, void *stream) {
     while (n_tile >= 16 && (c->n_pad % n_tile)) n_tile -= 16;
     LSSVC_REQUIRE(n_tile >= 16, "conv_tc: cannot tile n_pad=%d", c->n_pad);
   }
+
+  {
+    const int ps_ = c->pixel_shuffle ? 2 : 1;
+    auto shape_ok = [&](const lssvc_view &v) {
+      return !v.ptr || (v.H == Ho * ps_ && v.W == Wo * ps_ && v.C == c_store);
+    };
+    LSSVC_REQUIRE(shape_ok(c->res1) && shape_ok(c->res2) && shape_ok(c->out2), "conv_tc: res1/res2/out2 shape mismatch");
+  }
+  if (int rc = resolve_driver()) return rc;
 
   TcParams p;
   memset(&p, 0, sizeof(p));

@@ -1,0 +1,241 @@
+"""Shared execution helpers of the host-side models: weight (re)packing cache and the fused building blocks
+(conv + epilogue, ResBlock, DepthConvBlock, GDN, SpyNet, 3-scale extractor / fusion) expressed on the kernels.
+
+A model is a nets.ParamBag (reference-layout tensors) + this mixin.  Activations are `ops.View`s (NHWC fp32)."""
+import torch
+
+from . import _lib, nets, ops
+from .ops import View
+
+
+class Engine(nets.ParamBag):
+    def __init__(self, spec, model_tag, seed=None):
+        super().__init__(spec, seed=seed, gains=nets.model_gains(model_tag))
+        self._packs = {}
+        self.shape_hr = (256, 256)
+        self.scale_factor = 2.0
+        self.pad_size = (0, 0, 0, 0)
+        self.eval()
+
+    # ---- reference API shared by IntraSS / LSSVC (IntraSS.py:229-232, LSSVC_net.py:266-269) -----------------
+    def set_scale_information(self, scale, shape_hr, pad_size):
+        self.scale_factor = scale
+        self.shape_hr = tuple(shape_hr)
+        self.pad_size = tuple(pad_size)
+        if any(int(p) != 0 for p in self.pad_size):
+            # the reference's test.py always passes (0, 0, 0, 0) (test.py:212-213)
+            raise NotImplementedError("inter-layer de-padding with a non-zero pad_size is not implemented")
+
+    # ---- weight cache ---------------------------------------------------------------------------------------
+    def _invalidate(self):
+        self._packs = {}
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict=True):
+        self._invalidate()
+        return super().load_state_dict(state_dict, strict=strict)
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def _require_cuda(self):
+        if self.device.type != "cuda" and not _lib.DRY_RUN:
+            raise _lib.LssvcError("lssvc_b200 models run on a CUDA (sm_100a) device only; call .to('cuda') first — "
+                                  "there is no CPU fallback")
+
+    def pack(self, name, srcs, stride, ps, transposed, pad):
+        key = (name, tuple((v.real, v.C) for v in srcs), stride, ps, transposed, pad)
+        pc = self._packs.get(key)
+        if pc is None:
+            pc = ops.PackedConv(self.tensor(name + ".weight"), self.tensor(name + ".bias"), stride=stride, pad=pad,
+                                src_channels=[(v.real, v.C) for v in srcs], pixel_shuffle=ps, transposed=transposed,
+                                device=self.device)
+            self._packs[key] = pc
+        return pc
+
+    def cached(self, key, builder):
+        t = self._packs.get(key)
+        if t is None:
+            t = builder()
+            self._packs[key] = t
+        return t
+
+    # ---- primitives -----------------------------------------------------------------------------------------
+    def new(self, H, W, C):
+        return View.alloc_padded(H, W, C, self.device)
+
+    def conv(self, name, srcs, stride=1, act=None, ps=False, transposed=False, pad=None, res1=None, res2=None,
+             out=None, act_copy=None, act_copy_out=None, out_scale=1.0, engine=None):
+        """conv (+PixelShuffle) with fused epilogue.  Returns the output view, or (out, lrelu(out, act_copy))."""
+        if isinstance(srcs, View):
+            srcs = [srcs]
+        pc = self.pack(name, srcs, stride, ps, transposed, pad)
+        Hi, Wi = srcs[0].H, srcs[0].W
+        Ho = (Hi + 2 * pc.pad - pc.kh) // stride + 1
+        Wo = (Wi + 2 * pc.pad - pc.kw) // stride + 1
+        f = 2 if ps else 1
+        C = pc.cout // 4 if ps else pc.cout
+        if out is None:
+            out = self.new(Ho * f, Wo * f, C)
+        out2 = None
+        if act_copy is not None:
+            out2 = act_copy_out if act_copy_out is not None else self.new(Ho * f, Wo * f, C)
+        ex = lambda v: None if v is None else v.exact()
+        ops.conv(pc, srcs, out.exact(), act=act, res1=ex(res1), res2=ex(res2), out2=ex(out2),
+                 slope2=0.0 if act_copy is None else act_copy, out_scale=out_scale, engine=engine)
+        return (out, out2) if act_copy is not None else out
+
+    def lrelu(self, x, slope, out=None):
+        out = out if out is not None else self.new(x.H, x.W, x.real)
+        ops.lrelu_copy(x.exact(), slope, out.exact())
+        return out
+
+    def copy(self, x, out):
+        return self.lrelu(x, 1.0, out)
+
+    def gdn(self, name, x, inverse=False, res1=None, intra=False, out=None):
+        """GDN / IGDN: x * (beta + gamma . x^2)^(-/+ 1/2) (+ res1).  fp32 CUDA-core path (norm pool wants full precision).
+        intra: gdn.py:29-44 + others.py:43-67; inter: video_net_component.py:83-105."""
+        def build():
+            beta, gamma = self.tensor(name + ".beta").detach().float().cpu(), self.tensor(name + ".gamma").detach().float().cpu()
+            if intra:
+                ped = 2.0 ** -36
+                beta = torch.max(beta, torch.tensor((1e-6 + ped) ** 0.5)) ** 2 - ped
+                gamma = torch.max(gamma, torch.tensor(ped ** 0.5)) ** 2 - ped
+            else:
+                ped = (2.0 ** -18) ** 2
+                beta = torch.max(beta, torch.ones_like(beta) * ((1e-6 + ped) ** 0.5)) ** 2 - ped
+                gamma = torch.max(gamma, torch.ones_like(gamma) * (2.0 ** -18)) ** 2 - ped
+            C = beta.numel()
+            return ops.PackedConv(gamma.view(C, C, 1, 1), beta, pad=0, src_channels=[(C, x.C)], device=self.device)
+        pc = self.cached(("gdn", name, x.C), build)
+        out = out if out is not None else self.new(x.H, x.W, x.real)
+        ops.conv(pc, [x], out.exact(), in_transform=_lib.IN_SQUARE, epi=_lib.EPI_IGDN if inverse else _lib.EPI_GDN,
+                 gdn_x=x.exact(), res1=None if res1 is None else res1.exact(), engine="simt")
+        return out
+
+    def dwconv(self, name, x):
+        def build():
+            w = self.tensor(name + ".weight").detach().float()
+            C = w.shape[0]
+            return (w.reshape(C, 9).t().contiguous().to(self.device), self.tensor(name + ".bias").detach().float().to(self.device))
+        w, b = self.cached(("dw", name), build)
+        out = self.new(x.H, x.W, x.real)
+        ops.dwconv3x3(x.exact(), w, b, out.exact())
+        return out
+
+    def deconv_s2(self, name, x, act=None):
+        """nn.ConvTranspose2d(3, stride=2, padding=1, output_padding=1)."""
+        def build():
+            w = self.tensor(name + ".weight").detach().float()          # [cin, cout, 3, 3]
+            cin, cout = w.shape[0], w.shape[1]
+            return (w.permute(2, 3, 0, 1).reshape(9, cin, cout).contiguous().to(self.device),
+                    self.tensor(name + ".bias").detach().float().to(self.device), cout)
+        w, b, cout = self.cached(("deconv", name), build)
+        out = self.new(x.H * 2, x.W * 2, cout)
+        ops.deconv3x3_s2(x.exact(), w, b, out.exact(), act=act)
+        return out
+
+    def resize(self, x, H, W, scale=1.0):
+        out = self.new(H, W, x.real)
+        ops.bilinear_resize(x.exact(), out.exact(), scale=scale)
+        return out
+
+    def warp(self, src, flow, out=None):
+        out = out if out is not None else self.new(src.H, src.W, src.real)
+        ops.flow_warp(src.exact(), flow, out.exact())
+        return out
+
+    def image_view(self, t):
+        """[1,3,H,W] fp32 tensor -> NHWC view with 8 channels (5 zero) readable by every kernel."""
+        if t.device != self.device:
+            t = t.to(self.device)
+        return View.from_nchw(t.float(), C_view=8)
+
+    def feature_view(self, t):
+        if t.device != self.device:
+            t = t.to(self.device)
+        C = t.shape[1]
+        return View.from_nchw(t.float(), C_view=ops.round_up(C, 8))
+
+    # ---- blocks -----------------------------------------------------------------------------------------------
+    def res_block(self, name, x, x_act=None, slope=0.01, start_from_relu=True, end_with_relu=False, res2=None, out=None,
+                  act_copy=None, act_copy_out=None):
+        """ResBlock (video_net_component.py:170-188, layers.py:229-255): x + last(conv2(lrelu(conv1(first(x))))).
+        x_act: lrelu(x, slope) if the producer already wrote it (saves a pass)."""
+        inp = x
+        if start_from_relu:
+            inp = x_act if x_act is not None else self.lrelu(x, slope)
+        t = self.conv(name + ".conv1", inp, act=slope)
+        return self.conv(name + ".conv2", t, act=slope if end_with_relu else None, res1=x, res2=res2, out=out,
+                         act_copy=act_copy, act_copy_out=act_copy_out)
+
+    def depth_conv_block(self, name, x, res2=None, out=None):
+        """DepthConvBlock (lssvc_modules.py:15-72): DepthConv (1x1, lrelu .01, dw3x3, 1x1, + identity/adaptor)
+        then ConvFFN (x + lrelu(1x1(lrelu(1x1 x, .1)), .1))."""
+        dc, ffn = name + ".block.0", name + ".block.1"
+        t = self.conv(dc + ".conv1.0", x, act=0.01, pad=0)
+        t = self.dwconv(dc + ".depth_conv", t)
+        has_adaptor = (dc + ".adaptor.weight") in self._spec
+        identity = self.conv(dc + ".adaptor", x, pad=0) if has_adaptor else x
+        o = self.conv(dc + ".conv2", t, pad=0, res1=identity)
+        f = self.conv(ffn + ".conv.0", o, act=0.1, pad=0)
+        return self.conv(ffn + ".conv.2", f, act=0.1, pad=0, res1=o, res2=res2, out=out)
+
+    def extractor3(self, name, x):
+        """conv1/res_block1, conv2 s2/res_block2, conv3 s2/res_block3
+        (layers.py:288-308, lssvc_modules.py:157-200, dmc_net.py:11-31)."""
+        outs = []
+        cur = x
+        for i, stride in ((1, 1), (2, 2), (3, 2)):
+            t, t_act = self.conv(f"{name}.conv{i}", cur, stride=stride, act_copy=0.01)
+            cur = self.res_block(f"{name}.res_block{i}", t, x_act=t_act)
+            outs.append(cur)
+        return outs
+
+    def fusion3(self, name, c1, c2, c3, out2_slopes=None, outs=None):
+        """MultiScaleContextFusion / MultiScaleTextureFusion (lssvc_modules.py:203-232, dmc_net.py:34-62,
+        layers.py:311-339).  Returns (c1 + c1_out, c2 + c2_out, c3 + c3_out); outs: optional destination views."""
+        outs = outs or (None, None, None)
+        t, ta = self.conv(name + ".conv3_up.0", c3, ps=True, act_copy=0.01)
+        c3_up = self.res_block(name + ".res_block3_up", t, x_act=ta)
+        t, ta = self.conv(name + ".conv3_out", c3, act_copy=0.01)
+        o3 = self.res_block(name + ".res_block3_out", t, x_act=ta, res2=c3, out=outs[2])
+        t, ta = self.conv(name + ".conv2_up.0", [c3_up, c2], ps=True, act_copy=0.01)
+        c2_up = self.res_block(name + ".res_block2_up", t, x_act=ta)
+        t, ta = self.conv(name + ".conv2_out", [c3_up, c2], act_copy=0.01)
+        o2 = self.res_block(name + ".res_block2_out", t, x_act=ta, res2=c2, out=outs[1])
+        t, ta = self.conv(name + ".conv1_out", [c2_up, c1], act_copy=0.01)
+        o1 = self.res_block(name + ".res_block1_out", t, x_act=ta, res2=c1, out=outs[0])
+        return o1, o2, o3
+
+    def spynet(self, name, im1, im2):
+        """ME_Spynet / ME_Spynet_DCVC (video_net_component.py:222-248, 300-326): 4-level coarse-to-fine flow."""
+        p1, p2 = [im1], [im2]
+        for _ in range(3):
+            for p in (p1, p2):
+                src = p[-1]
+                dst = View.alloc(src.H // 2, src.W // 2, src.C, self.device, pitch=src.pitch)
+                dst.real = src.real
+                ops.avgpool2(src, dst)
+                p.append(dst)
+        flow = None
+        for level in range(4):
+            a, b = p1[3 - level], p2[3 - level]
+            x8 = View.alloc(a.H, a.W, 8, self.device, pitch=8)
+            flow_up = self.new(a.H, a.W, 2)
+            ops.spynet_prep(a, b, flow, x8, flow_up)
+            m = f"{name}.moduleBasic.{level}"
+            t = x8
+            for k in range(1, 5):
+                t = self.conv(f"{m}.conv{k}", t, act=0.0, pad=3)
+            flow = self.conv(f"{m}.conv5", t, pad=3, res1=flow_up)
+        return flow
+
+    def seq2(self, name, x, out=None, **kw):
+        """conv, LeakyReLU, conv."""
+        return self.conv(name + ".2", self.conv(name + ".0", x, act=0.01), out=out, **kw)

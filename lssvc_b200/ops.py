@@ -11,6 +11,8 @@ _NULL_VIEW = CView(None, 0, 0, 0, 0)
 
 
 def _stream():
+    if _lib.DRY_RUN and not torch.cuda.is_available():
+        return None
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -25,10 +27,11 @@ def round_up(x, m):
 class View:
     """A window of C channels of an NHWC fp32 buffer with `pitch` floats per pixel."""
 
-    __slots__ = ("buf", "H", "W", "C", "pitch", "coff")
+    __slots__ = ("buf", "H", "W", "C", "pitch", "coff", "real")
 
-    def __init__(self, buf, H, W, C, pitch, coff=0):
+    def __init__(self, buf, H, W, C, pitch, coff=0, real=None):
         self.buf, self.H, self.W, self.C, self.pitch, self.coff = buf, H, W, C, pitch, coff
+        self.real = C if real is None else real   # channels that carry data; C - real trailing channels are zero
 
     @staticmethod
     def alloc(H, W, C, device, pitch=None, zero=False):
@@ -41,9 +44,23 @@ class View:
         return View(self.buf, self.H, self.W, c1 - c0, self.pitch, self.coff + c0)
 
     def widen(self, C):
-        """Same window start, C channels wide (to expose zeroed pad channels to a conv)."""
-        assert self.coff + C <= self.pitch
-        return View(self.buf, self.H, self.W, C, self.pitch, self.coff)
+        """Same window start, C channels wide, exposing zeroed pad channels to a conv; `real` is kept."""
+        assert self.coff + C <= self.pitch and C >= self.real
+        return View(self.buf, self.H, self.W, C, self.pitch, self.coff, real=self.real)
+
+    def exact(self):
+        """The window without its pad channels (what a producer kernel writes)."""
+        return View(self.buf, self.H, self.W, self.real, self.pitch, self.coff)
+
+    @staticmethod
+    def alloc_padded(H, W, C, device, mult=8):
+        """C data channels in a buffer padded (and zeroed) to a multiple of `mult` so tensor-core convs can read it."""
+        Cp = round_up(C, mult)
+        if Cp == C:
+            return View.alloc(H, W, C, device)
+        v = View.alloc(H, W, Cp, device, pitch=Cp, zero=True)
+        v.real = C
+        return v
 
     @property
     def device(self):
@@ -57,9 +74,11 @@ class View:
         return self.buf.view(self.H, self.W, self.pitch)[:, :, self.coff:self.coff + self.C]
 
     def to_nchw(self):
-        out = torch.empty(1, self.C, self.H, self.W, dtype=torch.float32, device=self.device)
+        """[1, real, H, W] contiguous copy."""
+        v = self.exact() if self.real != self.C else self
+        out = torch.empty(1, v.C, v.H, v.W, dtype=torch.float32, device=self.device)
         lib = _lib.load()
-        _lib.check(lib.lssvc_nhwc_to_nchw(byref(self.c()), _ptr(out), _stream()), "nhwc_to_nchw")
+        _lib.check(lib.lssvc_nhwc_to_nchw(byref(v.c()), _ptr(out), _stream()), "nhwc_to_nchw")
         return out
 
     @staticmethod
@@ -69,10 +88,11 @@ class View:
             assert t.shape[0] == 1, "batch 1 only"
             t = t[0]
         t = t.contiguous()
-        assert t.dtype == torch.float32 and t.is_cuda
+        assert t.dtype == torch.float32 and (t.is_cuda or _lib.DRY_RUN)
         C, H, W = t.shape
         if out is None:
             out = View.alloc(H, W, C_view or C, t.device)
+            out.real = C
         lib = _lib.load()
         _lib.check(lib.lssvc_nchw_to_nhwc(_ptr(t), C, byref(out.c()), _stream()), "nchw_to_nhwc")
         return out
@@ -161,7 +181,7 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
     if engine is None:
         tc_ok = (not _FORCE_SIMT and in_transform == _lib.IN_NONE and epi == _lib.EPI_PLAIN
                  and all(s.C % 8 == 0 and s.pitch % 4 == 0 and (s.coff % 4 == 0) for s in srcs)
-                 and pc.stride in (1, 2))
+                 and pc.stride in (1, 2) and srcs[0].H % pc.stride == 0 and srcs[0].W % pc.stride == 0)
         engine = "tc" if tc_ok else "simt"
     if engine == "tc":
         _lib.check(lib.lssvc_conv_tc(byref(d), _stream()), "conv_tc")

@@ -1,0 +1,143 @@
+"""End-to-end parity of the CUDA path against the oracle (the reference's algorithm on CPU fp32) on identical
+synthetic frames and weights, through the public model API.
+
+Tolerances (BASELINE.json north_star): reconstructions within 1e-3 max-abs, quantised symbols >= 99.99 % equal,
+per-layer bits within 0.1 %.  They are asserted for the fp32 CUDA-core configuration (exact fp32 arithmetic);
+the tcgen05 TF32 configuration is asserted at the looser bounds written next to each check and its measured
+deviations are printed ("precision")."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+H = W = 128
+
+
+@pytest.fixture(scope="module")
+def setup(cuda_device):
+    from lssvc_b200 import IntraSS, LSSVC_extend, synth
+    from oracle import lssvc_oracle as orc
+    torch.set_num_threads(8)
+    net_i = IntraSS(seed=0)
+    net_p = LSSVC_extend(seed=1)
+    sd_i = {k: v.clone() for k, v in net_i.state_dict().items()}
+    sd_p = {k: v.clone() for k, v in net_p.state_dict().items()}
+    net_i.to(cuda_device)
+    net_p.to(cuda_device)
+    for n in (net_i, net_p):
+        n.set_scale_information(2.0, (H, W), (0, 0, 0, 0))
+    frames = synth.make_sequence(H, W, 4, seed=0)
+    with torch.no_grad():
+        o_i = orc.intra_ss(sd_i, frames[0][0], frames[0][1], (H, W))
+        dpb = {"ref_frame_bl": o_i["x_hat_bl"].clamp(0, 1), "ref_frame_el": o_i["x_hat_el"].clamp(0, 1),
+               "ref_feature_bl": None, "ref_feature_el": o_i["feature_el"]}
+        o_p1 = orc.lssvc(sd_p, frames[1][0], frames[1][1], dpb, (H, W), 2.0)
+        dpb2 = dict(o_p1["dpb"])
+        dpb2["ref_frame_bl"] = dpb2["ref_frame_bl"].clamp(0, 1)
+        dpb2["ref_frame_el"] = dpb2["ref_frame_el"].clamp(0, 1)
+        o_p2 = orc.lssvc(sd_p, frames[2][0], frames[2][1], dpb2, (H, W), 2.0)
+    return dict(net_i=net_i, net_p=net_p, frames=frames, o_i=o_i, o_p1=o_p1, o_p2=o_p2, dpb1=dpb, dpb2=dpb2,
+                dev=cuda_device)
+
+
+def _cmp(name, got, ref):
+    d = (got.cpu() - ref).abs().max().item()
+    print(f"  {name:14s} max|d| {d:.3e}  (ref absmax {ref.abs().max().item():.3g})")
+    return d
+
+
+def _match(name, got, ref):
+    m = (got.cpu() == ref).float().mean().item()
+    print(f"  {name:14s} equal {100 * m:.4f} %")
+    return m
+
+
+def _run_intra(s, simt):
+    from lssvc_b200 import ops
+    ops.force_simt(simt)
+    try:
+        net = s["net_i"]
+        net._debug = {}
+        x_bl, x_el = s["frames"][0]
+        r = net.encode_decode(x_bl.to(s["dev"]), x_el.to(s["dev"]), None, None, H // 2, W // 2, H, W)
+        dbg = {k: v for k, v in net._debug.items()}
+    finally:
+        ops.force_simt(False)
+        s["net_i"]._debug = None
+    return r, dbg
+
+
+def _run_inter(s, simt, frame, dpb_cpu):
+    from lssvc_b200 import ops
+    ops.force_simt(simt)
+    try:
+        net = s["net_p"]
+        net._debug = {}
+        x_bl, x_el = s["frames"][frame]
+        dpb = {k: (None if v is None else v.to(s["dev"])) for k, v in dpb_cpu.items()}
+        r = net.encode_decode(x_bl.to(s["dev"]), x_el.to(s["dev"]), dpb, None, None, W, H, W // 2, H // 2)
+        dbg = {k: v for k, v in net._debug.items()}
+    finally:
+        ops.force_simt(False)
+        s["net_p"]._debug = None
+    return r, dbg
+
+
+@pytest.mark.parametrize("simt", [True, False], ids=["fp32_simt", "tf32_tcgen05"])
+def test_intra_frame_parity(setup, simt):
+    s, o = setup, setup["o_i"]
+    r, dbg = _run_intra(s, simt)
+    print(f"I-frame ({'fp32 CUDA cores' if simt else 'tcgen05 TF32'}): bits {r['bit_bl']:.1f}/{r['bit_el']:.1f} "
+          f"oracle {o['bit_bl']:.1f}/{o['bit_el']:.1f}")
+    tol_rec, tol_sym, tol_bits = (1e-3, 0.9999, 1e-3) if simt else (2e-2, 0.98, 1e-2)
+    assert _cmp("x_hat_bl", r["x_hat_bl"], o["x_hat_bl"]) < tol_rec
+    assert _cmp("x_hat_el", r["x_hat_el"], o["x_hat_el"]) < tol_rec
+    _cmp("feature_el", r["feature_el"], o["feature_el"])
+    sym_ref = torch.round(o["y"] - o["means"])
+    sym_got = torch.round(dbg["y_hat"].to_nchw().cpu() - dbg["params_el"].slice(96, 192).to_nchw().cpu())
+    assert _match("EL symbols", sym_got, sym_ref) >= tol_sym
+    assert _match("BL z_hat", dbg["z_hat_bl"].to_nchw(), o["bl"]["z_hat"]) >= tol_sym
+    assert _match("EL z_hat", dbg["z_hat"].to_nchw(), o["z_hat"]) >= tol_sym
+    assert abs(r["bit_bl"] - o["bit_bl"]) / o["bit_bl"] < tol_bits
+    assert abs(r["bit_el"] - o["bit_el"]) / o["bit_el"] < tol_bits
+
+
+@pytest.mark.parametrize("simt", [True, False], ids=["fp32_simt", "tf32_tcgen05"])
+@pytest.mark.parametrize("which", ["first_p", "second_p"])
+def test_inter_frame_parity_teacher_forced(setup, simt, which):
+    s = setup
+    frame, dpb, o = (1, s["dpb1"], s["o_p1"]) if which == "first_p" else (2, s["dpb2"], s["o_p2"])
+    r, dbg = _run_inter(s, simt, frame, dpb)
+    print(f"P-frame {which} ({'fp32 CUDA cores' if simt else 'tcgen05 TF32'}): bits {r['bit_bl']:.1f}/{r['bit_el']:.1f} "
+          f"oracle {o['bit_bl']:.1f}/{o['bit_el']:.1f}")
+    tol_rec, tol_sym, tol_bits = (1e-3, 0.9999, 1e-3) if simt else (2e-2, 0.98, 1e-2)
+    assert _cmp("BL mv_hat", dbg["bl_mv_hat"].to_nchw(), o["bl"]["mv_hat"]) < tol_rec * 10
+    assert _cmp("ref_frame_bl", r["dpb"]["ref_frame_bl"], o["dpb"]["ref_frame_bl"]) < tol_rec
+    assert _cmp("mv_hat", r["mv_hat"], o["mv_hat"]) < tol_rec * 10
+    assert _cmp("warp_frame", r["warp_frame"], o["warp_frame"]) < tol_rec
+    assert _cmp("ref_frame_el", r["dpb"]["ref_frame_el"], o["dpb"]["ref_frame_el"]) < tol_rec
+    _cmp("ref_feature_bl", r["dpb"]["ref_feature_bl"], o["dpb"]["ref_feature_bl"])
+    _cmp("ref_feature_el", r["dpb"]["ref_feature_el"], o["dpb"]["ref_feature_el"])
+    assert _match("EL y_q", dbg["y_q"].to_nchw(), o["four_part"]["y_q"]) >= tol_sym
+    assert _match("EL z_hat", dbg["z_hat"].to_nchw(), o["z_hat"]) >= tol_sym
+    assert _match("EL mv_z_hat", dbg["mv_z_hat"].to_nchw(), o["mv_z_hat"]) >= tol_sym
+    assert _match("BL z_hat", dbg["bl_z_hat"].to_nchw(), o["bl"]["z_hat"]) >= tol_sym
+    mvq = torch.round(dbg["mv_y_hat"].to_nchw().cpu() - dbg["mv_prm"].slice(64, 128).to_nchw().cpu())
+    assert _match("EL mv_y_q", mvq, o["mv_y_q"]) >= tol_sym
+    assert abs(r["bit_bl"] - o["bit_bl"]) / o["bit_bl"] < tol_bits
+    assert abs(r["bit_el"] - o["bit_el"]) / o["bit_el"] < tol_bits
+
+
+def test_dpb_roundtrip_and_inplace_clamp(setup):
+    """The caller clamps the returned reference frames in place and hands the dict back (test.py:249-250)."""
+    s = setup
+    r1, _ = _run_inter(s, False, 1, s["dpb1"])
+    dpb = r1["dpb"]
+    dpb["ref_frame_bl"].clamp_(0, 1)
+    dpb["ref_frame_el"].clamp_(0, 1)
+    x_bl, x_el = s["frames"][2]
+    r2 = s["net_p"].encode_decode(x_bl.to(s["dev"]), x_el.to(s["dev"]), dpb, None, None, W, H, W // 2, H // 2)
+    assert torch.isfinite(r2["dpb"]["ref_frame_el"]).all()
+    assert set(r2["dpb"]) >= {"ref_frame_bl", "ref_feature_bl", "ref_frame_el", "ref_feature_el"}
+    assert r2["dpb"]["ref_feature_el"].shape == (1, 48, H, W) and r2["dpb"]["ref_feature_bl"].shape == (1, 64, H // 2, W // 2)
+    assert isinstance(r2["bit_el"], float) and r2["bit_el"] > 0
