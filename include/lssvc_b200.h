@@ -47,6 +47,9 @@ typedef struct {
 #define LSSVC_IN_SQUARE 1 /* x*x, used by GDN's norm pool */
 #define LSSVC_IN_LRELU 2
 
+#define LSSVC_PREC_TF32 0   /* tensor core reads the fp32 operands as TF32 (10 mantissa bits)            */
+#define LSSVC_PREC_3XTF32 1 /* error-compensated: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32-reference parity */
+
 #define LSSVC_EPI_PLAIN 0
 #define LSSVC_EPI_GDN 1  /* out = gdn_x * rsqrt(acc + bias)   (gdn.py:29-44, video_net_component.py:83-105) */
 #define LSSVC_EPI_IGDN 2 /* out = gdn_x * sqrt(acc + bias)                                               */
@@ -63,7 +66,7 @@ typedef struct {
  *   out  = v                                (optionally through PixelShuffle(2))
  *   out2 = lrelu(v, slope2)                 (optional second copy, same addressing mode)
  *
- * weight is packed [kh*kw][n_pad][cin_total] (K-major rows), bias is [n_pad];
+ * weight is packed [kh*kw][n_pad][cin_total] (K-major rows, full fp32), bias is [n_pad];
  * cin_total = sum of src[i].C, n_pad = cout rounded up to 16.
  * With pixel_shuffle the packed output-channel order is (2*i + j) * (cout/4) + c for
  * reference channel 4*c + 2*i + j, so that each sub-pixel's channels are contiguous.
@@ -87,6 +90,10 @@ typedef struct {
   lssvc_view out2;
   float slope2;
   lssvc_view gdn_x;
+  /* tensor-core path only: LSSVC_PREC_*; weight_split is [2*kh*kw][n_pad][cin_total] = (w_hi taps | w_lo taps)
+   * with w_hi = w & 0xFFFFE000 (bitwise) and w_lo = w - w_hi, required for LSSVC_PREC_3XTF32 */
+  int32_t precision;
+  const float *weight_split;
 } lssvc_conv;
 
 /* ---- library ---------------------------------------------------------------------------- */

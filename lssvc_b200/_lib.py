@@ -13,6 +13,7 @@ MAX_SRC = 3
 ACT_NONE, ACT_LRELU = 0, 1
 IN_NONE, IN_SQUARE, IN_LRELU = 0, 1, 2
 EPI_PLAIN, EPI_GDN, EPI_IGDN = 0, 1, 2
+PREC_TF32, PREC_3XTF32 = 0, 1
 
 
 class LssvcError(RuntimeError):
@@ -43,6 +44,8 @@ class CConv(Structure):
         ("out2", CView),
         ("slope2", c_float),
         ("gdn_x", CView),
+        ("precision", c_int32),
+        ("weight_split", c_void_p),
     ]
 
 

@@ -11,10 +11,18 @@
 // [tap][n_pad][cin_total] fetched with a 3-D box.  Both land in the canonical K-major
 // SWIZZLE_{128,64,32}B layout (row = KC * 4 bytes), so the UMMA descriptors are the plain ones.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue
-// (TMEM -> registers -> bias / activation / residual / pixel-shuffle -> global).
-// Persistent over tiles; two TMEM accumulator buffers overlap the epilogue of tile i with the
-// MMAs of tile i + 1.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue
+// (TMEM -> registers -> bias / activation / residual / pixel-shuffle -> global), warps 6..9 operand
+// splitters (3xTF32 mode only).  Persistent over tiles; two TMEM accumulator buffers overlap the
+// epilogue of tile i with the MMAs of tile i + 1.
+//
+// Precision modes
+//   TF32   : operands are used as they are (the tensor core keeps 10 mantissa bits of each fp32).
+//   3xTF32 : error-compensated.  Weights are pre-split on the host into w_hi (exactly representable in
+//            TF32) and w_lo = w - w_hi; the splitter warps rewrite each landed A tile in shared memory as
+//            a_hi = a & 0xFFFFE000 and a_lo = a - a_hi, and the MMA warp issues
+//            a_hi*w_hi + a_lo*w_hi + a_hi*w_lo into the same fp32 TMEM accumulator (the dropped a_lo*w_lo
+//            term is below 2^-22 relative).  This is what gives the fp32-reference parity of the symbols.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -25,7 +33,8 @@ namespace {
 constexpr int TILE_H = 8;
 constexpr int TILE_W = 16;
 constexpr int MAX_STAGES = 8;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;
+constexpr int SPLIT_THREADS = 128;
 
 struct alignas(64) TcParams {
   CUtensorMap a_map[LSSVC_MAX_SRC];
@@ -38,6 +47,7 @@ struct alignas(64) TcParams {
   int tiles_x, tiles_y, n_tiles, n_tile;
   int cout;
   int stages, stage_bytes, tmem_cols;
+  int split;  // 1: 3xTF32
   const float *bias;
   int act;
   float slope;
@@ -80,6 +90,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[MAX_STAGES];
   __shared__ uint64_t empty_bar[MAX_STAGES];
+  __shared__ uint64_t ready_bar[MAX_STAGES];
   __shared__ uint64_t tfull_bar[2];
   __shared__ uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_slot;
@@ -97,6 +108,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&ready_bar[s]), SPLIT_THREADS);
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(ptx::smem_u32(&tfull_bar[b]), 1);
@@ -142,11 +154,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 const int px = dx - qx * p.stride;
                 const uint32_t full = ptx::smem_u32(&full_bar[stage]);
                 ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
-                ptx::mbar_expect_tx(full, static_cast<uint32_t>(A_BYTES + b_bytes));
+                ptx::mbar_expect_tx(full, static_cast<uint32_t>(A_BYTES + (p.split ? 2 : 1) * b_bytes));
                 const uint32_t a_dst = smem_base + static_cast<uint32_t>(stage * p.stage_bytes);
+                const uint32_t b_dst = a_dst + (p.split ? 2 : 1) * A_BYTES;
                 ptx::tma_load_5d(a_dst, &p.a_map[j], full, c * KC, px, ox0 + qx, py, oy0 + qy);
-                ptx::tma_load_3d(a_dst + A_BYTES, &p.b_map, full, p.coff[j] + c * KC, n0,
-                                 r * p.kw + s);
+                ptx::tma_load_3d(b_dst, &p.b_map, full, p.coff[j] + c * KC, n0, r * p.kw + s);
+                if (p.split)
+                  ptx::tma_load_3d(b_dst + b_bytes, &p.b_map, full, p.coff[j] + c * KC, n0,
+                                   p.kh * p.kw + r * p.kw + s);
                 if (++stage == p.stages) {
                   stage = 0;
                   phase ^= 1u;
@@ -169,16 +184,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.n_tile);
       for (int it = 0; it < iters; ++it) {
-        ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+        ptx::mbar_wait(ptx::smem_u32(p.split ? &ready_bar[stage] : &full_bar[stage]), phase);
         ptx::tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_base + static_cast<uint32_t>(stage * p.stage_bytes);
-          const uint32_t b_addr = a_addr + A_BYTES;
+          const uint32_t b_addr = a_addr + (p.split ? 2 : 1) * A_BYTES;
 #pragma unroll
           for (int kk = 0; kk < KC / 8; ++kk) {
             const uint64_t a_desc = ptx::make_kmajor_desc(a_addr + kk * 32, SBO, LAYOUT);
             const uint64_t b_desc = ptx::make_kmajor_desc(b_addr + kk * 32, SBO, LAYOUT);
             ptx::mma_tf32(d_tmem, a_desc, b_desc, idesc, (it | kk) != 0 ? 1u : 0u);
+            if (p.split) {
+              const uint64_t al_desc = ptx::make_kmajor_desc(a_addr + A_BYTES + kk * 32, SBO, LAYOUT);
+              const uint64_t bl_desc = ptx::make_kmajor_desc(b_addr + b_bytes + kk * 32, SBO, LAYOUT);
+              ptx::mma_tf32(d_tmem, al_desc, b_desc, idesc, 1u);
+              ptx::mma_tf32(d_tmem, a_desc, bl_desc, idesc, 1u);
+            }
           }
           ptx::mma_commit(ptx::smem_u32(&empty_bar[stage]));
           if (it == iters - 1) ptx::mma_commit(ptx::smem_u32(&tfull_bar[buf]));
@@ -191,6 +212,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       }
       buf ^= 1;
       if (buf == 0) acc_phase ^= 1u;
+    }
+  } else if (warp >= 6) {
+    // ------------------------------- operand splitters (3xTF32) ---------------------------
+    if (p.split) {
+      const int t = threadIdx.x - 6 * 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int it = 0; it < iters; ++it) {
+          ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+          uint8_t *a_hi = smem_raw + (smem_base - ptx::smem_u32(smem_raw)) + stage * p.stage_bytes;
+          uint8_t *a_lo = a_hi + A_BYTES;
+#pragma unroll
+          for (int off = 0; off < A_BYTES; off += SPLIT_THREADS * 16) {
+            float4 v = *reinterpret_cast<const float4 *>(a_hi + off + t * 16);
+            float4 h;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            *reinterpret_cast<float4 *>(a_hi + off + t * 16) = h;
+            *reinterpret_cast<float4 *>(a_lo + off + t * 16) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(ptx::smem_u32(&ready_bar[stage]));
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
     }
   } else {
     // ------------------------------- epilogue ---------------------------------------------
@@ -360,6 +412,10 @@ extern "C" int32_t lssvc_conv_tc(const lssvc_conv *c, void *stream) {
   LSSVC_REQUIRE(c->n_pad % 16 == 0 && c->n_pad >= c->cout, "conv_tc: n_pad=%d cout=%d", c->n_pad, c->cout);
   LSSVC_REQUIRE((reinterpret_cast<uintptr_t>(c->weight) & 15) == 0 && (reinterpret_cast<uintptr_t>(c->bias) & 15) == 0,
                 "conv_tc: weight/bias not 16-byte aligned");
+  LSSVC_REQUIRE(c->precision == LSSVC_PREC_TF32 || c->precision == LSSVC_PREC_3XTF32, "conv_tc: precision %d", c->precision);
+  LSSVC_REQUIRE(c->precision != LSSVC_PREC_3XTF32 ||
+                    (c->weight_split && (reinterpret_cast<uintptr_t>(c->weight_split) & 15) == 0),
+                "conv_tc: 3xTF32 needs the hi|lo split weights");
 
   int n_tile = c->n_pad;
   if (n_tile > 256) {
@@ -405,12 +461,14 @@ extern "C" int32_t lssvc_conv_tc(const lssvc_conv *c, void *stream) {
   }
   {
     const int taps = c->kh * c->kw;
+    const bool split = c->precision == LSSVC_PREC_3XTF32;
     const cuuint64_t dims[3] = {static_cast<cuuint64_t>(cin_total), static_cast<cuuint64_t>(c->n_pad),
-                                static_cast<cuuint64_t>(taps)};
+                                static_cast<cuuint64_t>(split ? 2 * taps : taps)};
     const cuuint64_t strides[2] = {static_cast<cuuint64_t>(cin_total) * 4,
                                    static_cast<cuuint64_t>(cin_total) * 4 * c->n_pad};
     const cuuint32_t box[3] = {static_cast<cuuint32_t>(kc), static_cast<cuuint32_t>(n_tile), 1};
-    CUresult r = g_encode(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(c->weight), dims, strides,
+    const float *wsrc = split ? c->weight_split : c->weight;
+    CUresult r = g_encode(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(wsrc), dims, strides,
                           box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc),
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -426,7 +484,8 @@ extern "C" int32_t lssvc_conv_tc(const lssvc_conv *c, void *stream) {
   p.n_tile = n_tile;
   p.cout = c->cout;
   const int row_bytes = kc * 4;
-  p.stage_bytes = ((TILE_H * TILE_W + n_tile) * row_bytes + 1023) & ~1023;
+  p.split = c->precision == LSSVC_PREC_3XTF32 ? 1 : 0;
+  p.stage_bytes = (((TILE_H * TILE_W + n_tile) * row_bytes * (p.split ? 2 : 1)) + 1023) & ~1023;
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   LSSVC_REQUIRE(p.stages >= 2, "conv_tc: stage of %d bytes does not fit twice", p.stage_bytes);

@@ -1,6 +1,7 @@
 """Host-side operator layer: NHWC views over torch-owned device memory and thin wrappers that hand raw
 pointers to the C-ABI kernels.  torch is used for allocation and stream handles only."""
 import ctypes
+import os
 
 import torch
 
@@ -105,7 +106,8 @@ def _cv(v):
 class PackedConv:
     """Weights of one Conv2d repacked for the kernels: [kh*kw][n_pad][cin_total] + bias[n_pad]."""
 
-    __slots__ = ("weight", "bias", "kh", "kw", "stride", "pad", "cout", "n_pad", "cin_total", "src_c", "pixel_shuffle")
+    __slots__ = ("weight", "bias", "kh", "kw", "stride", "pad", "cout", "n_pad", "cin_total", "src_c", "pixel_shuffle",
+                 "_split")
 
     def __init__(self, w, b, stride=1, pad=None, src_channels=None, pixel_shuffle=False, transposed=False, device=None):
         """w: [Cout, Cin, kh, kw] (Conv2d) or, with transposed=True, a stride-1 ConvTranspose2d weight
@@ -143,21 +145,63 @@ class PackedConv:
         self.cout, self.n_pad, self.cin_total = cout, n_pad, cin_total
         self.src_c = [v for _, v in src_channels]
         self.pixel_shuffle = pixel_shuffle
+        self._split = None
+
+    def weight_split(self):
+        """(w_hi | w_lo) along the tap axis for the 3xTF32 kernel: w_hi keeps the 10 TF32 mantissa bits exactly."""
+        if self._split is None:
+            hi = (self.weight.view(torch.int32) & -8192).view(torch.float32)
+            self._split = torch.cat([hi, self.weight - hi], dim=0).contiguous()
+        return self._split
 
 
-_FORCE_SIMT = False
+# Convolution engines:
+#   "simt" fp32 CUDA cores (exact fp32 arithmetic)
+#   "tc"   tcgen05 kind::tf32, operands truncated to TF32 by the tensor core (fast, ~5e-4 relative error per conv)
+#   "tc3"  tcgen05 kind::tf32, error-compensated 3xTF32 (fp32-level accuracy: the parity configuration)
+ENGINES = {
+    "simt": {"kernel": "conv_simt_kernel", "dtype": "f32", "peak_vs_bf16": 0.5,
+             "note": "fp32 FMA on CUDA cores (no tensor cores); shown against the TF32 tensor peak for comparison"},
+    "tc": {"kernel": "conv_tc_kernel", "dtype": "tf32", "peak_vs_bf16": 0.5,
+           "note": "tcgen05.mma kind::tf32, fp32 accumulate in TMEM"},
+    "tc3": {"kernel": "conv_tc_kernel(3xTF32)", "dtype": "tf32x3", "peak_vs_bf16": 0.5,
+            "note": "tcgen05.mma kind::tf32 error-compensated 3xTF32 (3 MMAs per algorithmic MAC); FLOPs counted are algorithmic"},
+}
+_ENGINE = os.environ.get("LSSVC_CONV_ENGINE", "tc3")
+assert _ENGINE in ENGINES, _ENGINE
+
+
+def default_engine():
+    return _ENGINE
+
+
+def set_engine(name):
+    global _ENGINE
+    assert name in ENGINES, name
+    prev, _ENGINE = _ENGINE, name
+    return prev
+
+
+def engine_info(name):
+    return ENGINES[name]
 
 
 def force_simt(flag):
     """Route every convolution through the fp32 CUDA-core kernel (on-device cross-check of tcgen05)."""
-    global _FORCE_SIMT
-    _FORCE_SIMT = bool(flag)
+    global _ENGINE, _SAVED
+    if flag:
+        _SAVED = set_engine("simt")
+    else:
+        set_engine(_SAVED)
+
+
+_SAVED = _ENGINE
 
 
 def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, out_scale=1.0,
          in_transform=_lib.IN_NONE, in_slope=0.0, epi=_lib.EPI_PLAIN, gdn_x=None, engine=None):
     """Run one packed convolution.  act: None or the LeakyReLU slope (0.0 = ReLU).
-    engine: None (auto), 'tc' or 'simt'."""
+    engine: None (the default engine), 'tc3', 'tc' or 'simt'."""
     if isinstance(srcs, View):
         srcs = [srcs]
     assert len(srcs) == len(pc.src_c), (len(srcs), pc.src_c)
@@ -178,15 +222,22 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
     d.res1, d.res2, d.out2, d.gdn_x = _cv(res1), _cv(res2), _cv(out2), _cv(gdn_x)
     d.slope2 = float(slope2)
     lib = _lib.load()
-    if engine is None:
-        tc_ok = (not _FORCE_SIMT and in_transform == _lib.IN_NONE and epi == _lib.EPI_PLAIN
+    engine = engine or _ENGINE
+    if engine != "simt":
+        tc_ok = (in_transform == _lib.IN_NONE and epi == _lib.EPI_PLAIN
                  and all(s.C % 8 == 0 and s.pitch % 4 == 0 and (s.coff % 4 == 0) for s in srcs)
                  and pc.stride in (1, 2) and srcs[0].H % pc.stride == 0 and srcs[0].W % pc.stride == 0)
-        engine = "tc" if tc_ok else "simt"
-    if engine == "tc":
-        _lib.check(lib.lssvc_conv_tc(byref(d), _stream()), "conv_tc")
-    else:
+        if not tc_ok:
+            engine = "simt"
+    if engine == "simt":
         _lib.check(lib.lssvc_conv_simt(byref(d), _stream()), "conv_simt")
+    else:
+        if engine == "tc3":
+            d.precision = _lib.PREC_3XTF32
+            d.weight_split = pc.weight_split().data_ptr()
+        else:
+            d.precision = _lib.PREC_TF32
+        _lib.check(lib.lssvc_conv_tc(byref(d), _stream()), "conv_tc")
     return out
 
 

@@ -108,6 +108,25 @@ def test_conv_tc(case, extras, cuda_device):
     assert err < 2e-3, err
 
 
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("extras", [False, True], ids=["plain", "epilogue"])
+def test_conv_tc3(case, extras, cuda_device):
+    """Error-compensated 3xTF32: fp32-level accuracy (same bound as the fp32 CUDA-core kernel, x2 for the dropped
+    lo*lo term and the tensor core's accumulation order)."""
+    err = _run_conv_case(case, "tc3", cuda_device, extras)
+    print(f"tcgen05 3xTF32 conv {case[0]} rel err {err:.3e}")
+    assert err < 2e-5, err
+
+
+def test_conv_tc3_large_persistent(cuda_device):
+    err = _run_conv_case(("big", [64], [64], 64, 3, 1, 256, 320, False), "tc3", cuda_device, True)
+    assert err < 2e-5, err
+    err = _run_conv_case(("big48", [48, 48], [48, 48], 48, 3, 1, 200, 312, False), "tc3", cuda_device, False)
+    assert err < 2e-5, err
+    err = _run_conv_case(("big256", [128], [128], 256, 3, 1, 96, 160, True), "tc3", cuda_device, False)
+    assert err < 2e-5, err
+
+
 def test_conv_tc_large_persistent(cuda_device):
     """More tiles than SMs: exercises the persistent loop, TMEM double buffering and barrier phase wrap."""
     err = _run_conv_case(("big", [64], [64], 64, 3, 1, 256, 320, False), "tc", cuda_device, True)

@@ -2,9 +2,11 @@
 synthetic frames and weights, through the public model API.
 
 Tolerances (BASELINE.json north_star): reconstructions within 1e-3 max-abs, quantised symbols >= 99.99 % equal,
-per-layer bits within 0.1 %.  They are asserted for the fp32 CUDA-core configuration (exact fp32 arithmetic);
-the tcgen05 TF32 configuration is asserted at the looser bounds written next to each check and its measured
-deviations are printed ("precision")."""
+per-layer bits within 0.1 %.  They are asserted for the two fp32-accurate configurations: "tc3" (tcgen05
+error-compensated 3xTF32, the default) and "simt" (fp32 CUDA cores).  The plain-TF32 tensor-core configuration
+("tc") flips a fraction of the quantised symbols, each of which moves the reconstruction by O(0.1) with random
+weights, so it is only checked for the bits (1 %) and its measured deviations are printed ("precision")."""
+TOL = {"simt": (1e-3, 0.9999, 1e-3), "tc3": (1e-3, 0.9999, 1e-3), "tc": (None, 0.9, 1e-2)}
 import pytest
 import torch
 
@@ -52,9 +54,9 @@ def _match(name, got, ref):
     return m
 
 
-def _run_intra(s, simt):
+def _run_intra(s, engine):
     from lssvc_b200 import ops
-    ops.force_simt(simt)
+    prev = ops.set_engine(engine)
     try:
         net = s["net_i"]
         net._debug = {}
@@ -62,14 +64,14 @@ def _run_intra(s, simt):
         r = net.encode_decode(x_bl.to(s["dev"]), x_el.to(s["dev"]), None, None, H // 2, W // 2, H, W)
         dbg = {k: v for k, v in net._debug.items()}
     finally:
-        ops.force_simt(False)
+        ops.set_engine(prev)
         s["net_i"]._debug = None
     return r, dbg
 
 
-def _run_inter(s, simt, frame, dpb_cpu):
+def _run_inter(s, engine, frame, dpb_cpu):
     from lssvc_b200 import ops
-    ops.force_simt(simt)
+    prev = ops.set_engine(engine)
     try:
         net = s["net_p"]
         net._debug = {}
@@ -78,20 +80,23 @@ def _run_inter(s, simt, frame, dpb_cpu):
         r = net.encode_decode(x_bl.to(s["dev"]), x_el.to(s["dev"]), dpb, None, None, W, H, W // 2, H // 2)
         dbg = {k: v for k, v in net._debug.items()}
     finally:
-        ops.force_simt(False)
+        ops.set_engine(prev)
         s["net_p"]._debug = None
     return r, dbg
 
 
-@pytest.mark.parametrize("simt", [True, False], ids=["fp32_simt", "tf32_tcgen05"])
-def test_intra_frame_parity(setup, simt):
+def _lt(value, tol):
+    return tol is None or value < tol
+
+
+@pytest.mark.parametrize("engine", ["tc3", "simt", "tc"])
+def test_intra_frame_parity(setup, engine):
     s, o = setup, setup["o_i"]
-    r, dbg = _run_intra(s, simt)
-    print(f"I-frame ({'fp32 CUDA cores' if simt else 'tcgen05 TF32'}): bits {r['bit_bl']:.1f}/{r['bit_el']:.1f} "
-          f"oracle {o['bit_bl']:.1f}/{o['bit_el']:.1f}")
-    tol_rec, tol_sym, tol_bits = (1e-3, 0.9999, 1e-3) if simt else (2e-2, 0.98, 1e-2)
-    assert _cmp("x_hat_bl", r["x_hat_bl"], o["x_hat_bl"]) < tol_rec
-    assert _cmp("x_hat_el", r["x_hat_el"], o["x_hat_el"]) < tol_rec
+    r, dbg = _run_intra(s, engine)
+    print(f"I-frame ({engine}): bits {r['bit_bl']:.1f}/{r['bit_el']:.1f} oracle {o['bit_bl']:.1f}/{o['bit_el']:.1f}")
+    tol_rec, tol_sym, tol_bits = TOL[engine]
+    assert _lt(_cmp("x_hat_bl", r["x_hat_bl"], o["x_hat_bl"]), tol_rec)
+    assert _lt(_cmp("x_hat_el", r["x_hat_el"], o["x_hat_el"]), tol_rec)
     _cmp("feature_el", r["feature_el"], o["feature_el"])
     sym_ref = torch.round(o["y"] - o["means"])
     sym_got = torch.round(dbg["y_hat"].to_nchw().cpu() - dbg["params_el"].slice(96, 192).to_nchw().cpu())
@@ -102,20 +107,19 @@ def test_intra_frame_parity(setup, simt):
     assert abs(r["bit_el"] - o["bit_el"]) / o["bit_el"] < tol_bits
 
 
-@pytest.mark.parametrize("simt", [True, False], ids=["fp32_simt", "tf32_tcgen05"])
+@pytest.mark.parametrize("engine", ["tc3", "simt", "tc"])
 @pytest.mark.parametrize("which", ["first_p", "second_p"])
-def test_inter_frame_parity_teacher_forced(setup, simt, which):
+def test_inter_frame_parity_teacher_forced(setup, engine, which):
     s = setup
     frame, dpb, o = (1, s["dpb1"], s["o_p1"]) if which == "first_p" else (2, s["dpb2"], s["o_p2"])
-    r, dbg = _run_inter(s, simt, frame, dpb)
-    print(f"P-frame {which} ({'fp32 CUDA cores' if simt else 'tcgen05 TF32'}): bits {r['bit_bl']:.1f}/{r['bit_el']:.1f} "
-          f"oracle {o['bit_bl']:.1f}/{o['bit_el']:.1f}")
-    tol_rec, tol_sym, tol_bits = (1e-3, 0.9999, 1e-3) if simt else (2e-2, 0.98, 1e-2)
-    assert _cmp("BL mv_hat", dbg["bl_mv_hat"].to_nchw(), o["bl"]["mv_hat"]) < tol_rec * 10
-    assert _cmp("ref_frame_bl", r["dpb"]["ref_frame_bl"], o["dpb"]["ref_frame_bl"]) < tol_rec
-    assert _cmp("mv_hat", r["mv_hat"], o["mv_hat"]) < tol_rec * 10
-    assert _cmp("warp_frame", r["warp_frame"], o["warp_frame"]) < tol_rec
-    assert _cmp("ref_frame_el", r["dpb"]["ref_frame_el"], o["dpb"]["ref_frame_el"]) < tol_rec
+    r, dbg = _run_inter(s, engine, frame, dpb)
+    print(f"P-frame {which} ({engine}): bits {r['bit_bl']:.1f}/{r['bit_el']:.1f} oracle {o['bit_bl']:.1f}/{o['bit_el']:.1f}")
+    tol_rec, tol_sym, tol_bits = TOL[engine]
+    assert _lt(_cmp("BL mv_hat", dbg["bl_mv_hat"].to_nchw(), o["bl"]["mv_hat"]), tol_rec)
+    assert _lt(_cmp("ref_frame_bl", r["dpb"]["ref_frame_bl"], o["dpb"]["ref_frame_bl"]), tol_rec)
+    assert _lt(_cmp("mv_hat", r["mv_hat"], o["mv_hat"]), tol_rec)
+    assert _lt(_cmp("warp_frame", r["warp_frame"], o["warp_frame"]), tol_rec)
+    assert _lt(_cmp("ref_frame_el", r["dpb"]["ref_frame_el"], o["dpb"]["ref_frame_el"]), tol_rec)
     _cmp("ref_feature_bl", r["dpb"]["ref_feature_bl"], o["dpb"]["ref_feature_bl"])
     _cmp("ref_feature_el", r["dpb"]["ref_feature_el"], o["dpb"]["ref_feature_el"])
     assert _match("EL y_q", dbg["y_q"].to_nchw(), o["four_part"]["y_q"]) >= tol_sym
@@ -131,7 +135,7 @@ def test_inter_frame_parity_teacher_forced(setup, simt, which):
 def test_dpb_roundtrip_and_inplace_clamp(setup):
     """The caller clamps the returned reference frames in place and hands the dict back (test.py:249-250)."""
     s = setup
-    r1, _ = _run_inter(s, False, 1, s["dpb1"])
+    r1, _ = _run_inter(s, "tc3", 1, s["dpb1"])
     dpb = r1["dpb"]
     dpb["ref_frame_bl"].clamp_(0, 1)
     dpb["ref_frame_el"].clamp_(0, 1)
