@@ -91,7 +91,7 @@ typedef struct {
   float slope2;
   lssvc_view gdn_x;
   /* tensor-core path only: LSSVC_PREC_*; weight_split is [2*kh*kw][n_pad][cin_total] = (w_hi taps | w_lo taps)
-   * with w_hi = w & 0xFFFFE000 (bitwise) and w_lo = w - w_hi, required for LSSVC_PREC_3XTF32 */
+   * with w_hi = rn_tf32(w) and w_lo = rn_tf32(w - w_hi), required for LSSVC_PREC_3XTF32 */
   int32_t precision;
   const float *weight_split;
 } lssvc_conv;

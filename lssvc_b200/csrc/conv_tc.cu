@@ -18,9 +18,9 @@
 //
 // Precision modes
 //   TF32   : operands are used as they are (the tensor core keeps 10 mantissa bits of each fp32).
-//   3xTF32 : error-compensated.  Weights are pre-split on the host into w_hi (exactly representable in
-//            TF32) and w_lo = w - w_hi; the splitter warps rewrite each landed A tile in shared memory as
-//            a_hi = a & 0xFFFFE000 and a_lo = a - a_hi, and the MMA warp issues
+//   3xTF32 : error-compensated.  Weights are pre-split on the host into w_hi = rn_tf32(w) and
+//            w_lo = rn_tf32(w - w_hi); the splitter warps rewrite each landed A tile in shared memory as
+//            a_hi = rn_tf32(a) and a_lo = rn_tf32(a - a_hi), and the MMA warp issues
 //            a_hi*w_hi + a_lo*w_hi + a_hi*w_lo into the same fp32 TMEM accumulator (the dropped a_lo*w_lo
 //            term is below 2^-22 relative).  This is what gives the fp32-reference parity of the symbols.
 #include <cuda.h>
@@ -226,14 +226,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           uint8_t *a_lo = a_hi + A_BYTES;
 #pragma unroll
           for (int off = 0; off < A_BYTES; off += SPLIT_THREADS * 16) {
-            float4 v = *reinterpret_cast<const float4 *>(a_hi + off + t * 16);
-            float4 h;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            *reinterpret_cast<float4 *>(a_hi + off + t * 16) = h;
-            *reinterpret_cast<float4 *>(a_lo + off + t * 16) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            const float4 v = *reinterpret_cast<const float4 *>(a_hi + off + t * 16);
+            // hi = rn_tf32(a); lo = rn_tf32(a - hi): both exactly representable, so the tensor core's own
+            // fp32 -> TF32 conversion is the identity and the split error is unbiased (< 2^-22 |a|)
+            const float hx = ptx::rn_tf32(v.x), hy = ptx::rn_tf32(v.y), hz = ptx::rn_tf32(v.z), hw = ptx::rn_tf32(v.w);
+            *reinterpret_cast<float4 *>(a_hi + off + t * 16) = make_float4(hx, hy, hz, hw);
+            *reinterpret_cast<float4 *>(a_lo + off + t * 16) =
+                make_float4(ptx::rn_tf32(v.x - hx), ptx::rn_tf32(v.y - hy), ptx::rn_tf32(v.z - hz), ptx::rn_tf32(v.w - hw));
           }
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(ptx::smem_u32(&ready_bar[stage]));

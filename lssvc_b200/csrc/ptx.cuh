@@ -24,6 +24,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// fp32 -> nearest TF32 (10 mantissa bits, ties away from zero), returned as an fp32 bit pattern
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // ---- mbarrier ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

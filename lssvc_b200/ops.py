@@ -148,10 +148,11 @@ class PackedConv:
         self._split = None
 
     def weight_split(self):
-        """(w_hi | w_lo) along the tap axis for the 3xTF32 kernel: w_hi keeps the 10 TF32 mantissa bits exactly."""
+        """(w_hi | w_lo) along the tap axis for the 3xTF32 kernel: w_hi = rn_tf32(w), w_lo = rn_tf32(w - w_hi)."""
         if self._split is None:
-            hi = (self.weight.view(torch.int32) & -8192).view(torch.float32)
-            self._split = torch.cat([hi, self.weight - hi], dim=0).contiguous()
+            rn = lambda t: ((t.view(torch.int32) + 4096) & -8192).view(torch.float32)
+            hi = rn(self.weight)
+            self._split = torch.cat([hi, rn(self.weight - hi)], dim=0).contiguous()
         return self._split
 
 
