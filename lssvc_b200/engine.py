@@ -85,6 +85,7 @@ class Engine(nets.ParamBag):
         if act_copy is not None:
             out2 = act_copy_out if act_copy_out is not None else self.new(Ho * f, Wo * f, C)
         ex = lambda v: None if v is None else v.exact()
+        ops.TRACE_NAME = name
         ops.conv(pc, srcs, out.exact(), act=act, res1=ex(res1), res2=ex(res2), out2=ex(out2),
                  slope2=0.0 if act_copy is None else act_copy, out_scale=out_scale, engine=engine)
         return (out, out2) if act_copy is not None else out

@@ -30,6 +30,30 @@ def _dbg(model, **views):
         d.update(views)
 
 
+def _force(model, key, out, mean=None, mask=None, q_view=None):
+    """Test hook (symbol teacher-forcing): when model._force holds reference symbols under `key`, count how many of
+    the symbols just produced differ and overwrite `out` (= symbols + mean) with the reference symbols, so that
+    everything downstream can be compared with the oracle even when a value sitting on a rounding boundary flipped.
+    Host-side torch indexing on the strided NHWC views; never active outside tests."""
+    f = getattr(model, "_force", None)
+    if not f or key not in f:
+        return
+    ref = f[key].to(model.device)[0].permute(1, 2, 0)
+    dst = out.exact().as_tensor()
+    if q_view is not None:
+        # progressive coding (four-part prior): out = symbols + means on `mask`, symbols kept in q_view
+        q = q_view.exact().as_tensor()
+        delta = torch.where(mask & (q != ref), ref - q, torch.zeros_like(q))
+        model._force_flips[key] = model._force_flips.get(key, 0) + int((delta != 0).sum().item())
+        dst.add_(delta)
+        q.add_(delta)
+        return
+    m = mean.as_tensor() if mean is not None else None
+    got = torch.round(dst - m) if m is not None else dst
+    model._force_flips[key] = int((got != ref).sum().item())
+    dst.copy_(ref + m if m is not None else ref)
+
+
 class _Bits:
     """Device-side double accumulators for the per-layer bit counts of one frame."""
 
@@ -227,6 +251,7 @@ class IntraSS(Engine):
         w = _write
         ops.eb_quant(z_bl, self._eb_coef("base_layer_model.entropy_bottleneck."), z_hat_bl, bits.ptr(0),
                      sym=w.buf("bl_z", z_bl) if w else None)
+        _force(self, "bl_z_hat", z_hat_bl)
         prm = self._bl_params(z_hat_bl)
         C = y_bl.real
         y_hat_bl = self.new(y_bl.H, y_bl.W, C)
@@ -234,18 +259,22 @@ class IntraSS(Engine):
         ops.gaussian_quant(y_bl, prm.slice(C, 2 * C), prm.slice(0, C), y_hat_bl, bits.ptr(0),
                            sym=w.buf("bl_y", y_bl) if w else None, index=w.buf("bl_y_idx", y_bl) if w else None,
                            thresholds=thr if w else None)
+        _force(self, "bl_y_q", y_hat_bl, mean=prm.slice(C, 2 * C))
+        _dbg(self, params_bl=prm)
         x_hat_bl = self._bl_synthesis(y_hat_bl)
         # ---- enhancement layer
         c1, c2, c3 = self._context_mining(x_hat_bl)
         y, z = self._el_analysis(xe, c1, c2, c3)
         z_hat = self.new(z.H, z.W, z.real)
         ops.eb_quant(z, self._eb_coef("entropy_bottleneck."), z_hat, bits.ptr(1), sym=w.buf("el_z", z) if w else None)
+        _force(self, "z_hat", z_hat)
         prm = self._el_params(z_hat, y_hat_bl, c3)
         C = y.real
         y_hat = self.new(y.H, y.W, C)
         ops.gaussian_quant(y, prm.slice(C, 2 * C), prm.slice(0, C), y_hat, bits.ptr(1),
                            sym=w.buf("el_y", y) if w else None, index=w.buf("el_y_idx", y) if w else None,
                            thresholds=thr if w else None)
+        _force(self, "y_q", y_hat, mean=prm.slice(C, 2 * C))
         res_hat = self._res_decoder_gdn("g_s", y_hat, c2, c3, intra=True)
         feature, x_hat = self._recon_generation("recon_net", res_hat, c1)
         _dbg(self, y_bl=y_bl, y_hat_bl=y_hat_bl, z_hat_bl=z_hat_bl, y=y, y_hat=y_hat, z_hat=z_hat, params_el=prm,
@@ -373,12 +402,14 @@ class LSSVC(Engine):
         mv_z_hat = self.new(mv_z.H, mv_z.W, mv_z.real)
         ops.bitparm_quant(mv_z, self._bitparm_coef(p + "bit_estimator_z_mv."), mv_z_hat, bits.ptr(0),
                           sym=w.buf("bl_mv_z", mv_z) if w else None)
+        _force(self, "bl_mv_z_hat", mv_z_hat)
         mv_prm = self._bl_mv_params(p, mv_z_hat)
         C = mv_y.real
         mv_y_hat = self.new(mv_y.H, mv_y.W, C)
         ops.laplace_quant(mv_y, mv_prm.slice(C, 2 * C), mv_prm.slice(0, C), None, mv_y_hat, bits.ptr(0),
                           sym=w.buf("bl_mv_y", mv_y) if w else None, index=w.buf("bl_mv_y_idx", mv_y) if w else None,
                           thresholds=thr)
+        _force(self, "bl_mv_y_q", mv_y_hat, mean=mv_prm.slice(C, 2 * C))
         mv_hat = self._bl_mv_decode(p, mv_y_hat)
         c1, c2, c3 = self._bl_contexts(p, ref_frame, ref_feature, mv_hat)
         y = self._res_encoder_gdn(p + "res_encoder", xb, c1, c2, c3, intra=False)
@@ -386,11 +417,13 @@ class LSSVC(Engine):
         z_hat = self.new(z.H, z.W, z.real)
         ops.bitparm_quant(z, self._bitparm_coef(p + "bit_estimator_z."), z_hat, bits.ptr(0),
                           sym=w.buf("bl_z", z) if w else None)
+        _force(self, "bl_z_hat", z_hat)
         prm = self._bl_res_params(p, z_hat, c1, c2, c3)
         C = y.real
         y_hat = self.new(y.H, y.W, C)
         ops.laplace_quant(y, prm.slice(C, 2 * C), prm.slice(0, C), None, y_hat, bits.ptr(0),
                           sym=w.buf("bl_y", y) if w else None, index=w.buf("bl_y_idx", y) if w else None, thresholds=thr)
+        _force(self, "bl_y_q", y_hat, mean=prm.slice(C, 2 * C))
         rec_feat = self._res_decoder_gdn(p + "res_decoder", y_hat, c2, c3, intra=False)
         feature, recon = self._recon_generation(p + "recon_generation_net", rec_feat, c1)
         _dbg(self, bl_mv_y=mv_y, bl_mv_y_hat=mv_y_hat, bl_mv_prm=mv_prm, bl_mv_z_hat=mv_z_hat, bl_y=y, bl_y_hat=y_hat,
@@ -559,6 +592,9 @@ class LSSVC(Engine):
             ops.four_part_step(y, prm, step, y_hat, y_q, s_hat, bits.ptr(1),
                                sym=w.buf(f"el_y{step}", y, C // 4) if w else None,
                                index=w.buf(f"el_y{step}_idx", y, C // 4) if w else None, thresholds=thr)
+            if y_q is not None and getattr(self, "_force", None) and "y_q" in self._force:
+                # coded-so-far positions are the ones with a (strictly positive) scale recorded
+                _force(self, "y_q", y_hat, mask=s_hat.exact().as_tensor() != 0, q_view=y_q)
             if step < 3:
                 prm = self._spatial_prior(step + 1, y_hat, common)
         return y_hat
@@ -624,12 +660,14 @@ class LSSVC(Engine):
         mv_z_hat = self.new(mv_z.H, mv_z.W, mv_z.real)
         ops.bitparm_quant(mv_z, self._bitparm_coef("bit_estimator_z_mv."), mv_z_hat, bits.ptr(1),
                           sym=w.buf("el_mv_z", mv_z) if w else None)
+        _force(self, "mv_z_hat", mv_z_hat)
         mv_prm = self._mv_params(mv_z_hat, mv_ctx_prior)
         C = mv_y.real
         mv_y_hat = self.new(mv_y.H, mv_y.W, C)
         ops.laplace_quant(mv_y, mv_prm.slice(C, 2 * C), mv_prm.slice(0, C), None, mv_y_hat, bits.ptr(1),
                           sym=w.buf("el_mv_y", mv_y) if w else None, index=w.buf("el_mv_y_idx", mv_y) if w else None,
                           thresholds=self._thr() if w else None)
+        _force(self, "mv_y_q", mv_y_hat, mean=mv_prm.slice(C, 2 * C))
         mv_hat = self._mv_decode(mv_y_hat, mv_ctx)
         # contexts, residual coding
         c1, c2, c3, warp_frame = self._hybrid_contexts(bl["feature"], mv_hat, re, fe)
@@ -637,6 +675,7 @@ class LSSVC(Engine):
         z_hat = self.new(z.H, z.W, z.real)
         ops.bitparm_quant(z, self._bitparm_coef("bit_estimator_z."), z_hat, bits.ptr(1),
                           sym=w.buf("el_z", z) if w else None)
+        _force(self, "z_hat", z_hat)
         params = self._res_params(z_hat, c3, bl["y_hat"])
         y_hat = self._four_part(y, params, bits, w)
         feature, recon = self._res_decode(y_hat, c1, c2, c3)

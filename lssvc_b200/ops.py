@@ -199,6 +199,11 @@ def force_simt(flag):
 _SAVED = _ENGINE
 
 
+# Optional launch trace (tools/join_launches.py): when TRACE is a list every conv appends its shape and engine.
+TRACE = None
+TRACE_NAME = None
+
+
 def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, out_scale=1.0,
          in_transform=_lib.IN_NONE, in_slope=0.0, epi=_lib.EPI_PLAIN, gdn_x=None, engine=None):
     """Run one packed convolution.  act: None or the LeakyReLU slope (0.0 = ReLU).
@@ -230,6 +235,11 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
                  and pc.stride in (1, 2) and srcs[0].H % pc.stride == 0 and srcs[0].W % pc.stride == 0)
         if not tc_ok:
             engine = "simt"
+    if TRACE is not None:
+        Ho, Wo = (out.H // 2, out.W // 2) if pc.pixel_shuffle else (out.H, out.W)
+        TRACE.append({"name": TRACE_NAME, "engine": engine, "k": pc.kh, "stride": pc.stride, "cin": pc.cin_total,
+                      "src_c": list(pc.src_c), "cout": pc.cout, "Ho": Ho, "Wo": Wo, "ps": bool(pc.pixel_shuffle),
+                      "flops": 2.0 * Ho * Wo * pc.kh * pc.kw * sum(s.real for s in srcs) * pc.cout})
     if engine == "simt":
         _lib.check(lib.lssvc_conv_simt(byref(d), _stream()), "conv_simt")
     else:

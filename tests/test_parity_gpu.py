@@ -2,17 +2,26 @@
 synthetic frames and weights, through the public model API.
 
 Tolerances (BASELINE.json north_star): reconstructions within 1e-3 max-abs, quantised symbols >= 99.99 % equal,
-per-layer bits within 0.1 %.  They are asserted for the two fp32-accurate configurations: "tc3" (tcgen05
-error-compensated 3xTF32, the default) and "simt" (fp32 CUDA cores).  The plain-TF32 tensor-core configuration
-("tc") flips a fraction of the quantised symbols, each of which moves the reconstruction by O(0.1) with random
-weights, so it is only checked for the bits (1 %) and its measured deviations are printed ("precision")."""
+per-layer bits within 0.1 %.  They are asserted for the two fp32-accurate configurations: the default tensor-core
+engine (tcgen05, error-compensated split operands) and "simt" (fp32 CUDA cores).  The plain-TF32 tensor-core
+configuration ("tc") flips a fraction of the quantised symbols, each of which moves the reconstruction by O(0.1) with
+random weights, so it is only checked for the bits (2 %) and its measured deviations are printed (DESIGN.md,
+"precision").
+
+Every frame is coded twice.  (1) Teacher-forced on the symbols: after each quantiser the oracle's symbols replace the
+ones just produced (model._force) and the replaced ones are counted — this is the symbol-match figure (every latent
+tensor is judged given correct upstream symbols, as a decoder would see them), and because a value sitting on a .5
+rounding boundary that legitimately flipped (allowed: <= 0.01 % of symbols) no longer makes everything downstream of
+it incomparable, the reconstructions and bit counts of this run must meet the 1e-3 / 0.1 % bounds strictly.
+(2) Free-running: printed for information (one early flip cascades through the rest of the frame), asserted bit-exact
+only for the fp32 CUDA-core engine."""
 TOL = {"simt": (1e-3, 0.9999, 1e-3), "tc3": (1e-3, 0.9999, 1e-3), "tc": (None, 0.8, 2e-2)}
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
-H = W = 128
+H = W = 256
 
 
 @pytest.fixture(scope="module")
@@ -42,127 +51,166 @@ def setup(cuda_device):
                 dev=cuda_device)
 
 
-def _cmp(name, got, ref):
+def _cmp(name, got, ref, tol=None):
     d = (got.cpu() - ref).abs().max().item()
     print(f"  {name:14s} max|d| {d:.3e}  (ref absmax {ref.abs().max().item():.3g})")
+    assert tol is None or d < tol, f"{name}: max|d| {d:.3e} >= {tol}"
     return d
 
 
-def _match(name, got, ref):
-    m = (got.cpu() == ref).float().mean().item()
-    print(f"  {name:14s} equal {100 * m:.4f} %")
-    return m
+class _Symbols:
+    """Pools the quantised symbols of one frame: (equal, total) per tensor and overall."""
+
+    def __init__(self):
+        self.bad = self.total = 0
+
+    def add(self, name, got, ref):
+        got = got.cpu()
+        bad = int((got != ref).sum().item())
+        self.bad += bad
+        self.total += ref.numel()
+        print(f"  {name:14s} equal {100 * (1 - bad / ref.numel()):.4f} %  ({bad} of {ref.numel()} differ)")
+
+    def fraction(self):
+        return 1.0 - self.bad / self.total
 
 
-def _run_intra(s, engine):
+def _run_intra(s, engine, force=None):
     from lssvc_b200 import ops
     prev = ops.set_engine(engine)
+    net = s["net_i"]
     try:
-        net = s["net_i"]
-        net._debug = {}
+        net._debug, net._force, net._force_flips = {}, force, {}
         x_bl, x_el = s["frames"][0]
         r = net.encode_decode(x_bl.to(s["dev"]), x_el.to(s["dev"]), None, None, H // 2, W // 2, H, W)
-        dbg = {k: v for k, v in net._debug.items()}
+        dbg = dict(net._debug)
+        dbg["flips"] = dict(net._force_flips)
     finally:
         ops.set_engine(prev)
-        s["net_i"]._debug = None
+        net._debug = net._force = None
     return r, dbg
 
 
-def _run_inter(s, engine, frame, dpb_cpu):
+def _run_inter(s, engine, frame, dpb_cpu, force=None):
     from lssvc_b200 import ops
     prev = ops.set_engine(engine)
+    net = s["net_p"]
     try:
-        net = s["net_p"]
-        net._debug = {}
+        net._debug, net._force, net._force_flips = {}, force, {}
         x_bl, x_el = s["frames"][frame]
         dpb = {k: (None if v is None else v.to(s["dev"])) for k, v in dpb_cpu.items()}
         r = net.encode_decode(x_bl.to(s["dev"]), x_el.to(s["dev"]), dpb, None, None, W, H, W // 2, H // 2)
-        dbg = {k: v for k, v in net._debug.items()}
+        dbg = dict(net._debug)
+        dbg["flips"] = dict(net._force_flips)
     finally:
         ops.set_engine(prev)
-        s["net_p"]._debug = None
+        net._debug = net._force = None
     return r, dbg
 
 
-def _lt(value, tol):
-    return tol is None or value < tol
+ENGINES = ["default", "simt", "tc"]
 
 
-def _recon_ok(name, got, ref, tol, flips):
-    """max-abs <= tol; if a quantised symbol legitimately flipped upstream (allowed: <= 0.01 % of symbols), the
-    reconstruction differs by O(0.1) around that position with random weights — then require the deviation to be
-    confined: >= 98 % of the samples still within tol."""
-    d = (got.cpu() - ref).abs()
-    mx = d.max().item()
-    print(f"  {name:14s} max|d| {mx:.3e}  (ref absmax {ref.abs().max().item():.3g})" + (f"  [{flips} symbol flips upstream]" if flips else ""))
-    if tol is None or mx < tol:
-        return True
-    return flips > 0 and (d < tol).float().mean().item() >= 0.98
+def _engine(name):
+    from lssvc_b200 import ops
+    return ops.default_engine() if name == "default" else name
 
 
-def _flips(got, ref):
-    return int((got.cpu() != ref).sum().item())
+def _tol(engine):
+    return TOL["tc"] if engine == "tc" else TOL["simt"]
 
 
-@pytest.mark.parametrize("engine", ["tc3", "simt", "tc"])
+def _forced_fraction(flips, q_ref):
+    total = sum(v.numel() for v in q_ref.values())
+    bad = sum(flips.values())
+    print(f"  symbols (teacher-forced): {bad} of {total} differ -> equal {100 * (1 - bad / total):.4f} %   {flips}")
+    return 1.0 - bad / total
+
+
+@pytest.mark.parametrize("engine", ENGINES)
 def test_intra_frame_parity(setup, engine):
+    engine = _engine(engine)
     s, o = setup, setup["o_i"]
-    r, dbg = _run_intra(s, engine)
+    tol_rec, tol_sym, tol_bits = _tol(engine)
+    q_ref = {"bl_z_hat": o["bl"]["z_hat"], "bl_y_q": torch.round(o["bl"]["y"] - o["bl"]["means"]), "z_hat": o["z_hat"],
+             "y_q": torch.round(o["y"] - o["means"])}
+    # ---- (1) oracle symbols forced
+    r, dbg = _run_intra(s, engine, force=q_ref)
     print(f"I-frame ({engine}): bits {r['bit_bl']:.1f}/{r['bit_el']:.1f} oracle {o['bit_bl']:.1f}/{o['bit_el']:.1f}")
-    tol_rec, tol_sym, tol_bits = TOL[engine]
-    sym_ref = torch.round(o["y"] - o["means"])
-    sym_got = torch.round(dbg["y_hat"].to_nchw().cpu() - dbg["params_el"].slice(96, 192).to_nchw().cpu())
-    f_bl = _flips(dbg["z_hat_bl"].to_nchw(), o["bl"]["z_hat"]) + _flips(
-        torch.round(dbg["y_hat_bl"].to_nchw().cpu() - o["bl"]["means"]), torch.round(o["bl"]["y"] - o["bl"]["means"]))
-    f_el = f_bl + _flips(sym_got, sym_ref) + _flips(dbg["z_hat"].to_nchw(), o["z_hat"])
-    assert _recon_ok("x_hat_bl", r["x_hat_bl"], o["x_hat_bl"], tol_rec, f_bl)
-    assert _recon_ok("x_hat_el", r["x_hat_el"], o["x_hat_el"], tol_rec, f_el)
-    _cmp("feature_el", r["feature_el"], o["feature_el"])
-    assert _match("EL symbols", sym_got, sym_ref) >= tol_sym
-    assert _match("BL z_hat", dbg["z_hat_bl"].to_nchw(), o["bl"]["z_hat"]) >= tol_sym
-    assert _match("EL z_hat", dbg["z_hat"].to_nchw(), o["z_hat"]) >= tol_sym
+    frac = _forced_fraction(dbg["flips"], q_ref)
+    _cmp("x_hat_bl", r["x_hat_bl"], o["x_hat_bl"], tol_rec)
+    _cmp("x_hat_el", r["x_hat_el"], o["x_hat_el"], tol_rec)
+    _cmp("feature_el", r["feature_el"], o["feature_el"], None if tol_rec is None else 5 * tol_rec)
+    assert frac >= tol_sym
     assert abs(r["bit_bl"] - o["bit_bl"]) / o["bit_bl"] < tol_bits
     assert abs(r["bit_el"] - o["bit_el"]) / o["bit_el"] < tol_bits
+    # ---- (2) free-running
+    r, dbg = _run_intra(s, engine)
+    sym = _Symbols()
+    sym.add("BL z_hat", dbg["z_hat_bl"].to_nchw(), q_ref["bl_z_hat"])
+    sym.add("BL y_q", torch.round(dbg["y_hat_bl"].to_nchw().cpu() - dbg["params_bl"].slice(192, 384).to_nchw().cpu()), q_ref["bl_y_q"])
+    sym.add("EL z_hat", dbg["z_hat"].to_nchw(), q_ref["z_hat"])
+    sym.add("EL y_q", torch.round(dbg["y_hat"].to_nchw().cpu() - dbg["params_el"].slice(96, 192).to_nchw().cpu()), q_ref["y_q"])
+    print(f"  free-running: all symbols equal {100 * sym.fraction():.4f} %, bits {r['bit_bl']:.1f}/{r['bit_el']:.1f}")
+    if engine == "simt":
+        assert sym.fraction() >= tol_sym
 
 
-@pytest.mark.parametrize("engine", ["tc3", "simt", "tc"])
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("which", ["first_p", "second_p"])
 def test_inter_frame_parity_teacher_forced(setup, engine, which):
+    engine = _engine(engine)
     s = setup
     frame, dpb, o = (1, s["dpb1"], s["o_p1"]) if which == "first_p" else (2, s["dpb2"], s["o_p2"])
-    r, dbg = _run_inter(s, engine, frame, dpb)
+    tol_rec, tol_sym, tol_bits = _tol(engine)
+    q_ref = {"bl_mv_z_hat": o["bl"]["mv_z_hat"], "bl_mv_y_q": o["bl"]["mv_y_q"], "bl_z_hat": o["bl"]["z_hat"],
+             "bl_y_q": o["bl"]["y_q"], "mv_z_hat": o["mv_z_hat"], "mv_y_q": o["mv_y_q"], "z_hat": o["z_hat"],
+             "y_q": o["four_part"]["y_q"]}
+    # ---- (1) oracle symbols forced
+    r, dbg = _run_inter(s, engine, frame, dpb, force=q_ref)
     print(f"P-frame {which} ({engine}): bits {r['bit_bl']:.1f}/{r['bit_el']:.1f} oracle {o['bit_bl']:.1f}/{o['bit_el']:.1f}")
-    tol_rec, tol_sym, tol_bits = TOL[engine]
-    mvq = torch.round(dbg["mv_y_hat"].to_nchw().cpu() - dbg["mv_prm"].slice(64, 128).to_nchw().cpu())
-    bl_mvq = torch.round(dbg["bl_mv_y_hat"].to_nchw().cpu() - dbg["bl_mv_prm"].slice(128, 256).to_nchw().cpu())
-    bl_yq = torch.round(dbg["bl_y_hat"].to_nchw().cpu() - dbg["bl_prm"].slice(96, 192).to_nchw().cpu())
-    f_bl_mv = _flips(dbg["bl_mv_z_hat"].to_nchw(), o["bl"]["mv_z_hat"]) + _flips(bl_mvq, o["bl"]["mv_y_q"])
-    f_bl = f_bl_mv + _flips(dbg["bl_z_hat"].to_nchw(), o["bl"]["z_hat"]) + _flips(bl_yq, o["bl"]["y_q"])
-    f_mv = f_bl + _flips(dbg["mv_z_hat"].to_nchw(), o["mv_z_hat"]) + _flips(mvq, o["mv_y_q"])
-    f_el = f_mv + _flips(dbg["z_hat"].to_nchw(), o["z_hat"]) + _flips(dbg["y_q"].to_nchw(), o["four_part"]["y_q"])
-    assert _recon_ok("BL mv_hat", dbg["bl_mv_hat"].to_nchw(), o["bl"]["mv_hat"], tol_rec, f_bl_mv)
-    assert _recon_ok("ref_frame_bl", r["dpb"]["ref_frame_bl"], o["dpb"]["ref_frame_bl"], tol_rec, f_bl)
-    assert _recon_ok("mv_hat", r["mv_hat"], o["mv_hat"], tol_rec, f_mv)
-    assert _recon_ok("warp_frame", r["warp_frame"], o["warp_frame"], tol_rec, f_mv)
-    assert _recon_ok("ref_frame_el", r["dpb"]["ref_frame_el"], o["dpb"]["ref_frame_el"], tol_rec, f_el)
-    _cmp("ref_feature_bl", r["dpb"]["ref_feature_bl"], o["dpb"]["ref_feature_bl"])
-    _cmp("ref_feature_el", r["dpb"]["ref_feature_el"], o["dpb"]["ref_feature_el"])
-    assert _match("EL y_q", dbg["y_q"].to_nchw(), o["four_part"]["y_q"]) >= tol_sym
-    assert _match("EL z_hat", dbg["z_hat"].to_nchw(), o["z_hat"]) >= tol_sym
-    assert _match("EL mv_z_hat", dbg["mv_z_hat"].to_nchw(), o["mv_z_hat"]) >= tol_sym
-    assert _match("BL z_hat", dbg["bl_z_hat"].to_nchw(), o["bl"]["z_hat"]) >= tol_sym
-    assert _match("EL mv_y_q", mvq, o["mv_y_q"]) >= tol_sym
-    assert _match("BL y_q", bl_yq, o["bl"]["y_q"]) >= tol_sym
-    assert _match("BL mv_y_q", bl_mvq, o["bl"]["mv_y_q"]) >= tol_sym
+    frac = _forced_fraction(dbg["flips"], q_ref)
+    _cmp("BL mv_hat", dbg["bl_mv_hat"].to_nchw(), o["bl"]["mv_hat"], tol_rec)
+    _cmp("ref_frame_bl", r["dpb"]["ref_frame_bl"], o["dpb"]["ref_frame_bl"], tol_rec)
+    _cmp("mv_hat", r["mv_hat"], o["mv_hat"], tol_rec)
+    _cmp("warp_frame", r["warp_frame"], o["warp_frame"], tol_rec)
+    _cmp("ref_frame_el", r["dpb"]["ref_frame_el"], o["dpb"]["ref_frame_el"], tol_rec)
+    _cmp("ref_feature_bl", r["dpb"]["ref_feature_bl"], o["dpb"]["ref_feature_bl"], None if tol_rec is None else 5 * tol_rec)
+    _cmp("ref_feature_el", r["dpb"]["ref_feature_el"], o["dpb"]["ref_feature_el"], None if tol_rec is None else 5 * tol_rec)
+    assert frac >= tol_sym
     assert abs(r["bit_bl"] - o["bit_bl"]) / o["bit_bl"] < tol_bits
     assert abs(r["bit_el"] - o["bit_el"]) / o["bit_el"] < tol_bits
+    # ---- (2) free-running
+    r, dbg = _run_inter(s, engine, frame, dpb)
+    nchw = lambda k: dbg[k].to_nchw().cpu()
+    sym = _Symbols()
+    sym.add("BL mv_z_hat", nchw("bl_mv_z_hat"), q_ref["bl_mv_z_hat"])
+    sym.add("BL mv_y_q", torch.round(nchw("bl_mv_y_hat") - dbg["bl_mv_prm"].slice(128, 256).to_nchw().cpu()), q_ref["bl_mv_y_q"])
+    sym.add("BL z_hat", nchw("bl_z_hat"), q_ref["bl_z_hat"])
+    sym.add("BL y_q", torch.round(nchw("bl_y_hat") - dbg["bl_prm"].slice(96, 192).to_nchw().cpu()), q_ref["bl_y_q"])
+    sym.add("EL mv_z_hat", nchw("mv_z_hat"), q_ref["mv_z_hat"])
+    sym.add("EL mv_y_q", torch.round(nchw("mv_y_hat") - dbg["mv_prm"].slice(64, 128).to_nchw().cpu()), q_ref["mv_y_q"])
+    sym.add("EL z_hat", nchw("z_hat"), q_ref["z_hat"])
+    sym.add("EL y_q", nchw("y_q"), q_ref["y_q"])
+    print(f"  free-running: all symbols equal {100 * sym.fraction():.4f} %, bits {r['bit_bl']:.1f}/{r['bit_el']:.1f}")
+    if engine == "simt":
+        assert sym.fraction() >= tol_sym
+
+
+def test_deterministic(setup):
+    """The same frame coded twice gives bit-identical outputs (no race in the pipelined kernels)."""
+    s = setup
+    a, _ = _run_inter(s, _engine("default"), 1, s["dpb1"])
+    b, _ = _run_inter(s, _engine("default"), 1, s["dpb1"])
+    assert abs(a["bit_el"] - b["bit_el"]) < 1e-6 * a["bit_el"]      # atomics: summation order only
+    for k in ("ref_frame_bl", "ref_frame_el", "ref_feature_el"):
+        assert torch.equal(a["dpb"][k], b["dpb"][k]), k
 
 
 def test_dpb_roundtrip_and_inplace_clamp(setup):
     """The caller clamps the returned reference frames in place and hands the dict back (test.py:249-250)."""
     s = setup
-    r1, _ = _run_inter(s, "tc3", 1, s["dpb1"])
+    r1, _ = _run_inter(s, _engine("default"), 1, s["dpb1"])
     dpb = r1["dpb"]
     dpb["ref_frame_bl"].clamp_(0, 1)
     dpb["ref_frame_el"].clamp_(0, 1)
