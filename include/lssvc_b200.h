@@ -49,6 +49,8 @@ typedef struct {
 
 #define LSSVC_PREC_TF32 0   /* tensor core reads the fp32 operands as TF32 (10 mantissa bits)            */
 #define LSSVC_PREC_3XTF32 1 /* error-compensated: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32-reference parity */
+#define LSSVC_PREC_H2 2     /* split-fp16: a = a_hi + a_lo, w = w_hi + w_lo in fp16 (22 significant bits each),
+                               3 kind::f16 MMAs per product, hi*hi and the cross terms in separate fp32 accumulators */
 
 #define LSSVC_EPI_PLAIN 0
 #define LSSVC_EPI_GDN 1  /* out = gdn_x * rsqrt(acc + bias)   (gdn.py:29-44, video_net_component.py:83-105) */
@@ -94,6 +96,12 @@ typedef struct {
    * with w_hi = rn_tf32(w) and w_lo = rn_tf32(w - w_hi), required for LSSVC_PREC_3XTF32 */
   int32_t precision;
   const float *weight_split;
+  /* lssvc_conv_h2 only: fp16 weights [kh*kw][2 (hi, lo)][n_pad][cin_pad16] of w * 2^w_shift (a power of two that
+   * moves max|w| to [2^13, 2^14) so that w_lo stays a normal fp16), cin_pad16 = sum of src[i].C rounded up to 16
+   * (each source's channels start at a multiple of 16), acc_scale = 2^-w_shift applied to the accumulator. */
+  const void *weight_h2;
+  int32_t cin_pad16;
+  float acc_scale;
 } lssvc_conv;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -107,6 +115,10 @@ int64_t lssvc_launch_count(void);
 /* ---- convolutions ------------------------------------------------------------------------ */
 /* tcgen05 / TMEM / TMA implicit-GEMM (TF32 operands, fp32 accumulate). */
 int32_t lssvc_conv_tc(const lssvc_conv *c, void *stream);
+/* tcgen05 kind::f16 implicit GEMM on split-fp16 operands (LSSVC_PREC_H2): activations are split in flight
+ * (fp32 halo tile by TMA -> hi/lo fp16 -> tensor memory), weights are pre-split (weight_h2).  Any kernel size,
+ * stride 1 or 2, up to 3 concatenated sources, input transform (GDN's x^2), GDN / IGDN epilogue. */
+int32_t lssvc_conv_h2(const lssvc_conv *c, void *stream);
 /* fp32 CUDA-core implicit GEMM: any shape, also hosts the GDN epilogue and input transforms. */
 int32_t lssvc_conv_simt(const lssvc_conv *c, void *stream);
 /* depthwise 3x3, pad 1 (lssvc_modules.py:23-24): weight [9][C], bias [C] */

@@ -13,7 +13,7 @@ MAX_SRC = 3
 ACT_NONE, ACT_LRELU = 0, 1
 IN_NONE, IN_SQUARE, IN_LRELU = 0, 1, 2
 EPI_PLAIN, EPI_GDN, EPI_IGDN = 0, 1, 2
-PREC_TF32, PREC_3XTF32 = 0, 1
+PREC_TF32, PREC_3XTF32, PREC_H2 = 0, 1, 2
 
 
 class LssvcError(RuntimeError):
@@ -46,6 +46,9 @@ class CConv(Structure):
         ("gdn_x", CView),
         ("precision", c_int32),
         ("weight_split", c_void_p),
+        ("weight_h2", c_void_p),
+        ("cin_pad16", c_int32),
+        ("acc_scale", c_float),
     ]
 
 
@@ -57,6 +60,7 @@ _SIGNATURES = {
     "lssvc_last_error": (c_char_p, []),
     "lssvc_launch_count": (c_int64, []),
     "lssvc_conv_tc": (c_int32, [POINTER(CConv), c_void_p]),
+    "lssvc_conv_h2": (c_int32, [POINTER(CConv), c_void_p]),
     "lssvc_conv_simt": (c_int32, [POINTER(CConv), c_void_p]),
     "lssvc_dwconv3x3": (c_int32, [_PV, c_void_p, c_void_p, _PV, c_void_p]),
     "lssvc_deconv3x3_s2": (c_int32, [_PV, c_void_p, c_void_p, c_int32, c_float, _PV, c_void_p]),

@@ -1,6 +1,7 @@
 """Host-side operator layer: NHWC views over torch-owned device memory and thin wrappers that hand raw
 pointers to the C-ABI kernels.  torch is used for allocation and stream handles only."""
 import ctypes
+import math
 import os
 
 import torch
@@ -107,7 +108,7 @@ class PackedConv:
     """Weights of one Conv2d repacked for the kernels: [kh*kw][n_pad][cin_total] + bias[n_pad]."""
 
     __slots__ = ("weight", "bias", "kh", "kw", "stride", "pad", "cout", "n_pad", "cin_total", "src_c", "pixel_shuffle",
-                 "_split")
+                 "_split", "_h2")
 
     def __init__(self, w, b, stride=1, pad=None, src_channels=None, pixel_shuffle=False, transposed=False, device=None):
         """w: [Cout, Cin, kh, kw] (Conv2d) or, with transposed=True, a stride-1 ConvTranspose2d weight
@@ -146,6 +147,31 @@ class PackedConv:
         self.src_c = [v for _, v in src_channels]
         self.pixel_shuffle = pixel_shuffle
         self._split = None
+        self._h2 = None
+
+    def weight_h2(self):
+        """Split-fp16 weights for lssvc_conv_h2: (fp16 [taps][2 (hi, lo)][n_pad][cin_pad16], cin_pad16, acc_scale).
+        The weights are first scaled by the power of two that puts max|w| in [2^13, 2^14), so that w_lo is a normal
+        fp16 for every weight that matters; acc_scale = 2^-shift undoes it on the fp32 accumulator (exact).
+        Each source's channels start at a multiple of 16 (the MMA's K step); pad columns are zero."""
+        if self._h2 is None:
+            w = self.weight
+            taps, n_pad, _ = w.shape
+            m = float(w.abs().max())
+            shift = 0 if m == 0.0 else 13 - int(math.floor(math.log2(m)))
+            ws = w * (2.0 ** shift)
+            cin16 = sum(round_up(c, 16) for c in self.src_c)
+            packed = torch.zeros(taps, 2, n_pad, cin16, dtype=torch.float16, device=w.device)
+            ci = co = 0
+            for c in self.src_c:
+                blk = ws[:, :, ci:ci + c]
+                hi = blk.to(torch.float16)
+                packed[:, 0, :, co:co + c] = hi
+                packed[:, 1, :, co:co + c] = (blk - hi.to(torch.float32)).to(torch.float16)
+                ci += c
+                co += round_up(c, 16)
+            self._h2 = (packed.contiguous(), cin16, 2.0 ** -shift)
+        return self._h2
 
     def weight_split(self):
         """(w_hi | w_lo) along the tap axis for the 3xTF32 kernel: w_hi = rn_tf32(w), w_lo = rn_tf32(w - w_hi)."""
@@ -167,8 +193,11 @@ ENGINES = {
            "note": "tcgen05.mma kind::tf32, fp32 accumulate in TMEM"},
     "tc3": {"kernel": "conv_tc_kernel(3xTF32)", "dtype": "tf32x3", "peak_vs_bf16": 0.5,
             "note": "tcgen05.mma kind::tf32 error-compensated 3xTF32 (3 MMAs per algorithmic MAC); FLOPs counted are algorithmic"},
+    "h2": {"kernel": "conv_h2_kernel", "dtype": "f16x2-split", "peak_vs_bf16": 1.0,
+           "note": "tcgen05.mma kind::f16 on split-fp16 operands (x = x_hi + x_lo; 3 MMAs per algorithmic MAC, A operand in "
+                   "TMEM, hi*hi and cross terms in separate fp32 accumulators); FLOPs counted are algorithmic"},
 }
-_ENGINE = os.environ.get("LSSVC_CONV_ENGINE", "tc3")
+_ENGINE = os.environ.get("LSSVC_CONV_ENGINE", "h2")
 assert _ENGINE in ENGINES, _ENGINE
 
 
@@ -229,7 +258,12 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
     d.slope2 = float(slope2)
     lib = _lib.load()
     engine = engine or _ENGINE
-    if engine != "simt":
+    if engine == "h2":
+        ok = (all(s.C % 4 == 0 and s.pitch % 4 == 0 and (s.coff % 4 == 0) for s in srcs) and pc.kh * pc.kw <= 49
+              and pc.stride in (1, 2) and srcs[0].H % pc.stride == 0 and srcs[0].W % pc.stride == 0)
+        if not ok:
+            engine = "simt"
+    elif engine != "simt":
         tc_ok = (in_transform == _lib.IN_NONE and epi == _lib.EPI_PLAIN
                  and all(s.C % 8 == 0 and s.pitch % 4 == 0 and (s.coff % 4 == 0) for s in srcs)
                  and pc.stride in (1, 2) and srcs[0].H % pc.stride == 0 and srcs[0].W % pc.stride == 0)
@@ -242,6 +276,11 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
                       "flops": 2.0 * Ho * Wo * pc.kh * pc.kw * sum(s.real for s in srcs) * pc.cout})
     if engine == "simt":
         _lib.check(lib.lssvc_conv_simt(byref(d), _stream()), "conv_simt")
+    elif engine == "h2":
+        wh, cin16, acc_scale = pc.weight_h2()
+        d.precision = _lib.PREC_H2
+        d.weight_h2, d.cin_pad16, d.acc_scale = wh.data_ptr(), cin16, acc_scale
+        _lib.check(lib.lssvc_conv_h2(byref(d), _stream()), "conv_h2")
     else:
         if engine == "tc3":
             d.precision = _lib.PREC_3XTF32

@@ -118,6 +118,29 @@ def test_conv_tc3(case, extras, cuda_device):
     assert err < 2e-5, err
 
 
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("extras", [False, True], ids=["plain", "epilogue"])
+def test_conv_h2(case, extras, cuda_device):
+    """Split-fp16 tcgen05 engine (A operand in TMEM, separate hi*hi / cross-term accumulators): fp32-reference level."""
+    err = _run_conv_case(case, "h2", cuda_device, extras)
+    print(f"tcgen05 split-fp16 conv {case[0]} rel err {err:.3e}")
+    assert err < 5e-6, err
+
+
+def test_conv_h2_large_persistent(cuda_device):
+    """More tiles than SMs: persistent loop, halo / slot ring wrap, TMEM double buffering, single-buffer (n_tile 128) mode."""
+    err = _run_conv_case(("big", [64], [64], 64, 3, 1, 256, 320, False), "h2", cuda_device, True)
+    assert err < 5e-6, err
+    err = _run_conv_case(("big48", [48, 48], [48, 48], 48, 3, 1, 200, 312, False), "h2", cuda_device, False)
+    assert err < 5e-6, err
+    err = _run_conv_case(("big256", [128], [128], 256, 3, 1, 96, 160, True), "h2", cuda_device, False)
+    assert err < 5e-6, err
+    err = _run_conv_case(("big_s2", [64, 8], [64, 8], 96, 3, 2, 192, 320, False), "h2", cuda_device, True)
+    assert err < 5e-6, err
+    err = _run_conv_case(("big_7x7", [32], [32], 64, 7, 1, 128, 256, False), "h2", cuda_device, False)
+    assert err < 5e-6, err
+
+
 def test_conv_tc3_large_persistent(cuda_device):
     err = _run_conv_case(("big", [64], [64], 64, 3, 1, 256, 320, False), "tc3", cuda_device, True)
     assert err < 2e-5, err
