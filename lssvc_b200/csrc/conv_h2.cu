@@ -38,10 +38,10 @@ namespace {
 constexpr int TILE_H = 8;
 constexpr int TILE_W = 16;
 constexpr int MAX_SLOTS = 8;   // ring of (A slot in TMEM, weight tile in smem)
-constexpr int MAX_HALO = 4;    // ring of halo tiles
+constexpr int MAX_HALO = 8;    // ring of halo tiles
 constexpr int MAX_TAPS = 49;
 constexpr int MAX_GROUPS = 4;  // stride-2: one halo per input parity plane
-constexpr int TAPS_PER_STAGE = 2;  // taps of one halo group that share a pipeline stage (one barrier round trip)
+constexpr int STAGE_K = 64;    // input channels x taps of one pipeline stage: KC = 32 -> 2 taps, KC = 16 -> 4 taps
 constexpr int NUM_THREADS = 512;
 constexpr int TMEM_COLS = 512;
 
@@ -140,6 +140,7 @@ __device__ __forceinline__ void transform_row(float4 (&v)[NV], int in_transform,
 
 template <int KC>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_constant__ H2Params p) {
+  constexpr int TAPS_PER_STAGE = STAGE_K / KC;  // taps of one halo group sharing a stage (one barrier round trip)
   constexpr int ROWB = KC * 4;        // bytes of one halo pixel (fp32, or fp16 hi | fp16 lo after conversion)
   constexpr int NV = KC / 4;          // 16-byte chunks per halo pixel
   constexpr int KS = KC / 16;         // K = 16 MMA slices per stage
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
             }
             for (int t = t0; t < t1; t += TAPS_PER_STAGE) {
               if (parity == static_cast<uint32_t>(set)) {
-                const bool two = t + 1 < t1;  // warp-uniform: the stage holds a second tap
+                const int items = t1 - t < TAPS_PER_STAGE ? t1 - t : TAPS_PER_STAGE;  // warp-uniform
                 uint32_t hi[TAPS_PER_STAGE][HALF], lo[TAPS_PER_STAGE][HALF];
                 {
                   const int r = pix_row + p.tap_off[t];
@@ -412,16 +413,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
                     split_row<NV>(v, hi[0], lo[0]);
                   }
                 }
-                if (two) {  // only pre-converted groups have more than one tap
-                  const int r = pix_row + p.tap_off[t + 1];
-                  const uint32_t a0 = (halo + static_cast<uint32_t>(r) * ROWB) |
-                                      (static_cast<uint32_t>(KC == 32 ? (r & 7) : ((r >> 1) & 3)) << 4);
 #pragma unroll
-                  for (int i = 0; i < NV / 2; ++i)
-                    ptx::lds_u4(a0 ^ (i << 4), hi[1][4 * i], hi[1][4 * i + 1], hi[1][4 * i + 2], hi[1][4 * i + 3]);
+                for (int e = 1; e < TAPS_PER_STAGE; ++e) {
+                  if (e < items) {  // only pre-converted groups have more than one tap
+                    const int r = pix_row + p.tap_off[t + e];
+                    const uint32_t a0 = (halo + static_cast<uint32_t>(r) * ROWB) |
+                                        (static_cast<uint32_t>(KC == 32 ? (r & 7) : ((r >> 1) & 3)) << 4);
 #pragma unroll
-                  for (int i = 0; i < NV / 2; ++i)
-                    ptx::lds_u4(a0 ^ ((NV / 2 + i) << 4), lo[1][4 * i], lo[1][4 * i + 1], lo[1][4 * i + 2], lo[1][4 * i + 3]);
+                    for (int i = 0; i < NV / 2; ++i)
+                      ptx::lds_u4(a0 ^ (i << 4), hi[e][4 * i], hi[e][4 * i + 1], hi[e][4 * i + 2], hi[e][4 * i + 3]);
+#pragma unroll
+                    for (int i = 0; i < NV / 2; ++i)
+                      ptx::lds_u4(a0 ^ ((NV / 2 + i) << 4), lo[e][4 * i], lo[e][4 * i + 1], lo[e][4 * i + 2], lo[e][4 * i + 3]);
+                  }
                 }
                 if (pending >= 0) {  // publish the previous stage of this warp
                   ptx::tmem_st_wait();
@@ -434,19 +438,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
                 ptx::tc_fence_after();
                 const uint32_t dst = lane_base + static_cast<uint32_t>(s * TAPS_PER_STAGE * KC);
                 if (!no_st) {
-                  if constexpr (KC == 32) {
-                    ptx::tmem_st16(dst, hi[0]);
-                    ptx::tmem_st16(dst + HALF, lo[0]);
-                    if (two) {
-                      ptx::tmem_st16(dst + KC, hi[1]);
-                      ptx::tmem_st16(dst + KC + HALF, lo[1]);
-                    }
-                  } else {
-                    ptx::tmem_st8(dst, hi[0]);
-                    ptx::tmem_st8(dst + HALF, lo[0]);
-                    if (two) {
-                      ptx::tmem_st8(dst + KC, hi[1]);
-                      ptx::tmem_st8(dst + KC + HALF, lo[1]);
+#pragma unroll
+                  for (int e = 0; e < TAPS_PER_STAGE; ++e) {
+                    if (e < items) {
+                      if constexpr (KC == 32) {
+                        ptx::tmem_st16(dst + e * KC, hi[e]);
+                        ptx::tmem_st16(dst + e * KC + HALF, lo[e]);
+                      } else {
+                        ptx::tmem_st8(dst + e * KC, hi[e]);
+                        ptx::tmem_st8(dst + e * KC + HALF, lo[e]);
+                      }
                     }
                   }
                 }
@@ -792,7 +793,7 @@ extern "C" int32_t lssvc_conv_h2(const lssvc_conv *c, void *stream) {
   {
     int per_chunk = 0;
     for (int g = 0; g < p.n_groups; ++g)
-      per_chunk += (p.g_tap0[g + 1] - p.g_tap0[g] + TAPS_PER_STAGE - 1) / TAPS_PER_STAGE;
+      per_chunk += (p.g_tap0[g + 1] - p.g_tap0[g] + (STAGE_K / kc) - 1) / (STAGE_K / kc);
     p.stages_per_tile = total_chunks * per_chunk;
   }
   p.Ho = Ho; p.Wo = Wo;
@@ -801,17 +802,22 @@ extern "C" int32_t lssvc_conv_h2(const lssvc_conv *c, void *stream) {
   p.n_tiles = c->n_pad / n_tile;
   p.n_tile = n_tile;
   p.cout = c->cout;
-  p.d_bufs = (4 * n_tile + 2 * TAPS_PER_STAGE * kc <= TMEM_COLS) ? 2 : 1;
+  p.d_bufs = (4 * n_tile + 2 * STAGE_K <= TMEM_COLS) ? 2 : 1;
   p.a_col0 = p.d_bufs * 2 * n_tile;
-  p.slots = (TMEM_COLS - p.a_col0) / (TAPS_PER_STAGE * kc);
+  const int tps = STAGE_K / kc;
+  p.slots = (TMEM_COLS - p.a_col0) / STAGE_K;
   if (p.slots > MAX_SLOTS) p.slots = MAX_SLOTS;
   p.halo_tx = halo_w * halo_h * row_bytes;
   p.halo_rows = halo_w * halo_h;
   p.halo_bytes = (p.halo_tx + 1023) & ~1023;
-  p.b_bytes = TAPS_PER_STAGE * (2 * n_tile * kc * 2);  // n_tile % 16 == 0 keeps every tile 1024-byte aligned
+  p.b_bytes = tps * (2 * n_tile * kc * 2);  // n_tile % 16 == 0 keeps every tile 1024-byte aligned
   const int smem_budget = 224 * 1024;
-  p.halo_bufs = 3;
-  while (p.halo_bufs > 2 && p.halo_bufs * p.halo_bytes + 4 * p.b_bytes + 1024 > smem_budget) --p.halo_bufs;
+  // as many halo tiles in flight as fit next to the weight ring: HBM latency x bandwidth wants > 64 KB per SM
+  p.halo_bufs = MAX_HALO;
+  {
+    const int want_slots = p.slots < 4 ? p.slots : 4;
+    while (p.halo_bufs > 2 && p.halo_bufs * p.halo_bytes + want_slots * p.b_bytes + 1024 > smem_budget) --p.halo_bufs;
+  }
   while (p.slots > 2 && p.halo_bufs * p.halo_bytes + p.slots * p.b_bytes + 1024 > smem_budget) --p.slots;
   LSSVC_REQUIRE(p.slots >= 2 && p.halo_bufs * p.halo_bytes + p.slots * p.b_bytes + 1024 <= smem_budget,
                 "conv_h2: pipeline does not fit in shared memory (halo %d B x %d, weights %d B x %d)", p.halo_bytes,

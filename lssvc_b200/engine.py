@@ -99,7 +99,7 @@ class Engine(nets.ParamBag):
         return self.lrelu(x, 1.0, out)
 
     def gdn(self, name, x, inverse=False, res1=None, intra=False, out=None):
-        """GDN / IGDN: x * (beta + gamma . x^2)^(-/+ 1/2) (+ res1).  fp32 CUDA-core path (norm pool wants full precision).
+        """GDN / IGDN: x * (beta + gamma . x^2)^(-/+ 1/2) (+ res1).
         intra: gdn.py:29-44 + others.py:43-67; inter: video_net_component.py:83-105."""
         def build():
             beta, gamma = self.tensor(name + ".beta").detach().float().cpu(), self.tensor(name + ".gamma").detach().float().cpu()
@@ -115,8 +115,11 @@ class Engine(nets.ParamBag):
             return ops.PackedConv(gamma.view(C, C, 1, 1), beta, pad=0, src_channels=[(C, x.C)], device=self.device)
         pc = self.cached(("gdn", name, x.C), build)
         out = out if out is not None else self.new(x.H, x.W, x.real)
+        # split-fp16 tensor-core engine: x^2 is formed and split in the kernel's operand path; the other engines keep
+        # the norm pool on the fp32 CUDA cores (ops.conv falls back for input transforms / GDN epilogues)
+        ops.TRACE_NAME = name
         ops.conv(pc, [x], out.exact(), in_transform=_lib.IN_SQUARE, epi=_lib.EPI_IGDN if inverse else _lib.EPI_GDN,
-                 gdn_x=x.exact(), res1=None if res1 is None else res1.exact(), engine="simt")
+                 gdn_x=x.exact(), res1=None if res1 is None else res1.exact())
         return out
 
     def dwconv(self, name, x):
@@ -130,7 +133,29 @@ class Engine(nets.ParamBag):
         return out
 
     def deconv_s2(self, name, x, act=None):
-        """nn.ConvTranspose2d(3, stride=2, padding=1, output_padding=1)."""
+        """nn.ConvTranspose2d(3, stride=2, padding=1, output_padding=1).
+
+        On the tensor-core engine it runs as its sub-pixel decomposition: out[2y+i, 2x+j] only involves in[y+a, x+b]
+        with a, b in {0, 1} (ky = 1 for (i,a)=(0,0), 2 for (1,0), 0 for (1,1); same in x), i.e. a stride-1 conv with
+        4*cout output channels (taps r = a+1, s = b+1 of a 3x3 / pad 1 kernel, the others zero) + PixelShuffle(2)."""
+        if ops.default_engine() == "h2":
+            def build_ps():
+                w = self.tensor(name + ".weight").detach().float().cpu()       # [cin, cout, 3, 3]
+                b = self.tensor(name + ".bias").detach().float().cpu()
+                cin, cout = w.shape[0], w.shape[1]
+                w3 = torch.zeros(4 * cout, cin, 3, 3)
+                kmap = {(0, 0): 1, (1, 0): 2, (1, 1): 0}
+                for (i, a), ky in kmap.items():
+                    for (j, bb), kx in kmap.items():
+                        w3[2 * i + j::4, :, a + 1, bb + 1] = w[:, :, ky, kx].t()
+                return ops.PackedConv(w3, b.repeat_interleave(4), pad=1, src_channels=[(x.real, x.C)], pixel_shuffle=True,
+                                      device=self.device)
+            pc = self.cached(("deconv_ps", name, x.real, x.C), build_ps)
+            out = self.new(x.H * 2, x.W * 2, pc.cout // 4)
+            ops.TRACE_NAME = name
+            ops.conv(pc, [x], out.exact(), act=act)
+            return out
+
         def build():
             w = self.tensor(name + ".weight").detach().float()          # [cin, cout, 3, 3]
             cin, cout = w.shape[0], w.shape[1]

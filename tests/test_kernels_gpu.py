@@ -158,7 +158,8 @@ def test_conv_tc_large_persistent(cuda_device):
     assert err < 2e-3, err
 
 
-def test_gdn_epilogue(cuda_device):
+@pytest.mark.parametrize("engine", ["simt", "h2"])
+def test_gdn_epilogue(cuda_device, engine):
     ops = _ops()
     from lssvc_b200 import _lib
     dev = cuda_device
@@ -173,10 +174,33 @@ def test_gdn_epilogue(cuda_device):
     for inverse in (False, True):
         out = ops.View.alloc(H, W, C, dev)
         ops.conv(pc, xv, out, in_transform=_lib.IN_SQUARE, epi=_lib.EPI_IGDN if inverse else _lib.EPI_GDN, gdn_x=xv,
-                 res1=make_view(res, ops), engine="simt")
+                 res1=make_view(res, ops), engine=engine)
         norm = F.conv2d(x.double() ** 2, gamma.double().view(C, C, 1, 1), beta.double())
         ref = (x.double() * (norm.sqrt() if inverse else norm.rsqrt()) + res.double()).float()
         assert rel_err(out.to_nchw(), ref) < 1e-5
+
+
+def test_deconv_subpixel_h2(cuda_device):
+    """ConvTranspose2d(3, stride 2, padding 1, output_padding 1) as sub-pixel conv + PixelShuffle on the tensor cores
+    (Engine.deconv_s2) against torch, incl. an odd channel count and the fused LeakyReLU."""
+    from lssvc_b200 import engine as eng, nets
+    ops = _ops()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    for cin, cout, H, W, act in ((64, 96, 9, 15, 0.01), (128, 2, 18, 30, None)):
+        spec = nets.Spec()
+        spec.deconv("d", cin, cout, 3)
+        m = eng.Engine(spec, "P", seed=0)
+        w = torch.randn(cin, cout, 3, 3, generator=g) / math.sqrt(cin * 9)
+        b = torch.randn(cout, generator=g)
+        m.load_state_dict({"d.weight": w, "d.bias": b})
+        m.to(dev)
+        x = torch.randn(1, cin, H, W, generator=g).to(dev)
+        out = m.deconv_s2("d", make_view(x, ops), act=act)
+        ref = F.conv_transpose2d(x.double(), w.double().to(dev), b.double().to(dev), stride=2, padding=1, output_padding=1)
+        if act is not None:
+            ref = F.leaky_relu(ref, act)
+        assert rel_err(out.to_nchw(), ref.float()) < 5e-6
 
 
 def test_dwconv_and_deconv(cuda_device):

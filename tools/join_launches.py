@@ -41,7 +41,7 @@ def main():
     frames = trace(size, p_frames)
     lines = [l for l in open(path) if l.startswith('"')]
     tc = [float(r["Metric Value"].replace(",", "")) for r in csv.DictReader(lines)
-          if r.get("Metric Name") == "gpu__time_duration.sum" and "conv_tc" in r["Kernel Name"]]
+          if r.get("Metric Name") == "gpu__time_duration.sum" and ("conv_tc" in r["Kernel Name"] or "conv_h2" in r["Kernel Name"])]
     convs = [c for f in frames for c in f if c["engine"] != "simt"]
     assert len(convs) == len(tc), (len(convs), len(tc))
     n_last = len([c for c in frames[-1] if c["engine"] != "simt"])
