@@ -22,9 +22,10 @@
 //     neither the 9x re-fetch of the taps from L2 nor any A traffic of the MMA touches shared memory.
 //   * the stacked weight tile [2][n_tile][KC] fp16 of each (chunk, tap) is TMA-loaded into a swizzled K-major ring.
 //
-// Warp roles (512 threads): 0 halo TMA producer, 1 MMA issuer, 2 TMEM allocator + weight TMA producer,
-// 4..11 splitters (two sets of 4 warps, alternate stages), 12..15 epilogue (TMEM -> registers -> bias /
-// activation / GDN / residuals / pixel-shuffle -> global).  Persistent over tiles; the accumulators are double
+// Warp roles (896 threads): 0 halo TMA producer, 1 MMA issuer, 2 TMEM allocator + weight TMA producer,
+// 4..11 splitters (two sets of 4 warps, alternate stages), 12..19 epilogue (two sets, alternate 16-channel
+// chunks: TMEM -> registers -> bias / activation / GDN / residuals / pixel-shuffle -> global), 20..27 halo
+// converters (fp32 -> fp16 hi | lo in place).  Persistent over tiles; the accumulators are double
 // buffered when 4 * n_tile + ring fits in the 512 TMEM columns.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -42,12 +43,14 @@ constexpr int MAX_HALO = 8;    // ring of halo tiles
 constexpr int MAX_TAPS = 49;
 constexpr int MAX_GROUPS = 4;  // stride-2: one halo per input parity plane
 constexpr int STAGE_K = 64;    // input channels x taps of one pipeline stage: KC = 32 -> 2 taps, KC = 16 -> 4 taps
-constexpr int NUM_THREADS = 512;
+constexpr int NUM_THREADS = 896;
 constexpr int TMEM_COLS = 512;
 
 struct alignas(64) H2Params {
   CUtensorMap a_map[LSSVC_MAX_SRC];
   CUtensorMap b_map;
+  CUtensorMap out_map, out2_map;  // TMA-store epilogue (use_tma)
+  int use_tma, slab_w, n_slabs, stage_off, stage2_off, stage_bufs, stage_stride;  // staging: [bufs][out, out2][n_slabs][128 px][slab_w fp32]
   int n_src;
   int chunks[LSSVC_MAX_SRC];  // ceil(C / KC) per source
   int coff[LSSVC_MAX_SRC];    // first packed input channel of the source
@@ -148,12 +151,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
   constexpr uint32_t B_ROWB = KC * 2;  // bytes of one weight row (fp16)
   constexpr uint32_t B_LAYOUT = KC == 32 ? 4u : 6u;  // SWIZZLE_64B : SWIZZLE_32B
   constexpr uint32_t B_SBO = 8 * B_ROWB;
+  constexpr uint32_t SWZ = KC == 32 ? 0x70u : 0x30u;  // 16-byte-chunk XOR of the TMA swizzle: address bits 7.. -> bits 4..
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_s[MAX_SLOTS];
   __shared__ uint64_t empty_s[MAX_SLOTS];
   __shared__ uint64_t halo_full[MAX_HALO];
   __shared__ uint64_t halo_empty[MAX_HALO];
+  __shared__ uint64_t halo_conv[MAX_HALO];
   __shared__ uint64_t tfull_bar[2];
   __shared__ uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_slot;
@@ -167,6 +172,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
   const uint32_t bar_full = ptx::pin(ptx::smem_u32(full_s));
   const uint32_t bar_empty = ptx::pin(ptx::smem_u32(empty_s));
   const uint32_t bar_halo_full = ptx::pin(ptx::smem_u32(halo_full)), bar_halo_empty = ptx::pin(ptx::smem_u32(halo_empty));
+  const uint32_t bar_halo_conv = ptx::pin(ptx::smem_u32(halo_conv));
   const uint32_t bar_tfull = ptx::pin(ptx::smem_u32(tfull_bar)), bar_tempty = ptx::pin(ptx::smem_u32(tempty_bar));
 
   if (warp == 0 && lane == 0) {
@@ -181,10 +187,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
     for (int h = 0; h < p.halo_bufs; ++h) {
       ptx::mbar_init(bar_halo_full + 8 * h, 1);
       ptx::mbar_init(bar_halo_empty + 8 * h, 8);
+      ptx::mbar_init(bar_halo_conv + 8 * h, 8);
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar_tfull + 8 * b, 1);
-      ptx::mbar_init(bar_tempty + 8 * b, 4);
+      ptx::mbar_init(bar_tempty + 8 * b, 8);
     }
     ptx::fence_barrier_init();
   }
@@ -199,7 +206,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
 
   const int tiles_per_n = p.tiles_x * p.tiles_y;
   const int total_tiles = tiles_per_n * p.n_tiles;
-  const int n_taps = p.g_tap0[p.n_groups];
 
   if (warp == 0) {
     // ------------------------------- halo TMA producer -----------------------------------
@@ -339,23 +345,68 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
         acc_ph ^= 1u;
       }
     }
-  } else if (warp >= 4 && warp < 12) {
-    // ------------------------------- splitters: halo -> fp16 hi/lo -> TMEM ----------------
-    // Halo groups with several taps are first converted IN PLACE (one thread per halo pixel: fp32 row ->
-    // [hi fp16 x KC | lo fp16 x KC], same 16-byte-chunk swizzle), so that a tap is NV LDS.128 feeding tcgen05.st
-    // directly; a group with a single tap (1x1 convs) is converted on the fly.  The TMEM store of a tap is
-    // completed (wait::st + arrive) only after the loads of the warp's next tap have been issued.
-    const int set = (warp - 4) >> 2;
-    const int q = warp & 3;  // TMEM lane quarter of this warp
-    const int m = q * 32 + lane;
-    const int st = threadIdx.x - 128;  // 0..255 over both sets
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(p.a_col0);
-    const int halo_rows = p.halo_rows, slots = p.slots, halo_bufs = p.halo_bufs;
-    const int pix_row = (m / TILE_W) * p.halo_w + (m % TILE_W);
+  } else if (warp >= 20) {
+    // ------------------------------- converters: fp32 halo -> fp16 hi | lo, in place -------
+    // One thread per halo pixel: the 4*KC-byte fp32 row becomes [hi fp16 x KC | lo fp16 x KC] with the same
+    // 16-byte-chunk swizzle, so that a tap of the splitters is NV LDS.128 feeding tcgen05.st with no arithmetic.
+    // Groups with a single tap (1x1 convs) are left as they are (the splitters convert on the fly).
+    const int ct = threadIdx.x - 640;  // 0..255
+    const int halo_rows = p.halo_rows, halo_bufs = p.halo_bufs;
     const int in_transform = p.in_transform;
     const float in_slope = p.in_slope;
     const uint32_t halo_bytes = static_cast<uint32_t>(p.halo_bytes);
-    const bool no_conv = (p.dbg & 2) != 0, no_st = (p.dbg & 4) != 0;
+    const bool no_conv = (p.dbg & 2) != 0;
+    int hb = 0;
+    uint32_t hph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int j = 0; j < p.n_src; ++j) {
+        for (int c = 0; c < p.chunks[j]; ++c) {
+          for (int g = 0; g < p.n_groups; ++g) {
+            ptx::mbar_wait(bar_halo_full + 8 * hb, hph);
+            if (p.g_tap0[g + 1] - p.g_tap0[g] > 1 && !no_conv) {
+              const uint32_t halo = smem_base + static_cast<uint32_t>(hb) * halo_bytes;
+              for (int r = ct; r < halo_rows; r += 256) {
+                const uint32_t x = halo + static_cast<uint32_t>(r) * ROWB;
+                const uint32_t a0 = x | ((x >> 3) & SWZ);
+                float4 v[NV];
+#pragma unroll
+                for (int i = 0; i < NV; ++i) v[i] = ptx::lds_f4(a0 ^ (i << 4));
+                transform_row<NV>(v, in_transform, in_slope);
+                uint32_t hi[HALF], lo[HALF];
+                split_row<NV>(v, hi, lo);
+#pragma unroll
+                for (int i = 0; i < NV / 2; ++i) {
+                  ptx::sts_u4(a0 ^ (i << 4), hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                  ptx::sts_u4(a0 ^ ((NV / 2 + i) << 4), lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                }
+              }
+              ptx::fence_proxy_async_smem();
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar_halo_conv + 8 * hb);
+            if (++hb == halo_bufs) {
+              hb = 0;
+              hph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ------------------------------- splitters: halo window -> TMEM -----------------------
+    // Each thread owns one output pixel (= one TMEM lane): per tap it reads the shifted halo row (already fp16
+    // hi | lo) and stores it into the stage's A slot.  Two sets of 4 warps alternate stages; a stage is published
+    // (wait::st + arrive) after the loads of the warp's next stage have been issued.
+    const int set = (warp - 4) >> 2;
+    const int q = warp & 3;  // TMEM lane quarter of this warp
+    const int m = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(p.a_col0);
+    const int slots = p.slots, halo_bufs = p.halo_bufs;
+    const uint32_t pix_boff = static_cast<uint32_t>((m / TILE_W) * p.halo_w + (m % TILE_W)) * ROWB;
+    const int in_transform = p.in_transform;
+    const float in_slope = p.in_slope;
+    const uint32_t halo_bytes = static_cast<uint32_t>(p.halo_bytes);
+    const bool no_st = (p.dbg & 4) != 0;
     int s = 0;
     uint32_t ph = 0;
     int hb = 0;
@@ -366,87 +417,52 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
       for (int j = 0; j < p.n_src; ++j) {
         for (int c = 0; c < p.chunks[j]; ++c) {
           for (int g = 0; g < p.n_groups; ++g) {
-            ptx::mbar_wait(bar_halo_full + 8 * hb, hph);
-            const uint32_t halo = smem_base + static_cast<uint32_t>(hb) * halo_bytes;
+            ptx::mbar_wait(bar_halo_conv + 8 * hb, hph);
+            const uint32_t halo = smem_base + static_cast<uint32_t>(hb) * halo_bytes + pix_boff;
             const int t0 = p.g_tap0[g], t1 = p.g_tap0[g + 1];
             const bool pre = (t1 - t0) > 1;
-            if (pre) {
-              if (!no_conv) {
-                for (int r = st; r < halo_rows; r += 256) {
-                  const uint32_t a0 = (halo + static_cast<uint32_t>(r) * ROWB) |
-                                      (static_cast<uint32_t>(KC == 32 ? (r & 7) : ((r >> 1) & 3)) << 4);
-                  float4 v[NV];
-#pragma unroll
-                  for (int i = 0; i < NV; ++i) v[i] = ptx::lds_f4(a0 ^ (i << 4));
-                  transform_row<NV>(v, in_transform, in_slope);
-                  uint32_t hi[HALF], lo[HALF];
-                  split_row<NV>(v, hi, lo);
-#pragma unroll
-                  for (int i = 0; i < NV / 2; ++i) {
-                    ptx::sts_u4(a0 ^ (i << 4), hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                    ptx::sts_u4(a0 ^ ((NV / 2 + i) << 4), lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-                  }
-                }
-              }
-              ptx::named_bar_sync(1, 256);
-            }
             for (int t = t0; t < t1; t += TAPS_PER_STAGE) {
               if (parity == static_cast<uint32_t>(set)) {
                 const int items = t1 - t < TAPS_PER_STAGE ? t1 - t : TAPS_PER_STAGE;  // warp-uniform
-                uint32_t hi[TAPS_PER_STAGE][HALF], lo[TAPS_PER_STAGE][HALF];
-                {
-                  const int r = pix_row + p.tap_off[t];
-                  const uint32_t a0 = (halo + static_cast<uint32_t>(r) * ROWB) |
-                                      (static_cast<uint32_t>(KC == 32 ? (r & 7) : ((r >> 1) & 3)) << 4);
-                  if (pre) {
-#pragma unroll
-                    for (int i = 0; i < NV / 2; ++i)
-                      ptx::lds_u4(a0 ^ (i << 4), hi[0][4 * i], hi[0][4 * i + 1], hi[0][4 * i + 2], hi[0][4 * i + 3]);
-#pragma unroll
-                    for (int i = 0; i < NV / 2; ++i)
-                      ptx::lds_u4(a0 ^ ((NV / 2 + i) << 4), lo[0][4 * i], lo[0][4 * i + 1], lo[0][4 * i + 2], lo[0][4 * i + 3]);
-                  } else {
-                    float4 v[NV];
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) v[i] = ptx::lds_f4(a0 ^ (i << 4));
-                    transform_row<NV>(v, in_transform, in_slope);
-                    split_row<NV>(v, hi[0], lo[0]);
-                  }
-                }
-#pragma unroll
-                for (int e = 1; e < TAPS_PER_STAGE; ++e) {
-                  if (e < items) {  // only pre-converted groups have more than one tap
-                    const int r = pix_row + p.tap_off[t + e];
-                    const uint32_t a0 = (halo + static_cast<uint32_t>(r) * ROWB) |
-                                        (static_cast<uint32_t>(KC == 32 ? (r & 7) : ((r >> 1) & 3)) << 4);
-#pragma unroll
-                    for (int i = 0; i < NV / 2; ++i)
-                      ptx::lds_u4(a0 ^ (i << 4), hi[e][4 * i], hi[e][4 * i + 1], hi[e][4 * i + 2], hi[e][4 * i + 3]);
-#pragma unroll
-                    for (int i = 0; i < NV / 2; ++i)
-                      ptx::lds_u4(a0 ^ ((NV / 2 + i) << 4), lo[e][4 * i], lo[e][4 * i + 1], lo[e][4 * i + 2], lo[e][4 * i + 3]);
-                  }
-                }
-                if (pending >= 0) {  // publish the previous stage of this warp
-                  ptx::tmem_st_wait();
-                  ptx::tc_fence_before();
-                  __syncwarp();
-                  if (lane == 0) ptx::mbar_arrive(bar_full + 8 * pending);
-                }
-                // the slot is free once the MMAs of its previous use have completed
-                ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                ptx::tc_fence_after();
                 const uint32_t dst = lane_base + static_cast<uint32_t>(s * TAPS_PER_STAGE * KC);
-                if (!no_st) {
 #pragma unroll
-                  for (int e = 0; e < TAPS_PER_STAGE; ++e) {
-                    if (e < items) {
+                for (int e = 0; e < TAPS_PER_STAGE; ++e) {
+                  if (e < items) {
+                    const uint32_t x = halo + static_cast<uint32_t>(p.tap_off[t + e]) * ROWB;
+                    const uint32_t a0 = x | ((x >> 3) & SWZ);
+                    uint32_t hi[HALF], lo[HALF];
+                    if (pre) {
+#pragma unroll
+                      for (int i = 0; i < NV / 2; ++i)
+                        ptx::lds_u4(a0 ^ (i << 4), hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+#pragma unroll
+                      for (int i = 0; i < NV / 2; ++i)
+                        ptx::lds_u4(a0 ^ ((NV / 2 + i) << 4), lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                    } else {
+                      float4 v[NV];
+#pragma unroll
+                      for (int i = 0; i < NV; ++i) v[i] = ptx::lds_f4(a0 ^ (i << 4));
+                      transform_row<NV>(v, in_transform, in_slope);
+                      split_row<NV>(v, hi, lo);
+                    }
+                    if (e == 0) {
+                      if (pending >= 0) {  // publish the previous stage of this warp
+                        ptx::tmem_st_wait();
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(bar_full + 8 * pending);
+                      }
+                      // the slot is free once the MMAs of its previous use have completed
+                      ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                      ptx::tc_fence_after();
+                    }
+                    if (!no_st) {
                       if constexpr (KC == 32) {
-                        ptx::tmem_st16(dst + e * KC, hi[e]);
-                        ptx::tmem_st16(dst + e * KC + HALF, lo[e]);
+                        ptx::tmem_st16(dst + e * KC, hi);
+                        ptx::tmem_st16(dst + e * KC + HALF, lo);
                       } else {
-                        ptx::tmem_st8(dst + e * KC, hi[e]);
-                        ptx::tmem_st8(dst + e * KC + HALF, lo[e]);
+                        ptx::tmem_st8(dst + e * KC, hi);
+                        ptx::tmem_st8(dst + e * KC + HALF, lo);
                       }
                     }
                   }
@@ -478,8 +494,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
         }
       }
     }
-  } else if (warp >= 12) {
+  } else if (warp >= 12 && warp < 20) {
     // ------------------------------- epilogue ---------------------------------------------
+    // two sets of 4 warps; set e takes the 16-channel chunks e, e + 2, ... of every tile
+    const int eset = (warp - 12) >> 2;
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int h = m / TILE_W, w = m % TILE_W;
@@ -498,6 +516,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
     const float *const bias = p.bias;
     const long long out_pitch = p.out_pitch, out2_pitch = p.out2_pitch, res1_pitch = p.res1_pitch,
                     res2_pitch = p.res2_pitch, gdn_pitch = p.gdn_pitch;
+    const bool use_tma = p.use_tma != 0 && fast && chunk_uniform;
+    const uint32_t slab_w = static_cast<uint32_t>(p.slab_w);
+    const uint32_t stage_base = smem_base + static_cast<uint32_t>(p.stage_off), stage2_delta = static_cast<uint32_t>(p.stage2_off - p.stage_off);
+    const uint32_t stage_stride = static_cast<uint32_t>(p.stage_stride);
+    const int stage_bufs = p.stage_bufs;
+    int sb = 0;
+    const bool store_thread = warp == 12 && lane == 0;
     int buf = 0;
     uint32_t acc_ph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -508,10 +533,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
       const int oy = ty * TILE_H + h, ox = tx * TILE_W + w, n0 = nt * n_tile;
       const bool valid = (oy < p.Ho) && (ox < Wo) && !no_store;
       const long long pix = static_cast<long long>(oy) * Wo + ox;
+      const uint32_t stage = stage_base + static_cast<uint32_t>(sb) * stage_stride, stage2 = stage + stage2_delta;
+      if (use_tma) {
+        // the staging tile is free once the TMA stores issued from it (1 or 2 tiles ago) have read it
+        if (store_thread) {
+          if (stage_bufs == 2) ptx::bulk_wait_read_1();
+          else ptx::bulk_wait_read_all();
+        }
+        ptx::named_bar_sync(2, 256);
+        if (++sb == stage_bufs) sb = 0;
+      }
       ptx::mbar_wait(bar_tfull + 8 * buf, acc_ph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * 2 * n_tile);
-      for (int n = 0; n < n_tile; n += 16) {
+      for (int n = 16 * eset; n < n_tile; n += 32) {
         const int cg = n0 + n;
         uint32_t r1[16], r2[16];
         ptx::tmem_ld16(t_row + static_cast<uint32_t>(n), r1);
@@ -525,52 +560,70 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
             c0 = cg - sub * cq;
             opix = static_cast<long long>(2 * oy + (sub >> 1)) * (2 * Wo) + (2 * ox + (sub & 1));
           }
-          const bool live = valid && cg < cout;
-          float4 a1[4], a2[4], gx[4], b4[4];
+          const bool live = (valid || use_tma) && cg < cout;
+          float4 b4v[4];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const bool on = live && (cg + 4 * g < cout);
-            a1[g] = a2[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-            gx[g] = b4[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (on) {
-              b4[g] = __ldg(reinterpret_cast<const float4 *>(bias + cg) + g);
-              if (res1) a1[g] = reinterpret_cast<const float4 *>(res1 + opix * res1_pitch + c0)[g];
-              if (res2) a2[g] = reinterpret_cast<const float4 *>(res2 + opix * res2_pitch + c0)[g];
-              if (epi != LSSVC_EPI_PLAIN) gx[g] = reinterpret_cast<const float4 *>(gdn_x + pix * gdn_pitch + cg)[g];
-            }
-          }
+          for (int g = 0; g < 4; ++g)
+            b4v[g] = (live && cg + 4 * g < cout) ? __ldg(reinterpret_cast<const float4 *>(bias + cg) + g)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
           ptx::tmem_ld_wait();
           if (live) {
             float4 *const o = reinterpret_cast<float4 *>(out + opix * out_pitch + c0);
             float4 *const o2 = out2 ? reinterpret_cast<float4 *>(out2 + opix * out2_pitch + c0) : nullptr;
+            const float4 *const q1 = (res1 && valid) ? reinterpret_cast<const float4 *>(res1 + opix * res1_pitch + c0) : nullptr;
+            const float4 *const q2 = (res2 && valid) ? reinterpret_cast<const float4 *>(res2 + opix * res2_pitch + c0) : nullptr;
+            const float4 *const gq = (epi != LSSVC_EPI_PLAIN && valid) ? reinterpret_cast<const float4 *>(gdn_x + pix * gdn_pitch + cg) : nullptr;
+            // staging row of this pixel for the slab holding channels n .. n+15 (TMA-store path)
+            const uint32_t srow = static_cast<uint32_t>(n / slab_w) * (128u * slab_w * 4u) + static_cast<uint32_t>(m) * (slab_w * 4u);
+            const uint32_t sswz = (slab_w == 32 ? static_cast<uint32_t>(m & 7) : static_cast<uint32_t>((m >> 1) & 3)) << 4;
+            const uint32_t spiece = static_cast<uint32_t>(n % slab_w) << 2;  // byte offset of the chunk inside the row
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (cg + 4 * g < cout) {
+                const float4 b4 = b4v[g];
                 float v[4];
-                v[0] = (__uint_as_float(r1[4 * g + 0]) + __uint_as_float(r2[4 * g + 0])) * acc_scale + b4[g].x;
-                v[1] = (__uint_as_float(r1[4 * g + 1]) + __uint_as_float(r2[4 * g + 1])) * acc_scale + b4[g].y;
-                v[2] = (__uint_as_float(r1[4 * g + 2]) + __uint_as_float(r2[4 * g + 2])) * acc_scale + b4[g].z;
-                v[3] = (__uint_as_float(r1[4 * g + 3]) + __uint_as_float(r2[4 * g + 3])) * acc_scale + b4[g].w;
-                if (epi == LSSVC_EPI_GDN) {
-                  v[0] = gx[g].x * rsqrtf(v[0]); v[1] = gx[g].y * rsqrtf(v[1]);
-                  v[2] = gx[g].z * rsqrtf(v[2]); v[3] = gx[g].w * rsqrtf(v[3]);
-                } else if (epi == LSSVC_EPI_IGDN) {
-                  v[0] = gx[g].x * sqrtf(v[0]); v[1] = gx[g].y * sqrtf(v[1]);
-                  v[2] = gx[g].z * sqrtf(v[2]); v[3] = gx[g].w * sqrtf(v[3]);
+                v[0] = (__uint_as_float(r1[4 * g + 0]) + __uint_as_float(r2[4 * g + 0])) * acc_scale + b4.x;
+                v[1] = (__uint_as_float(r1[4 * g + 1]) + __uint_as_float(r2[4 * g + 1])) * acc_scale + b4.y;
+                v[2] = (__uint_as_float(r1[4 * g + 2]) + __uint_as_float(r2[4 * g + 2])) * acc_scale + b4.z;
+                v[3] = (__uint_as_float(r1[4 * g + 3]) + __uint_as_float(r2[4 * g + 3])) * acc_scale + b4.w;
+                if (epi != LSSVC_EPI_PLAIN) {
+                  const float4 gx = gq ? gq[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (epi == LSSVC_EPI_GDN) {
+                    v[0] = gx.x * rsqrtf(v[0]); v[1] = gx.y * rsqrtf(v[1]);
+                    v[2] = gx.z * rsqrtf(v[2]); v[3] = gx.w * rsqrtf(v[3]);
+                  } else {
+                    v[0] = gx.x * sqrtf(v[0]); v[1] = gx.y * sqrtf(v[1]);
+                    v[2] = gx.z * sqrtf(v[2]); v[3] = gx.w * sqrtf(v[3]);
+                  }
                 }
                 if (has_act) {
 #pragma unroll
                   for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
                 }
-                v[0] = v[0] * out_scale + a1[g].x + a2[g].x;
-                v[1] = v[1] * out_scale + a1[g].y + a2[g].y;
-                v[2] = v[2] * out_scale + a1[g].z + a2[g].z;
-                v[3] = v[3] * out_scale + a1[g].w + a2[g].w;
-                o[g] = make_float4(v[0], v[1], v[2], v[3]);
-                if (o2) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] *= out_scale;
+                if (q1) {
+                  const float4 t = q1[g];
+                  v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                }
+                if (q2) {
+                  const float4 t = q2[g];
+                  v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                }
+                const uint32_t soff = srow + ((spiece + 16u * g) ^ sswz);
+                if (use_tma) {
+                  ptx::sts_u4(stage + soff, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                } else {
+                  o[g] = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                if (out2) {
 #pragma unroll
                   for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope2;
-                  o2[g] = make_float4(v[0], v[1], v[2], v[3]);
+                  if (use_tma) {
+                    ptx::sts_u4(stage2 + soff, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                  } else {
+                    o2[g] = make_float4(v[0], v[1], v[2], v[3]);
+                  }
                 }
               }
             }
@@ -602,11 +655,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
+      if (use_tma) {
+        ptx::fence_proxy_async_smem();  // staging writes (generic proxy) -> visible to the TMA store (async proxy)
+        ptx::named_bar_sync(3, 256);
+        if (store_thread) {
+          const int oy0 = ty * TILE_H, ox0 = tx * TILE_W;
+          for (int k = 0; k < p.n_slabs; ++k) {
+            const int pc = n0 + k * static_cast<int>(slab_w);  // first packed channel of the slab
+            if (pc >= cout) break;
+            const uint32_t src = static_cast<uint32_t>(k) * (128u * slab_w * 4u);
+            if (ps) {
+              const int sub = pc / cq, c0 = pc - sub * cq;
+              ptx::tma_store_5d(&p.out_map, stage + src, c0, sub & 1, ox0, sub >> 1, oy0);
+              if (out2) ptx::tma_store_5d(&p.out2_map, stage2 + src, c0, sub & 1, ox0, sub >> 1, oy0);
+            } else {
+              ptx::tma_store_3d(&p.out_map, stage + src, pc, ox0, oy0);
+              if (out2) ptx::tma_store_3d(&p.out2_map, stage2 + src, pc, ox0, oy0);
+            }
+          }
+          ptx::bulk_commit();
+        }
+      }
       if (++buf == d_bufs) {
         buf = 0;
         acc_ph ^= 1u;
       }
     }
+    if (use_tma && store_thread) ptx::bulk_wait_all();
   }
 
   ptx::tc_fence_before();
@@ -811,18 +886,6 @@ extern "C" int32_t lssvc_conv_h2(const lssvc_conv *c, void *stream) {
   p.halo_rows = halo_w * halo_h;
   p.halo_bytes = (p.halo_tx + 1023) & ~1023;
   p.b_bytes = tps * (2 * n_tile * kc * 2);  // n_tile % 16 == 0 keeps every tile 1024-byte aligned
-  const int smem_budget = 224 * 1024;
-  // as many halo tiles in flight as fit next to the weight ring: HBM latency x bandwidth wants > 64 KB per SM
-  p.halo_bufs = MAX_HALO;
-  {
-    const int want_slots = p.slots < 4 ? p.slots : 4;
-    while (p.halo_bufs > 2 && p.halo_bufs * p.halo_bytes + want_slots * p.b_bytes + 1024 > smem_budget) --p.halo_bufs;
-  }
-  while (p.slots > 2 && p.halo_bufs * p.halo_bytes + p.slots * p.b_bytes + 1024 > smem_budget) --p.slots;
-  LSSVC_REQUIRE(p.slots >= 2 && p.halo_bufs * p.halo_bytes + p.slots * p.b_bytes + 1024 <= smem_budget,
-                "conv_h2: pipeline does not fit in shared memory (halo %d B x %d, weights %d B x %d)", p.halo_bytes,
-                p.halo_bufs, p.b_bytes, p.slots);
-
   p.in_transform = c->in_transform;
   p.in_slope = c->in_slope;
   p.acc_scale = c->acc_scale;
@@ -855,6 +918,73 @@ extern "C" int32_t lssvc_conv_h2(const lssvc_conv *c, void *stream) {
     vec = vec && (c->gdn_x.pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(c->gdn_x.ptr) & 15) == 0);
   }
   p.vec_ok = vec ? 1 : 0;
+
+  // ---- TMA-store epilogue: the output tile is staged in shared memory as 128-byte (or 64-byte) swizzled rows
+  // per slab of 32 (16) channels and written with cp.async.bulk.tensor stores (fully coalesced, clipped at the
+  // image border and at the view's last channel).  Needs vectorisable views; with PixelShuffle a slab must not
+  // straddle two sub-pixels.
+  const int cq = c->cout / 4;
+  int slab_w = 32;
+  const bool no_tma_env = getenv("LSSVC_H2_NOTMA") != nullptr;  // A/B switch for the epilogue store path (tools/find_tma_bug.py)
+  bool use_tma = vec && !no_tma_env && (!c->pixel_shuffle || cq % 16 == 0);
+  // a slab must be fully owned by this tile's channels (n_tile % slab_w == 0) and, with PixelShuffle, by one sub-pixel
+  if (n_tile % 32 != 0 || (c->pixel_shuffle && cq % 32 != 0)) slab_w = 16;
+  int stage_bytes = 0;
+  if (use_tma) {
+    p.slab_w = slab_w;
+    p.n_slabs = (n_tile + slab_w - 1) / slab_w;
+    stage_bytes = p.n_slabs * 128 * slab_w * 4;
+  }
+  const int smem_budget = 224 * 1024;
+  auto fits = [&](int halos, int slots, int stages) {
+    return halos * p.halo_bytes + slots * p.b_bytes + stages * stage_bytes + 1024 <= smem_budget;
+  };
+  const int per_buf = use_tma ? (p.out2 ? 2 : 1) : 0;  // staging tiles per buffer (out, out2)
+  // staging only when it leaves room for a healthy operand pipeline (>= 3 halo tiles, the TMEM-limited slots up to 4)
+  const int want_slots = p.slots < 4 ? p.slots : 4;
+  int n_stage = 0;
+  p.stage_bufs = 0;
+  if (per_buf && fits(4, want_slots, 2 * per_buf)) { n_stage = 2 * per_buf; p.stage_bufs = 2; }
+  else if (per_buf && fits(3, want_slots, per_buf)) { n_stage = per_buf; p.stage_bufs = 1; }
+  else use_tma = false;
+  // as many halo tiles in flight as fit next to the weight ring: HBM latency x bandwidth wants > 64 KB per SM
+  p.halo_bufs = MAX_HALO;
+  while (p.halo_bufs > 3 && !fits(p.halo_bufs, want_slots, n_stage)) --p.halo_bufs;
+  while (p.slots > 2 && !fits(p.halo_bufs, p.slots, n_stage)) --p.slots;
+  while (p.halo_bufs > 2 && !fits(p.halo_bufs, p.slots, n_stage)) --p.halo_bufs;
+  LSSVC_REQUIRE(p.slots >= 2 && fits(p.halo_bufs, p.slots, n_stage),
+                "conv_h2: pipeline does not fit in shared memory (halo %d B x %d, weights %d B x %d, staging %d B x %d)",
+                p.halo_bytes, p.halo_bufs, p.b_bytes, p.slots, stage_bytes, n_stage);
+  p.stage_stride = per_buf * stage_bytes;
+  p.use_tma = use_tma ? 1 : 0;
+  p.stage_off = p.halo_bufs * p.halo_bytes + p.slots * p.b_bytes;
+  p.stage2_off = p.stage_off + stage_bytes;
+  if (use_tma) {
+    auto make_out_map = [&](CUtensorMap *m, const lssvc_view &v) -> CUresult {
+      const cuuint64_t px = static_cast<cuuint64_t>(v.pitch) * 4;
+      const CUtensorMapSwizzle sw = slab_w == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+      if (c->pixel_shuffle) {
+        // [2Ho][2Wo][cq] viewed as [Ho][2][Wo][2][cq]: one box per sub-pixel (i, j)
+        const cuuint64_t dims[5] = {static_cast<cuuint64_t>(v.C), 2, static_cast<cuuint64_t>(Wo), 2, static_cast<cuuint64_t>(Ho)};
+        const cuuint64_t strides[4] = {px, px * 2, px * 2 * Wo, px * 2 * Wo * 2};
+        const cuuint32_t box[5] = {static_cast<cuuint32_t>(slab_w), 1, TILE_W, 1, TILE_H};
+        return g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, v.ptr, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+      const cuuint64_t dims[3] = {static_cast<cuuint64_t>(v.C), static_cast<cuuint64_t>(Wo), static_cast<cuuint64_t>(Ho)};
+      const cuuint64_t strides[2] = {px, px * Wo};
+      const cuuint32_t box[3] = {static_cast<cuuint32_t>(slab_w), TILE_W, TILE_H};
+      return g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, v.ptr, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUresult r = make_out_map(&p.out_map, c->out);
+    if (r == CUDA_SUCCESS && p.out2) r = make_out_map(&p.out2_map, c->out2);
+    if (r != CUDA_SUCCESS) {
+      lssvc::set_error("conv_h2: cuTensorMapEncodeTiled(out) failed with %d (C=%d pitch=%d %dx%d ps=%d)", static_cast<int>(r),
+                       c->out.C, c->out.pitch, Ho, Wo, c->pixel_shuffle);
+      return LSSVC_ERR_CUDA;
+    }
+  }
   {
     // bottleneck isolation (tools/conv_bench.py): 1 no MMAs, 2 no halo reads, 4 no TMEM stores, 8 no global
     // stores, 16 no halo TMA, 32 no weight TMA.  Never set outside profiling: the output is garbage.
@@ -864,7 +994,8 @@ extern "C" int32_t lssvc_conv_h2(const lssvc_conv *c, void *stream) {
 
   const int total_tiles = p.tiles_x * p.tiles_y * p.n_tiles;
   const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
-  const size_t smem = static_cast<size_t>(p.halo_bufs) * p.halo_bytes + static_cast<size_t>(p.slots) * p.b_bytes + 1024;
+  const size_t smem = static_cast<size_t>(p.halo_bufs) * p.halo_bytes + static_cast<size_t>(p.slots) * p.b_bytes +
+                      static_cast<size_t>(n_stage) * stage_bytes + 1024;
   const int ki = kc == 32 ? 0 : 1;
   cudaStream_t s = lssvc::as_stream(stream);
   if (!g_attr_set[ki]) {

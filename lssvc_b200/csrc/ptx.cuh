@@ -93,7 +93,7 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 }
 static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
-  while (!mbar_try_wait_hint(bar, parity)) {
+  while (!mbar_try_wait(bar, parity)) {  // plain try_wait suspends in hardware; the hinted form was measured to spin
     if (clock64() - t0 > 8000000000LL) __trap();
   }
 }
@@ -141,6 +141,26 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void *map, uint3
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+
+// TMA stores (shared -> global, bulk async group): OOB parts of the box are clipped
+__device__ __forceinline__ void tma_store_3d(const void *map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const void *map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent one
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- tcgen05 -------------------------------------------------------------------------------
 // Whole warp; writes the TMEM base address of `ncols` (power of two >= 32) columns to smem.

@@ -52,6 +52,9 @@ CONV_CASES = [
     ("ps_64_12", [64], [64], 12, 3, 1, 16, 16, True),
     ("odd_170_149", [170], [176], 149, 3, 1, 12, 20, False),
     ("1x1_s2_down", [64], [64], 64, 1, 2, 32, 32, False),
+    ("3x3_s2_64_144_ntile48", [64], [64], 144, 3, 2, 64, 64, False),   # 3 channel tiles of 48: 16-wide store slabs
+    ("ps_128_192_cq48", [128], [128], 192, 3, 1, 20, 36, True),        # PixelShuffle with 48 channels per sub-pixel
+    ("ps_64_128_cq32", [64], [64], 128, 1, 1, 24, 40, True),           # PixelShuffle, 32-wide store slabs
 ]
 
 

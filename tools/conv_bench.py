@@ -25,6 +25,7 @@ SHAPES = [
     ("3x3 s2 64->64 @1->1/2", [64], 64, 3, 2, 1152, 1920, False),
     ("7x7 32->64 @1/2", [32], 64, 7, 1, 576, 960, False),
     ("7x7 64->32 @1", [64], 32, 7, 1, 1152, 1920, False),
+    ("1x1 64->64 @1", [64], 64, 1, 1, 1152, 1920, False),
     ("1x1 64->256 @1", [64], 256, 1, 1, 1152, 1920, False),
     ("1x1 256->64 @1", [256], 64, 1, 1, 1152, 1920, False),
     ("3x3 192->192 @1/8(BL)", [192], 192, 3, 1, 144, 240, False),
