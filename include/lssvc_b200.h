@@ -104,6 +104,23 @@ typedef struct {
   float acc_scale;
 } lssvc_conv;
 
+/*
+ * Fused ConvFFN of DepthConvBlock (lssvc_modules.py:42-60):
+ *   out = in + lrelu(W2 . lrelu(W1 . in + b1, slope1) + b2, slope2)  (+ res2),   W1: C -> hidden, W2: hidden -> C (1x1)
+ * in.C = C in {16, 32, 48, 64}, hidden a multiple of 64 with 8 * C * hidden <= 128 KiB (weights stay in shared memory).
+ * w1: fp16 [hidden/32][C/16][2 (hi, lo)][32][16]   = split of W1 * 2^shift1 (rows = hidden channel, 16 input channels)
+ * w2: fp16 [hidden/32][2][2 (hi, lo)][C][16]       = split of W2 * 2^shift2 (rows = output channel, 16 hidden channels)
+ * both with the two 16-byte halves of row r swapped when (r >> 2) & 1 (SWIZZLE_32B image); scaleN = 2^-shiftN.
+ */
+typedef struct {
+  lssvc_view in, out, res2;
+  int32_t hidden;
+  const void *w1, *w2;
+  const float *b1, *b2; /* [hidden], [C] */
+  float scale1, scale2;
+  float slope1, slope2;
+} lssvc_ffn;
+
 /* ---- library ---------------------------------------------------------------------------- */
 int32_t lssvc_abi_version(void);
 /* 0 when device `dev` is sm_100-class and the driver entry points needed for TMA resolve. */
@@ -119,6 +136,8 @@ int32_t lssvc_conv_tc(const lssvc_conv *c, void *stream);
  * (fp32 halo tile by TMA -> hi/lo fp16 -> tensor memory), weights are pre-split (weight_h2).  Any kernel size,
  * stride 1 or 2, up to 3 concatenated sources, input transform (GDN's x^2), GDN / IGDN epilogue. */
 int32_t lssvc_conv_h2(const lssvc_conv *c, void *stream);
+/* fused 1x1 -> LeakyReLU -> 1x1 -> LeakyReLU -> + identity block (see lssvc_ffn) */
+int32_t lssvc_conv_ffn(const lssvc_ffn *f, void *stream);
 /* fp32 CUDA-core implicit GEMM: any shape, also hosts the GDN epilogue and input transforms. */
 int32_t lssvc_conv_simt(const lssvc_conv *c, void *stream);
 /* depthwise 3x3, pad 1 (lssvc_modules.py:23-24): weight [9][C], bias [C] */

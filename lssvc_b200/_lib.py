@@ -52,6 +52,12 @@ class CConv(Structure):
     ]
 
 
+class CFfn(Structure):
+    _fields_ = [("inp", CView), ("out", CView), ("res2", CView), ("hidden", c_int32), ("w1", c_void_p), ("w2", c_void_p),
+                ("b1", c_void_p), ("b2", c_void_p), ("scale1", c_float), ("scale2", c_float), ("slope1", c_float),
+                ("slope2", c_float)]
+
+
 _PV = POINTER(CView)
 _SIGNATURES = {
     # name: (restype, argtypes)
@@ -61,6 +67,7 @@ _SIGNATURES = {
     "lssvc_launch_count": (c_int64, []),
     "lssvc_conv_tc": (c_int32, [POINTER(CConv), c_void_p]),
     "lssvc_conv_h2": (c_int32, [POINTER(CConv), c_void_p]),
+    "lssvc_conv_ffn": (c_int32, [POINTER(CFfn), c_void_p]),
     "lssvc_conv_simt": (c_int32, [POINTER(CConv), c_void_p]),
     "lssvc_dwconv3x3": (c_int32, [_PV, c_void_p, c_void_p, _PV, c_void_p]),
     "lssvc_deconv3x3_s2": (c_int32, [_PV, c_void_p, c_void_p, c_int32, c_float, _PV, c_void_p]),

@@ -142,6 +142,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void *map, uint3
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (bytes a multiple of 16), completes on an mbarrier like a tensor load
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, int bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
 // TMA stores (shared -> global, bulk async group): OOB parts of the box are clipped
 __device__ __forceinline__ void tma_store_3d(const void *map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(

@@ -2,6 +2,8 @@
 (conv + epilogue, ResBlock, DepthConvBlock, GDN, SpyNet, 3-scale extractor / fusion) expressed on the kernels.
 
 A model is a nets.ParamBag (reference-layout tensors) + this mixin.  Activations are `ops.View`s (NHWC fp32)."""
+import os
+
 import torch
 
 from . import _lib, nets, ops
@@ -12,6 +14,7 @@ class Engine(nets.ParamBag):
     def __init__(self, spec, model_tag, seed=None):
         super().__init__(spec, seed=seed, gains=nets.model_gains(model_tag))
         self._packs = {}
+        self.fuse_ffn = os.environ.get("LSSVC_FUSE_FFN", "1") != "0"
         self.shape_hr = (256, 256)
         self.scale_factor = 2.0
         self.pad_size = (0, 0, 0, 0)
@@ -209,6 +212,19 @@ class Engine(nets.ParamBag):
         has_adaptor = (dc + ".adaptor.weight") in self._spec
         identity = self.conv(dc + ".adaptor", x, pad=0) if has_adaptor else x
         o = self.conv(dc + ".conv2", t, pad=0, res1=identity)
+        w1 = self.tensor(ffn + ".conv.0.weight")
+        hidden, C = w1.shape[0], w1.shape[1]
+        if (self.fuse_ffn and ops.default_engine() == "h2" and ops.PackedFfn.supported(C, hidden) and o.C == C
+                and o.pitch % 4 == 0 and o.coff % 4 == 0):
+            # fused ConvFFN: the 4x-wide intermediate stays in tensor memory (csrc/conv_ffn.cu)
+            pf = self.cached(("ffn", ffn), lambda: ops.PackedFfn(w1, self.tensor(ffn + ".conv.0.bias"),
+                                                                 self.tensor(ffn + ".conv.2.weight"),
+                                                                 self.tensor(ffn + ".conv.2.bias"), self.device))
+            out = out if out is not None else self.new(o.H, o.W, C)
+            ox = out.exact()
+            if ox.pitch % 4 == 0 and ox.coff % 4 == 0 and (res2 is None or (res2.pitch % 4 == 0 and res2.coff % 4 == 0)):
+                ops.ffn(pf, o.exact(), ox, res2=None if res2 is None else res2.exact())
+                return out
         f = self.conv(ffn + ".conv.0", o, act=0.1, pad=0)
         return self.conv(ffn + ".conv.2", f, act=0.1, pad=0, res1=o, res2=res2, out=out)
 

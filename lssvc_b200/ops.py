@@ -291,6 +291,70 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
     return out
 
 
+class PackedFfn:
+    """Weights of one ConvFFN (two 1x1 convs, lssvc_modules.py:42-60) packed for lssvc_conv_ffn: split fp16 hi/lo of
+    W * 2^shift in [chunk of 32 hidden channels][16-wide K slice][hi | lo][row][16] sub-tiles whose 32-byte rows carry
+    the SWIZZLE_32B pattern (16-byte halves swapped when (row >> 2) & 1), so a plain bulk copy lands them UMMA-ready."""
+
+    __slots__ = ("w1", "w2", "b1", "b2", "scale1", "scale2", "C", "hidden")
+
+    @staticmethod
+    def supported(C, hidden):
+        return C % 16 == 0 and 16 <= C <= 64 and hidden % 64 == 0 and hidden >= 64 and 8 * C * hidden + 3 * 128 * C * 4 <= 224 * 1024
+
+    def __init__(self, w1, b1, w2, b2, device):
+        w1 = w1.detach().to(torch.float32).cpu().reshape(w1.shape[0], w1.shape[1])     # [hidden, C]
+        w2 = w2.detach().to(torch.float32).cpu().reshape(w2.shape[0], w2.shape[1])     # [C, hidden]
+        hidden, C = w1.shape
+        assert w2.shape == (C, hidden) and PackedFfn.supported(C, hidden), (C, hidden)
+
+        def scaled(w):
+            m = float(w.abs().max())
+            shift = 0 if m == 0.0 else 13 - int(math.floor(math.log2(m)))
+            return w * (2.0 ** shift), 2.0 ** -shift
+
+        def split(w):
+            hi = w.to(torch.float16)
+            return hi, (w - hi.to(torch.float32)).to(torch.float16)
+
+        def swizzle(t):                     # t: [..., rows, 16] fp16 -> same shape, halves swapped on rows with (r >> 2) & 1
+            rows = t.shape[-2]
+            t = t.reshape(*t.shape[:-1], 2, 8)
+            swap = ((torch.arange(rows) >> 2) & 1).bool()
+            out = t.clone()
+            out[..., swap, 0, :] = t[..., swap, 1, :]
+            out[..., swap, 1, :] = t[..., swap, 0, :]
+            return out.reshape(*out.shape[:-2], 16)
+
+        w1s, self.scale1 = scaled(w1)
+        w2s, self.scale2 = scaled(w2)
+        n_chunks = hidden // 32
+        # W1: rows = hidden channel of the chunk, K = input channel     -> [chunk][ks][hi|lo][32][16]
+        h1, l1 = split(w1s)
+        t1 = torch.stack([h1, l1], 0).reshape(2, n_chunks, 32, C // 16, 16).permute(1, 3, 0, 2, 4)
+        # W2: rows = output channel, K = hidden channel of the chunk    -> [chunk][ks][hi|lo][C][16]
+        h2, l2 = split(w2s)
+        t2 = torch.stack([h2, l2], 0).reshape(2, C, n_chunks, 2, 16).permute(2, 3, 0, 1, 4)
+        # rows of a sub-tile run over (hi|lo, row): the swizzle pattern follows the row index inside the sub-tile
+        self.w1 = swizzle(t1.reshape(n_chunks, C // 16, 64, 16)).contiguous().to(device)
+        self.w2 = swizzle(t2.reshape(n_chunks, 2, 2 * C, 16)).contiguous().to(device)
+        self.b1 = b1.detach().to(torch.float32).contiguous().to(device)
+        self.b2 = b2.detach().to(torch.float32).contiguous().to(device)
+        self.C, self.hidden = C, hidden
+
+
+def ffn(pf, x, out, slope1=0.1, slope2=0.1, res2=None):
+    """out = x + lrelu(W2 . lrelu(W1 . x + b1, slope1) + b2, slope2) (+ res2), one fused kernel."""
+    d = _lib.CFfn()
+    d.inp, d.out, d.res2 = x.c(), out.c(), _cv(res2)
+    d.hidden = pf.hidden
+    d.w1, d.w2, d.b1, d.b2 = pf.w1.data_ptr(), pf.w2.data_ptr(), pf.b1.data_ptr(), pf.b2.data_ptr()
+    d.scale1, d.scale2, d.slope1, d.slope2 = pf.scale1, pf.scale2, float(slope1), float(slope2)
+    lib = _lib.load()
+    _lib.check(lib.lssvc_conv_ffn(byref(d), _stream()), "conv_ffn")
+    return out
+
+
 def dwconv3x3(x, weight9c, bias, out):
     lib = _lib.load()
     _lib.check(lib.lssvc_dwconv3x3(byref(x.c()), _ptr(weight9c), _ptr(bias), byref(out.c()), _stream()), "dwconv3x3")

@@ -144,6 +144,33 @@ def test_conv_h2_large_persistent(cuda_device):
     assert err < 5e-6, err
 
 
+@pytest.mark.parametrize("C,hidden,H,W,with_res", [(64, 256, 40, 56, False), (48, 192, 33, 50, True), (32, 128, 64, 96, False),
+                                                   (64, 256, 160, 272, True)])
+def test_conv_ffn_fused(C, hidden, H, W, with_res, cuda_device):
+    """Fused ConvFFN (csrc/conv_ffn.cu) against the fp64 torch composition of lssvc_modules.py:42-60."""
+    ops = _ops()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(C + hidden)
+    x = torch.randn(1, C, H, W, generator=g).to(dev)
+    w1 = (torch.randn(hidden, C, 1, 1, generator=g) / math.sqrt(C)).to(dev)
+    b1 = torch.randn(hidden, generator=g).to(dev)
+    w2 = (torch.randn(C, hidden, 1, 1, generator=g) / math.sqrt(hidden)).to(dev)
+    b2 = torch.randn(C, generator=g).to(dev)
+    res = torch.randn(1, C, H, W, generator=g).to(dev)
+    pf = ops.PackedFfn(w1, b1, w2, b2, dev)
+    out = ops.View.alloc(H, W, C, dev, zero=True)
+    ops.ffn(pf, make_view(x, ops), out, res2=make_view(res, ops) if with_res else None)
+    torch.cuda.synchronize()
+    xd = x.double()
+    f = F.leaky_relu(F.conv2d(xd, w1.double(), b1.double()), 0.1)
+    ref = xd + F.leaky_relu(F.conv2d(f, w2.double(), b2.double()), 0.1)
+    if with_res:
+        ref = ref + res.double()
+    err = rel_err(out.to_nchw(), ref.float())
+    print(f"fused ffn C={C} hidden={hidden} {H}x{W}: rel err {err:.3e}")
+    assert err < 5e-6, err
+
+
 def test_conv_tc3_large_persistent(cuda_device):
     err = _run_conv_case(("big", [64], [64], 64, 3, 1, 256, 320, False), "tc3", cuda_device, True)
     assert err < 2e-5, err
