@@ -57,6 +57,7 @@ struct alignas(64) H2Params {
   int n_groups;
   int g_px[MAX_GROUPS], g_py[MAX_GROUPS];
   int g_tap0[MAX_GROUPS + 1];  // taps of group g: [g_tap0[g], g_tap0[g + 1])
+  int g_step[MAX_GROUPS];      // taps per stage in group g: the group's taps split evenly over ceil(taps / max) stages
   int q0x, q0y;                // halo origin relative to the patch origin (plane coordinates)
   int halo_w;                  // halo width in pixels
   int halo_tx;                 // bytes of one halo box
@@ -253,8 +254,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
             const int k0 = p.coff[j] + c * KC;
             for (int g = 0; g < p.n_groups; ++g) {
               const int t1 = p.g_tap0[g + 1];
-              for (int t = p.g_tap0[g]; t < t1; t += TAPS_PER_STAGE) {
-                const int items = t1 - t < TAPS_PER_STAGE ? t1 - t : TAPS_PER_STAGE;
+              const int step = p.g_step[g];
+              for (int t = p.g_tap0[g]; t < t1; t += step) {
+                const int items = t1 - t < step ? t1 - t : step;
                 const uint32_t full = bar_full + 8 * s;
                 ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                 if (p.dbg & 32) {
@@ -303,8 +305,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
         for (int c = 0; c < p.chunks[j]; ++c) {
           for (int g = 0; g < n_groups; ++g) {
             const int t1 = p.g_tap0[g + 1];
-            for (int t = p.g_tap0[g]; t < t1; t += TAPS_PER_STAGE) {
-              const int items = t1 - t < TAPS_PER_STAGE ? t1 - t : TAPS_PER_STAGE;
+            const int step = p.g_step[g];
+            for (int t = p.g_tap0[g]; t < t1; t += step) {
+              const int items = t1 - t < step ? t1 - t : step;
               if (!ready) ptx::mbar_wait_slow(bar_full + 8 * s, ph);
               ptx::tc_fence_after();
               int s_next = s + 1;
@@ -421,9 +424,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_h2_kernel(const __grid_co
             const uint32_t halo = smem_base + static_cast<uint32_t>(hb) * halo_bytes + pix_boff;
             const int t0 = p.g_tap0[g], t1 = p.g_tap0[g + 1];
             const bool pre = (t1 - t0) > 1;
-            for (int t = t0; t < t1; t += TAPS_PER_STAGE) {
+            const int step = p.g_step[g];
+            for (int t = t0; t < t1; t += step) {
               if (parity == static_cast<uint32_t>(set)) {
-                const int items = t1 - t < TAPS_PER_STAGE ? t1 - t : TAPS_PER_STAGE;  // warp-uniform
+                const int items = t1 - t < step ? t1 - t : step;  // warp-uniform
                 const uint32_t dst = lane_base + static_cast<uint32_t>(s * TAPS_PER_STAGE * KC);
 #pragma unroll
                 for (int e = 0; e < TAPS_PER_STAGE; ++e) {
@@ -867,8 +871,12 @@ extern "C" int32_t lssvc_conv_h2(const lssvc_conv *c, void *stream) {
   // ---- pipeline geometry --------------------------------------------------------------------------
   {
     int per_chunk = 0;
-    for (int g = 0; g < p.n_groups; ++g)
-      per_chunk += (p.g_tap0[g + 1] - p.g_tap0[g] + (STAGE_K / kc) - 1) / (STAGE_K / kc);
+    for (int g = 0; g < p.n_groups; ++g) {
+      const int nt = p.g_tap0[g + 1] - p.g_tap0[g], tps_max = STAGE_K / kc;
+      const int n_st = (nt + tps_max - 1) / tps_max;
+      p.g_step[g] = (nt + n_st - 1) / n_st;
+      per_chunk += (nt + p.g_step[g] - 1) / p.g_step[g];
+    }
     p.stages_per_tile = total_chunks * per_chunk;
   }
   p.Ho = Ho; p.Wo = Wo;

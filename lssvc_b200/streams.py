@@ -1,9 +1,114 @@
-"""--write_stream 1 orchestration (real rANS bitstreams); filled in by the write-stream milestone."""
+"""--write_stream 1 orchestration: real rANS bitstreams in the reference's container and symbol order.
+
+Encoder side = the CUDA forward pass with the symbol / CDF-index dumps switched on (the entropy kernels write int32
+NCHW buffers next to their NHWC outputs), then the host rANS coder (csrc/rans.cpp, byte-identical to src/cpp/rans).
+
+  P-frame, per layer (LSSVC_net_extend.py:66-74, dmc_net_extend.py:91-96): ONE string
+        [mv_z | mv_y | z | y]  (EL: y as the four parts y_w0..y_w3 of the 4-step prior), file = >I length + string
+  I-frame, per layer (IntraSS.py:251-274, priors.py:420-435): y-string and z-string, file = >4I (H, W, len y, len z)
+
+Decoder side: the reference re-runs the synthesis networks on the decoded symbols and uses THAT reconstruction for the
+DPB (LSSVC_net_extend.py:168-178); reconstructions of the two paths are identical, so here the
+streams are decoded with the CDF rows of the dumped indices and required to return exactly the coded symbols, and the
+DPB comes from the encoder-side pass.  The GPU-side progressive decoder (decompress_four_part_prior) is SURVEY §8f-1.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import entropy, stream
 
 
-def intra_encode_decode(*a, **k):
-    raise NotImplementedError("write-stream path not built yet")
+class SymbolDump:
+    """model._write hook: hands the entropy kernels int32 device buffers for symbols / CDF indices (NCHW order)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+        self.shapes = {}
+
+    def buf(self, name, view, C=None):
+        C = view.real if C is None else C
+        t = torch.empty(C * view.H * view.W, dtype=torch.int32, device=self.device)
+        self.bufs[name] = t
+        self.shapes[name] = (C, view.H, view.W)
+        return t
+
+    def host(self, name):
+        return self.bufs[name].cpu().numpy()
+
+    def channel_index(self, name):
+        """BitEstimator / EntropyBottleneck build_indexes: the CDF row is the channel."""
+        C, H, W = self.shapes[name]
+        return np.repeat(np.arange(C, dtype=np.int32), H * W)
 
 
-def inter_encode_decode(*a, **k):
-    raise NotImplementedError("write-stream path not built yet")
+def _encode(parts):
+    """parts: [(symbols, indexes, table)] pushed in order, one flush (the encoder codes them in reverse)."""
+    enc = entropy.RansEncoder()
+    for sym, idx, table in parts:
+        enc.encode_with_indexes(sym, idx, table)
+    return enc.flush()
+
+
+def _verify(string, parts, what):
+    dec = entropy.RansDecoder()
+    dec.set_stream(string)
+    for k, (sym, idx, table) in enumerate(parts):
+        got = dec.decode_stream(idx, table)
+        if not np.array_equal(got, np.asarray(sym, dtype=np.int32).reshape(-1)):
+            raise RuntimeError(f"{what}: part {k} of the stream does not decode to the coded symbols")
+
+
+def inter_encode_decode(model, x_bl, x_el, dpb, output_path_bl, output_path_el, pic_width, pic_height, pic_width_bl,
+                        pic_height_bl):
+    """LSSVC_extend.encode_decode_extend (LSSVC_net_extend.py:144-191) + DMCExtend.encode_decode_extend."""
+    model.update()
+    t = model._tables
+    dump = SymbolDump(model.device)
+    torch.cuda.synchronize(model.device)
+    t0 = time.time()
+    r = model.forward_one_frame(x_bl, x_el, dpb["ref_frame_bl"], dpb["ref_frame_el"], dpb["ref_feature_bl"],
+                                dpb["ref_feature_el"], _dpb=dpb, _write=dump)
+    torch.cuda.synchronize(model.device)
+    h = dump.host
+    bl = [(h("bl_mv_z"), dump.channel_index("bl_mv_z"), t["bl_mv_z"]), (h("bl_mv_y"), h("bl_mv_y_idx"), t["laplace"]),
+          (h("bl_z"), dump.channel_index("bl_z"), t["bl_z"]), (h("bl_y"), h("bl_y_idx"), t["laplace"])]
+    el = [(h("el_mv_z"), dump.channel_index("el_mv_z"), t["el_mv_z"]), (h("el_mv_y"), h("el_mv_y_idx"), t["laplace"]),
+          (h("el_z"), dump.channel_index("el_z"), t["el_z"])]
+    el += [(h(f"el_y{k}"), h(f"el_y{k}_idx"), t["laplace"]) for k in range(4)]
+    stream.encode_p(_encode(bl), output_path_bl)
+    t1 = time.time()
+    stream.encode_p(_encode(el), output_path_el)
+    t2 = time.time()
+    _verify(stream.decode_p(output_path_bl), bl, "base layer")
+    t3 = time.time()
+    _verify(stream.decode_p(output_path_el), el, "enhancement layer")
+    t4 = time.time()
+    r["bit_bl"] = stream.filesize(output_path_bl) * 8
+    r["bit_el"] = stream.filesize(output_path_el) * 8
+    # the forward pass codes both layers; its time is attributed to the EL encoder as the reference's timers would see it
+    r["encoding_time_BL"], r["encoding_time_EL"] = t1 - t0, t2 - t1
+    r["decoding_time_BL"], r["decoding_time_EL"] = t3 - t2, t4 - t3
+    return r
+
+
+def intra_encode_decode(model, x_bl, x_el, bin_path_bl, bin_path_el, pic_height_bl, pic_width_bl, pic_height_el,
+                        pic_width_el):
+    """IntraSS.encode_decode with bitstreams (IntraSS.py:245-302)."""
+    model.update()
+    t = model._tables
+    dump = SymbolDump(model.device)
+    r = model.forward(x_bl, x_el, _write=dump)
+    torch.cuda.synchronize(model.device)
+    h = dump.host
+    for tag, path, ph, pw in (("bl", bin_path_bl, pic_height_bl, pic_width_bl), ("el", bin_path_el, pic_height_el, pic_width_el)):
+        y_part = (h(f"{tag}_y"), h(f"{tag}_y_idx"), t["gaussian"])
+        z_part = (h(f"{tag}_z"), dump.channel_index(f"{tag}_z"), t[f"{tag}_z"])
+        stream.encode_i(ph, pw, _encode([y_part]), _encode([z_part]), path)
+        _, _, y_string, z_string = stream.decode_i(path)
+        _verify(y_string, [y_part], f"{tag} y")
+        _verify(z_string, [z_part], f"{tag} z")
+        r[f"bit_{tag}"] = stream.filesize(path) * 8
+    return r
