@@ -121,6 +121,22 @@ typedef struct {
   float slope1, slope2;
 } lssvc_ffn;
 
+/*
+ * Pointwise convolution with resident weights, optionally fused with the depthwise 3x3 that precedes it in DepthConv
+ * (lssvc_modules.py:15-40):  out = act(W . u + bias) * out_scale (+ res1) (+ res2),  u = in  or  dw3x3(in) + dw_bias.
+ * in.C = Cin (multiple of 16, <= 128), out.C = Cout (multiple of 16, <= 64), 2*Cin + 4*Cout <= 512.
+ * w: fp16 [Cin/16][2 (hi, lo)][Cout][16] = split of W * 2^shift, SWIZZLE_32B image (see lssvc_ffn); acc_scale = 2^-shift.
+ * dw_weight: fp32 [9][Cin] (tap-major, tap = 3*ky + kx), dw_bias: [Cin]; both NULL for a plain 1x1 conv.
+ */
+typedef struct {
+  lssvc_view in, out, res1, res2;
+  const void *w;
+  const float *bias;
+  const float *dw_weight, *dw_bias;
+  int32_t act;
+  float slope, out_scale, acc_scale;
+} lssvc_pw;
+
 /* ---- library ---------------------------------------------------------------------------- */
 int32_t lssvc_abi_version(void);
 /* 0 when device `dev` is sm_100-class and the driver entry points needed for TMA resolve. */
@@ -138,6 +154,8 @@ int32_t lssvc_conv_tc(const lssvc_conv *c, void *stream);
 int32_t lssvc_conv_h2(const lssvc_conv *c, void *stream);
 /* fused 1x1 -> LeakyReLU -> 1x1 -> LeakyReLU -> + identity block (see lssvc_ffn) */
 int32_t lssvc_conv_ffn(const lssvc_ffn *f, void *stream);
+/* resident-weight 1x1 conv, optional fused depthwise 3x3 front end (see lssvc_pw) */
+int32_t lssvc_conv_pw(const lssvc_pw *f, void *stream);
 /* fp32 CUDA-core implicit GEMM: any shape, also hosts the GDN epilogue and input transforms. */
 int32_t lssvc_conv_simt(const lssvc_conv *c, void *stream);
 /* depthwise 3x3, pad 1 (lssvc_modules.py:23-24): weight [9][C], bias [C] */

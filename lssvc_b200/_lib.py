@@ -58,6 +58,12 @@ class CFfn(Structure):
                 ("slope2", c_float)]
 
 
+class CPw(Structure):
+    _fields_ = [("inp", CView), ("out", CView), ("res1", CView), ("res2", CView), ("w", c_void_p), ("bias", c_void_p),
+                ("dw_weight", c_void_p), ("dw_bias", c_void_p), ("act", c_int32), ("slope", c_float), ("out_scale", c_float),
+                ("acc_scale", c_float)]
+
+
 _PV = POINTER(CView)
 _SIGNATURES = {
     # name: (restype, argtypes)
@@ -68,6 +74,7 @@ _SIGNATURES = {
     "lssvc_conv_tc": (c_int32, [POINTER(CConv), c_void_p]),
     "lssvc_conv_h2": (c_int32, [POINTER(CConv), c_void_p]),
     "lssvc_conv_ffn": (c_int32, [POINTER(CFfn), c_void_p]),
+    "lssvc_conv_pw": (c_int32, [POINTER(CPw), c_void_p]),
     "lssvc_conv_simt": (c_int32, [POINTER(CConv), c_void_p]),
     "lssvc_dwconv3x3": (c_int32, [_PV, c_void_p, c_void_p, _PV, c_void_p]),
     "lssvc_deconv3x3_s2": (c_int32, [_PV, c_void_p, c_void_p, c_int32, c_float, _PV, c_void_p]),

@@ -15,6 +15,7 @@ class Engine(nets.ParamBag):
         super().__init__(spec, seed=seed, gains=nets.model_gains(model_tag))
         self._packs = {}
         self.fuse_ffn = os.environ.get("LSSVC_FUSE_FFN", "1") != "0"
+        self.fuse_pw = os.environ.get("LSSVC_FUSE_PW", "1") != "0"
         self.shape_hr = (256, 256)
         self.scale_factor = 2.0
         self.pad_size = (0, 0, 0, 0)
@@ -72,7 +73,7 @@ class Engine(nets.ParamBag):
         return View.alloc_padded(H, W, C, self.device)
 
     def conv(self, name, srcs, stride=1, act=None, ps=False, transposed=False, pad=None, res1=None, res2=None,
-             out=None, act_copy=None, act_copy_out=None, out_scale=1.0, engine=None):
+             out=None, act_copy=None, act_copy_out=None, out_scale=1.0, engine=None, in_lrelu=None):
         """conv (+PixelShuffle) with fused epilogue.  Returns the output view, or (out, lrelu(out, act_copy))."""
         if isinstance(srcs, View):
             srcs = [srcs]
@@ -89,8 +90,9 @@ class Engine(nets.ParamBag):
             out2 = act_copy_out if act_copy_out is not None else self.new(Ho * f, Wo * f, C)
         ex = lambda v: None if v is None else v.exact()
         ops.TRACE_NAME = name
+        kw = {} if in_lrelu is None else {"in_transform": _lib.IN_LRELU, "in_slope": float(in_lrelu)}
         ops.conv(pc, srcs, out.exact(), act=act, res1=ex(res1), res2=ex(res2), out2=ex(out2),
-                 slope2=0.0 if act_copy is None else act_copy, out_scale=out_scale, engine=engine)
+                 slope2=0.0 if act_copy is None else act_copy, out_scale=out_scale, engine=engine, **kw)
         return (out, out2) if act_copy is not None else out
 
     def lrelu(self, x, slope, out=None):
@@ -133,6 +135,26 @@ class Engine(nets.ParamBag):
         w, b = self.cached(("dw", name), build)
         out = self.new(x.H, x.W, x.real)
         ops.dwconv3x3(x.exact(), w, b, out.exact())
+        return out
+
+    def pointwise(self, name, x, act=None, res1=None, res2=None, out=None, dw=None):
+        """1x1 conv `name` (+ bias, LeakyReLU, residuals), with the depthwise 3x3 `dw` applied to x first when given.
+        Runs on the resident-weight kernel (csrc/conv_pw.cu) when the shapes allow, else dwconv + the general conv."""
+        w = self.tensor(name + ".weight")
+        cout, cin = w.shape[0], w.shape[1]
+        ok = (self.fuse_pw and ops.default_engine() == "h2" and ops.PackedPw.supported(cin, cout, dw is not None) and x.real == cin
+              and ops.view_aligned(x) and all(r is None or (r.real == cout and ops.view_aligned(r)) for r in (res1, res2, out)))
+        if not ok:
+            if dw is not None:
+                x = self.dwconv(dw, x)
+            return self.conv(name, x, act=act, pad=0, res1=res1, res2=res2, out=out)
+        pp = self.cached(("pw", name, dw), lambda: ops.PackedPw(
+            w, self.tensor(name + ".bias"), self.device,
+            dw_w=None if dw is None else self.tensor(dw + ".weight"), dw_b=None if dw is None else self.tensor(dw + ".bias")))
+        out = out if out is not None else self.new(x.H, x.W, cout)
+        ex = lambda v: None if v is None else v.exact()
+        ops.TRACE_NAME = name
+        ops.pw(pp, x.exact(), out.exact(), act=act, res1=ex(res1), res2=ex(res2))
         return out
 
     def deconv_s2(self, name, x, act=None):
@@ -196,10 +218,15 @@ class Engine(nets.ParamBag):
                   act_copy=None, act_copy_out=None):
         """ResBlock (video_net_component.py:170-188, layers.py:229-255): x + last(conv2(lrelu(conv1(first(x))))).
         x_act: lrelu(x, slope) if the producer already wrote it (saves a pass)."""
-        inp = x
+        inp, in_lrelu = x, None
         if start_from_relu:
-            inp = x_act if x_act is not None else self.lrelu(x, slope)
-        t = self.conv(name + ".conv1", inp, act=slope)
+            if x_act is not None:
+                inp = x_act
+            elif ops.default_engine() == "h2":
+                in_lrelu = slope        # LeakyReLU of the block input applied in the conv's operand path
+            else:
+                inp = self.lrelu(x, slope)
+        t = self.conv(name + ".conv1", inp, act=slope, in_lrelu=in_lrelu)
         return self.conv(name + ".conv2", t, act=slope if end_with_relu else None, res1=x, res2=res2, out=out,
                          act_copy=act_copy, act_copy_out=act_copy_out)
 
@@ -207,11 +234,10 @@ class Engine(nets.ParamBag):
         """DepthConvBlock (lssvc_modules.py:15-72): DepthConv (1x1, lrelu .01, dw3x3, 1x1, + identity/adaptor)
         then ConvFFN (x + lrelu(1x1(lrelu(1x1 x, .1)), .1))."""
         dc, ffn = name + ".block.0", name + ".block.1"
-        t = self.conv(dc + ".conv1.0", x, act=0.01, pad=0)
-        t = self.dwconv(dc + ".depth_conv", t)
         has_adaptor = (dc + ".adaptor.weight") in self._spec
-        identity = self.conv(dc + ".adaptor", x, pad=0) if has_adaptor else x
-        o = self.conv(dc + ".conv2", t, pad=0, res1=identity)
+        t = self.pointwise(dc + ".conv1.0", x, act=0.01)
+        identity = self.pointwise(dc + ".adaptor", x) if has_adaptor else x
+        o = self.pointwise(dc + ".conv2", t, res1=identity, dw=dc + ".depth_conv")
         w1 = self.tensor(ffn + ".conv.0.weight")
         hidden, C = w1.shape[0], w1.shape[1]
         if (self.fuse_ffn and ops.default_engine() == "h2" and ops.PackedFfn.supported(C, hidden) and o.C == C

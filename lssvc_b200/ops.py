@@ -355,6 +355,74 @@ def ffn(pf, x, out, slope1=0.1, slope2=0.1, res2=None):
     return out
 
 
+class PackedPw:
+    """Weights of one 1x1 conv (optionally with the depthwise 3x3 in front of it) packed for lssvc_conv_pw: split fp16
+    hi/lo of W * 2^shift as [Cin/16][hi | lo][Cout][16] sub-tiles with the SWIZZLE_32B row pattern (see PackedFfn)."""
+
+    __slots__ = ("w", "bias", "scale", "cin", "cout", "dw_w", "dw_b")
+
+    @staticmethod
+    def supported(cin, cout, dw=False):
+        if not (cin % 16 == 0 and 16 <= cin <= 128 and cout % 16 == 0 and 16 <= cout <= 64 and 2 * cin + 4 * cout <= 512):
+            return False
+        # shared memory of conv_pw.cu with two input buffers (it takes three when they fit)
+        slab_w = 32 if cin % 32 == 0 else 16
+        rows = 18 * 10 if dw else 128
+        in_bytes = (cin // slab_w) * round_up(rows * slab_w * 4, 1024)
+        smem = round_up(round_up(4 * cin * cout, 1024) + (40 * cin if dw else 0), 1024) + 2 * in_bytes + 512 * cout + 1024
+        return smem <= 226 * 1024
+
+    def __init__(self, w, b, device, dw_w=None, dw_b=None):
+        w = w.detach().to(torch.float32).cpu().reshape(w.shape[0], w.shape[1])          # [cout, cin]
+        cout, cin = w.shape
+        assert PackedPw.supported(cin, cout, dw_w is not None), (cin, cout)
+        m = float(w.abs().max())
+        shift = 0 if m == 0.0 else 13 - int(math.floor(math.log2(m)))
+        ws = w * (2.0 ** shift)
+        hi = ws.to(torch.float16)
+        lo = (ws - hi.to(torch.float32)).to(torch.float16)
+        t = torch.stack([hi, lo], 0).reshape(2, cout, cin // 16, 16).permute(2, 0, 1, 3).reshape(cin // 16, 2 * cout, 2, 8)
+        swap = ((torch.arange(2 * cout) >> 2) & 1).bool()
+        sw = t.clone()
+        sw[:, swap, 0, :] = t[:, swap, 1, :]
+        sw[:, swap, 1, :] = t[:, swap, 0, :]
+        self.w = sw.reshape(cin // 16, 2 * cout, 16).contiguous().to(device)
+        self.bias = (torch.zeros(cout) if b is None else b.detach().to(torch.float32).cpu()).contiguous().to(device)
+        self.scale = 2.0 ** -shift
+        self.cin, self.cout = cin, cout
+        if dw_w is not None:
+            dw = dw_w.detach().to(torch.float32).cpu()
+            assert dw.shape[0] == cin and dw.numel() == 9 * cin, dw.shape
+            self.dw_w = dw.reshape(cin, 9).t().contiguous().to(device)                 # [9][cin], tap = 3*ky + kx
+            self.dw_b = dw_b.detach().to(torch.float32).contiguous().to(device)
+        else:
+            self.dw_w = self.dw_b = None
+
+
+def view_aligned(v):
+    return v.pitch % 4 == 0 and v.coff % 4 == 0
+
+
+def pw(pp, x, out, act=None, res1=None, res2=None, out_scale=1.0):
+    """out = act(W . u + b) * out_scale (+ res1) (+ res2), u = x or dw3x3(x) + dw_b; one resident-weight kernel."""
+    d = _lib.CPw()
+    assert x.C == pp.cin and out.C == pp.cout, (x.C, out.C, pp.cin, pp.cout)
+    d.inp, d.out, d.res1, d.res2 = x.c(), out.c(), _cv(res1), _cv(res2)
+    d.w, d.bias = pp.w.data_ptr(), pp.bias.data_ptr()
+    d.dw_weight = None if pp.dw_w is None else pp.dw_w.data_ptr()
+    d.dw_bias = None if pp.dw_b is None else pp.dw_b.data_ptr()
+    d.act = _lib.ACT_NONE if act is None else _lib.ACT_LRELU
+    d.slope = 0.0 if act is None else float(act)
+    d.out_scale, d.acc_scale = float(out_scale), pp.scale
+    if TRACE is not None:
+        TRACE.append({"name": TRACE_NAME, "engine": "pw", "k": 1, "stride": 1, "cin": pp.cin, "src_c": [pp.cin],
+                      "cout": pp.cout, "Ho": out.H, "Wo": out.W, "ps": False, "dw": pp.dw_w is not None,
+                      "flops": 2.0 * out.H * out.W * pp.cin * (pp.cout + (9 if pp.dw_w is not None else 0))})
+    lib = _lib.load()
+    _lib.check(lib.lssvc_conv_pw(byref(d), _stream()), "conv_pw")
+    return out
+
+
 def dwconv3x3(x, weight9c, bias, out):
     lib = _lib.load()
     _lib.check(lib.lssvc_dwconv3x3(byref(x.c()), _ptr(weight9c), _ptr(bias), byref(out.c()), _stream()), "dwconv3x3")

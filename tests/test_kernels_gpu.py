@@ -171,6 +171,40 @@ def test_conv_ffn_fused(C, hidden, H, W, with_res, cuda_device):
     assert err < 5e-6, err
 
 
+@pytest.mark.parametrize("cin,cout,H,W,dw,act,nres", [(64, 64, 40, 56, False, 0.01, 0), (64, 64, 37, 50, True, None, 1),
+                                                     (48, 32, 64, 96, True, None, 2), (128, 64, 24, 40, False, 0.1, 1), (96, 48, 24, 40, True, 0.1, 1),
+                                                     (32, 48, 33, 20, False, None, 1), (64, 64, 160, 288, True, None, 1)])
+def test_conv_pw(cin, cout, H, W, dw, act, nres, cuda_device):
+    """Resident-weight 1x1 conv with optional fused depthwise 3x3 (csrc/conv_pw.cu) against the fp64 torch composition of
+    DepthConv (lssvc_modules.py:15-40)."""
+    ops = _ops()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn(1, cin, H, W, generator=g).to(dev)
+    w = (torch.randn(cout, cin, 1, 1, generator=g) / math.sqrt(cin)).to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    dw_w = (torch.randn(cin, 1, 3, 3, generator=g) / 3).to(dev)
+    dw_b = torch.randn(cin, generator=g).to(dev)
+    res = [torch.randn(1, cout, H, W, generator=g).to(dev) for _ in range(nres)]
+    pp = ops.PackedPw(w, b, dev, dw_w=dw_w if dw else None, dw_b=dw_b if dw else None)
+    out = ops.View.alloc(H, W, cout, dev, zero=True)
+    rv = [make_view(r, ops) for r in res] + [None, None]
+    ops.pw(pp, make_view(x, ops), out, act=act, res1=rv[0], res2=rv[1], out_scale=0.5)
+    torch.cuda.synchronize()
+    u = x.double()
+    if dw:
+        u = F.conv2d(u, dw_w.double(), dw_b.double(), padding=1, groups=cin)
+    ref = F.conv2d(u, w.double(), b.double())
+    if act is not None:
+        ref = F.leaky_relu(ref, act)
+    ref = ref * 0.5
+    for r in res:
+        ref = ref + r.double()
+    err = rel_err(out.to_nchw(), ref.float())
+    print(f"conv_pw {cin}->{cout} {H}x{W} dw={dw}: rel err {err:.3e}")
+    assert err < 5e-6, err
+
+
 def test_conv_tc3_large_persistent(cuda_device):
     err = _run_conv_case(("big", [64], [64], 64, 3, 1, 256, 320, False), "tc3", cuda_device, True)
     assert err < 2e-5, err

@@ -31,7 +31,7 @@ def main():
     coder = bench.Coder(dev, shape_hr)
     records = []
     state = {"on": False}
-    names = ["conv", "ffn", "dwconv3x3", "deconv3x3_s2", "lrelu_copy", "softmax2_blend", "flow_warp", "bilinear_resize", "avgpool2",
+    names = ["conv", "ffn", "pw", "dwconv3x3", "deconv3x3_s2", "lrelu_copy", "softmax2_blend", "flow_warp", "bilinear_resize", "avgpool2",
              "maxpool2", "spynet_prep", "offset_diversity", "laplace_quant", "four_part_step", "gaussian_quant",
              "bitparm_quant", "eb_quant", "sse"]
 
