@@ -152,6 +152,9 @@ int32_t lssvc_conv_tc(const lssvc_conv *c, void *stream);
  * (fp32 halo tile by TMA -> hi/lo fp16 -> tensor memory), weights are pre-split (weight_h2).  Any kernel size,
  * stride 1 or 2, up to 3 concatenated sources, input transform (GDN's x^2), GDN / IGDN epilogue. */
 int32_t lssvc_conv_h2(const lssvc_conv *c, void *stream);
+/* same arithmetic and arguments as lssvc_conv_h2; the activation operand is read by the tensor core straight from the
+ * converted halo tile in shared memory (tap = shifted descriptor), 16x8 / 16x16 pixel tiles (csrc/conv_hs.cu) */
+int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream);
 /* fused 1x1 -> LeakyReLU -> 1x1 -> LeakyReLU -> + identity block (see lssvc_ffn) */
 int32_t lssvc_conv_ffn(const lssvc_ffn *f, void *stream);
 /* resident-weight 1x1 conv, optional fused depthwise 3x3 front end (see lssvc_pw) */

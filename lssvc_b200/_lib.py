@@ -73,6 +73,7 @@ _SIGNATURES = {
     "lssvc_launch_count": (c_int64, []),
     "lssvc_conv_tc": (c_int32, [POINTER(CConv), c_void_p]),
     "lssvc_conv_h2": (c_int32, [POINTER(CConv), c_void_p]),
+    "lssvc_conv_hs": (c_int32, [POINTER(CConv), c_void_p]),
     "lssvc_conv_ffn": (c_int32, [POINTER(CFfn), c_void_p]),
     "lssvc_conv_pw": (c_int32, [POINTER(CPw), c_void_p]),
     "lssvc_conv_simt": (c_int32, [POINTER(CConv), c_void_p]),

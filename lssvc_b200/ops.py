@@ -199,6 +199,11 @@ ENGINES = {
 }
 _ENGINE = os.environ.get("LSSVC_CONV_ENGINE", "h2")
 assert _ENGINE in ENGINES, _ENGINE
+# Kernel behind the "h2" (split-fp16) engine: "hs" = activation operand read from shared memory by shifted descriptors
+# (csrc/conv_hs.cu, default), "h2t" = activation operand staged in tensor memory per tap (csrc/conv_h2.cu).
+# conv(..., engine="hs" | "h2t") forces one of them for A/B tests.
+_H2_IMPL = os.environ.get("LSSVC_H2_IMPL", "hs")
+assert _H2_IMPL in ("hs", "h2t"), _H2_IMPL
 
 
 def default_engine():
@@ -258,6 +263,9 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
     d.slope2 = float(slope2)
     lib = _lib.load()
     engine = engine or _ENGINE
+    impl = _H2_IMPL
+    if engine in ("hs", "h2t"):
+        engine, impl = "h2", engine
     if engine == "h2":
         ok = (all(s.C % 4 == 0 and s.pitch % 4 == 0 and (s.coff % 4 == 0) for s in srcs) and pc.kh * pc.kw <= 49
               and pc.stride in (1, 2) and srcs[0].H % pc.stride == 0 and srcs[0].W % pc.stride == 0)
@@ -271,7 +279,7 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
             engine = "simt"
     if TRACE is not None:
         Ho, Wo = (out.H // 2, out.W // 2) if pc.pixel_shuffle else (out.H, out.W)
-        TRACE.append({"name": TRACE_NAME, "engine": engine, "k": pc.kh, "stride": pc.stride, "cin": pc.cin_total,
+        TRACE.append({"name": TRACE_NAME, "engine": engine if engine != "h2" else impl, "k": pc.kh, "stride": pc.stride, "cin": pc.cin_total,
                       "src_c": list(pc.src_c), "cout": pc.cout, "Ho": Ho, "Wo": Wo, "ps": bool(pc.pixel_shuffle),
                       "flops": 2.0 * Ho * Wo * pc.kh * pc.kw * sum(s.real for s in srcs) * pc.cout})
     if engine == "simt":
@@ -280,7 +288,10 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
         wh, cin16, acc_scale = pc.weight_h2()
         d.precision = _lib.PREC_H2
         d.weight_h2, d.cin_pad16, d.acc_scale = wh.data_ptr(), cin16, acc_scale
-        _lib.check(lib.lssvc_conv_h2(byref(d), _stream()), "conv_h2")
+        if impl == "hs":
+            _lib.check(lib.lssvc_conv_hs(byref(d), _stream()), "conv_hs")
+        else:
+            _lib.check(lib.lssvc_conv_h2(byref(d), _stream()), "conv_h2")
     else:
         if engine == "tc3":
             d.precision = _lib.PREC_3XTF32

@@ -130,6 +130,30 @@ def test_conv_h2(case, extras, cuda_device):
     assert err < 5e-6, err
 
 
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("extras", [False, True], ids=["plain", "epilogue"])
+def test_conv_hs(case, extras, cuda_device):
+    """Split-fp16 conv with the activation operand read from shared memory through shifted descriptors (csrc/conv_hs.cu)."""
+    err = _run_conv_case(case, "hs", cuda_device, extras)
+    print(f"tcgen05 split-fp16 (smem A) conv {case[0]} rel err {err:.3e}")
+    assert err < 5e-6, err
+
+
+@pytest.mark.parametrize("mt", ["1", "2"])
+def test_conv_hs_large_persistent(cuda_device, mt, monkeypatch):
+    """More tiles than SMs: persistent loop, accumulator slots, barrier phase wrap; both sub-tile modes where allowed."""
+    monkeypatch.setenv("LSSVC_HS_MT", mt)
+    for case, extras in ((("big", [64], [64], 64, 3, 1, 256, 320, False), True),
+                         (("big48", [48, 48], [48, 48], 48, 3, 1, 200, 312, False), False),
+                         (("big256", [128], [128], 256, 3, 1, 96, 160, True), False),
+                         (("big_s2", [64, 8], [64, 8], 96, 3, 2, 192, 320, False), True),
+                         (("big_7x7", [32], [32], 64, 7, 1, 128, 256, False), False),
+                         (("big_1x1", [64], [64], 256, 1, 1, 160, 264, False), True)):
+        err = _run_conv_case(case, "hs", cuda_device, extras)
+        print(f"conv_hs {case[0]}: rel err {err:.3e}")
+        assert err < 5e-6, (case[0], err)
+
+
 def test_conv_h2_large_persistent(cuda_device):
     """More tiles than SMs: persistent loop, halo / slot ring wrap, TMEM double buffering, single-buffer (n_tile 128) mode."""
     err = _run_conv_case(("big", [64], [64], 64, 3, 1, 256, 320, False), "h2", cuda_device, True)
