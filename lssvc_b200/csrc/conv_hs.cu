@@ -60,7 +60,7 @@ struct alignas(64) HsParams {
   int halo_tx;                 // bytes of one halo box
   int halo_rows;               // pixels of one halo box
   unsigned char tap_w[MAX_TAPS];     // weight tap index r * kw + s
-  unsigned short tap_off[MAX_TAPS];  // pixel-row offset of the tap's window origin inside the halo
+  unsigned short tap16[MAX_TAPS + 7];  // (byte offset of the tap's window origin inside the halo) >> 4, zero padded
   int mt;                      // sub-tiles per tile (1 or 2)
   int n_acc;                   // accumulator slots in TMEM (2 or 4), each 2 * n_tile columns
   int Ho, Wo;
@@ -87,6 +87,8 @@ struct alignas(64) HsParams {
   float *out2;
   int out2_pitch;
   float slope2;
+  long long *prof;  // DBG variant: [5 roles][8] cycle counters of CTA 0
+  int dbg;  // LSSVC_HS_DBG: bottleneck-isolation switches (results are wrong when non-zero); see lssvc_conv_hs
 };
 
 __device__ __forceinline__ long long out_offset(const HsParams &p, int oy, int ox, int ch, int P) {
@@ -125,11 +127,26 @@ __device__ __forceinline__ void transform_row(float4 (&v)[NV], int in_transform,
   }
 }
 
-template <int KC>
+// DBG = true: the instrumented variant (LSSVC_HS_DBG switches + per-role wait-time counters), never on the product path
+template <int KC, int MT, bool DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_constant__ HsParams p) {
+  const int dbgf = DBG ? p.dbg : 0;
+  long long prof[6] = {0, 0, 0, 0, 0, 0};
+  const long long t_begin = DBG ? clock64() : 0;
+#define HS_WAIT(slot, bar, parity)                    \
+  do {                                                \
+    if (DBG) {                                        \
+      const long long t0__ = clock64();               \
+      ptx::mbar_wait(bar, parity);                    \
+      prof[slot] += clock64() - t0__;                 \
+    } else {                                          \
+      ptx::mbar_wait(bar, parity);                    \
+    }                                                 \
+  } while (0)
   constexpr int ROWB = KC * 4;         // bytes of one halo pixel (fp32, or fp16 hi | fp16 lo after conversion)
   constexpr int NV = KC / 4;           // 16-byte chunks per halo pixel
   constexpr int KS = KC / 16;          // K = 16 MMA slices per tap
+  constexpr int TAPS_PER_STAGE = STAGE_K / KC;
   constexpr uint32_t LO_OFF = KC * 2;  // byte offset of the lo half inside a pixel row
   constexpr uint32_t A_LAYOUT = KC == 32 ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
   constexpr uint32_t B_ROWB = KC * 2;  // bytes of one weight row (fp16)
@@ -189,8 +206,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
 
   const int tiles_per_n = p.tiles_x * p.tiles_y;
   const int total_tiles = tiles_per_n * p.n_tiles;
-  const int mt = p.mt;
-  const int tile_w = SUB_W * mt;
+  constexpr int mt = MT;
+  constexpr int tile_w = SUB_W * MT;
 
   if (warp == 0) {
     // ------------------------------- halo TMA producer -----------------------------------
@@ -206,10 +223,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
           for (int c = 0; c < p.chunks[j]; ++c) {
             for (int g = 0; g < p.n_groups; ++g) {
               const uint32_t full = bar_halo_full + 8 * hb;
-              ptx::mbar_wait(bar_halo_empty + 8 * hb, hph ^ 1u);
-              ptx::mbar_expect_tx(full, static_cast<uint32_t>(p.halo_tx));
-              ptx::tma_load_5d(smem_base + static_cast<uint32_t>(hb * p.halo_bytes), &p.a_map[j], full, c * KC, p.g_px[g],
-                               ox0, p.g_py[g], oy0);
+              HS_WAIT(0, bar_halo_empty + 8 * hb, hph ^ 1u);
+              if (dbgf & 16) {
+                ptx::mbar_arrive(full);
+              } else {
+                ptx::mbar_expect_tx(full, static_cast<uint32_t>(p.halo_tx));
+                ptx::tma_load_5d(smem_base + static_cast<uint32_t>(hb * p.halo_bytes), &p.a_map[j], full, c * KC, p.g_px[g],
+                                 ox0, p.g_py[g], oy0);
+              }
               if (++hb == p.halo_bufs) {
                 hb = 0;
                 hph ^= 1u;
@@ -238,11 +259,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
               for (int t = p.g_tap0[g]; t < t1; t += step) {
                 const int items = t1 - t < step ? t1 - t : step;
                 const uint32_t full = bar_full + 8 * s;
-                ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                ptx::mbar_expect_tx(full, tile_bytes * static_cast<uint32_t>(items));
-                for (int i = 0; i < items; ++i)
-                  ptx::tma_load_4d(b_base + static_cast<uint32_t>(s * p.b_bytes) + static_cast<uint32_t>(i) * tile_bytes,
-                                   &p.b_map, full, k0, n0, 0, static_cast<int>(p.tap_w[t + i]));
+                HS_WAIT(0, bar_empty + 8 * s, ph ^ 1u);
+                if (dbgf & 32) {
+                  ptx::mbar_arrive(full);
+                } else {
+                  ptx::mbar_expect_tx(full, tile_bytes * static_cast<uint32_t>(items));
+                  for (int i = 0; i < items; ++i)
+                    ptx::tma_load_4d(b_base + static_cast<uint32_t>(s * p.b_bytes) + static_cast<uint32_t>(i) * tile_bytes,
+                                     &p.b_map, full, k0, n0, 0, static_cast<int>(p.tap_w[t + i]));
+                }
                 if (++s == p.slots) {
                   s = 0;
                   ph ^= 1u;
@@ -255,84 +280,98 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ------------------------------------------
-    // The whole warp walks the loop (all lanes poll the barriers); one elected lane issues.
-    int s = 0;
-    uint32_t ph = 0;
-    int hb = 0;
-    uint32_t hph = 0;
-    int slot0 = 0;  // first accumulator slot of the current tile
-    uint32_t acc_ph = 0;
-    const uint32_t idesc_2n = ptx::make_idesc_f16_m128(static_cast<uint32_t>(2 * p.n_tile));
-    const uint32_t idesc_n = ptx::make_idesc_f16_m128(static_cast<uint32_t>(p.n_tile));
-    const int slots = p.slots, halo_bufs = p.halo_bufs, n_acc = p.n_acc;
-    const uint32_t n_tile = static_cast<uint32_t>(p.n_tile);
-    const uint32_t b_bytes = static_cast<uint32_t>(p.b_bytes);
-    const uint32_t halo_bytes = static_cast<uint32_t>(p.halo_bytes);
-    const uint32_t tile_bytes = 2u * n_tile * B_ROWB;
-    const uint32_t a_sbo = static_cast<uint32_t>(p.halo_w) * ROWB;
-    const int n_src = p.n_src, n_groups = p.n_groups;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int j = 0; j < mt; ++j) ptx::mbar_wait(bar_tempty + 8 * (slot0 + j), acc_ph ^ 1u);
-      ptx::tc_fence_after();
-      const uint32_t d_tile = tmem_base + static_cast<uint32_t>(slot0) * 2u * n_tile;
-      uint32_t acc = 0;  // 0 only for the first K slice of the tile
-      for (int js = 0; js < n_src; ++js) {
-        for (int c = 0; c < p.chunks[js]; ++c) {
-          for (int g = 0; g < n_groups; ++g) {
-            ptx::mbar_wait(bar_halo_conv + 8 * hb, hph);
-            const uint32_t halo = smem_base + static_cast<uint32_t>(hb) * halo_bytes;
-            const int t1 = p.g_tap0[g + 1];
-            const int step = p.g_step[g];
-            for (int t = p.g_tap0[g]; t < t1; t += step) {
-              const int items = t1 - t < step ? t1 - t : step;
-              ptx::mbar_wait(bar_full + 8 * s, ph);
-              ptx::tc_fence_after();
-              if (ptx::elect_one()) {
-                for (int i = 0; i < items; ++i) {
-                  const uint32_t a_tap = halo + static_cast<uint32_t>(p.tap_off[t + i]) * ROWB;
-                  const uint32_t b_addr = b_base + static_cast<uint32_t>(s) * b_bytes + static_cast<uint32_t>(i) * tile_bytes;
+    // One elected thread runs the whole loop.  It is a serial instruction stream (every dependent instruction costs
+    // ~5 cycles), so the per-MMA work is kept to a couple of 32-bit adds: descriptors are (lo, hi) word pairs whose
+    // hi word is constant and whose lo word is (address >> 4) + constant; tap offsets come pre-shifted from the
+    // parameter block and are fetched before the stage's barrier wait.
+    if (ptx::elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      int hb = 0;
+      uint32_t hph = 0;
+      int slot0 = 0;  // first accumulator slot of the current tile
+      uint32_t acc_ph = 0;
+      const uint32_t n_tile = static_cast<uint32_t>(p.n_tile);
+      const uint32_t idesc_2n = ptx::make_idesc_f16_m128(2u * n_tile);
+      const uint32_t idesc_n = ptx::make_idesc_f16_m128(n_tile);
+      const int slots = p.slots, halo_bufs = p.halo_bufs, n_acc = p.n_acc;
+      const uint32_t b16_stage = static_cast<uint32_t>(p.b_bytes) >> 4;
+      const uint32_t halo16 = static_cast<uint32_t>(p.halo_bytes) >> 4;
+      const uint32_t tile16 = (2u * n_tile * B_ROWB) >> 4;
+      constexpr uint32_t DESC_LO = 1u << 16;  // LBO field = 1 (unused for swizzled K-major)
+      const uint32_t a_hi_word = ((static_cast<uint32_t>(p.halo_w) * ROWB) >> 4) | (1u << 14) | (A_LAYOUT << 29);
+      constexpr uint32_t b_hi_word = (B_SBO >> 4) | (1u << 14) | (B_LAYOUT << 29);
+      const uint32_t a16_base = (smem_base >> 4) | DESC_LO, b16_base = (b_base >> 4) | DESC_LO;
+      constexpr uint32_t SUB16 = (SUB_W * ROWB) >> 4, LO16 = LO_OFF >> 4;
+      const int n_src = p.n_src, n_groups = p.n_groups;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 #pragma unroll
-                  for (int ks = 0; ks < KS; ++ks) {
-                    const uint64_t b_desc = ptx::make_kmajor_desc(b_addr + ks * 32, B_SBO, B_LAYOUT);
-                    for (int j = 0; j < mt; ++j) {
-                      const uint32_t a_addr = a_tap + static_cast<uint32_t>(j * SUB_W) * ROWB + ks * 32;
-                      const uint32_t d1 = d_tile + static_cast<uint32_t>(j) * 2u * n_tile;
-                      // [D1 | D2] (+)= A_hi * [W_hi | W_lo]   then   D2 += A_lo * W_hi
-                      ptx::mma_f16_ss(d1, ptx::make_kmajor_desc(a_addr, a_sbo, A_LAYOUT), b_desc, idesc_2n, acc);
-                      ptx::mma_f16_ss(d1 + n_tile, ptx::make_kmajor_desc(a_addr + LO_OFF, a_sbo, A_LAYOUT), b_desc, idesc_n, 1u);
+        for (int j = 0; j < MT; ++j) HS_WAIT(0, bar_tempty + 8 * (slot0 + j), acc_ph ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tile = tmem_base + static_cast<uint32_t>(slot0) * 2u * n_tile;
+        uint32_t acc = 0;  // 0 only for the first K slice of the tile
+        for (int js = 0; js < n_src; ++js) {
+          for (int c = 0; c < p.chunks[js]; ++c) {
+            for (int g = 0; g < n_groups; ++g) {
+              const int t1 = p.g_tap0[g + 1];
+              const int step = p.g_step[g];
+              const int t0 = p.g_tap0[g];
+              HS_WAIT(1, bar_halo_conv + 8 * hb, hph);
+              const uint32_t a16_halo = a16_base + static_cast<uint32_t>(hb) * halo16;
+              for (int t = t0; t < t1; t += step) {
+                const int items = t1 - t < step ? t1 - t : step;
+                uint32_t tap16[TAPS_PER_STAGE];
+#pragma unroll
+                for (int i = 0; i < TAPS_PER_STAGE; ++i) tap16[i] = p.tap16[t + i];  // the table is padded: no bound check
+                HS_WAIT(2, bar_full + 8 * s, ph);
+                ptx::tc_fence_after();
+                const long long ti0 = DBG ? clock64() : 0;
+                const uint32_t b16_s = b16_base + static_cast<uint32_t>(s) * b16_stage;
+#pragma unroll
+                for (int i = 0; i < TAPS_PER_STAGE; ++i) {
+                  if (i < items) {
+                    const uint32_t a16_tap = a16_halo + tap16[i];
+                    const uint32_t b16_tap = b16_s + static_cast<uint32_t>(i) * tile16;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                      for (int j = 0; j < MT; ++j) {
+                        const uint32_t a16 = a16_tap + j * SUB16 + ks * 2;
+                        const uint32_t d1 = d_tile + static_cast<uint32_t>(j) * 2u * n_tile;
+                        // [D1 | D2] (+)= A_hi * [W_hi | W_lo]   then   D2 += A_lo * W_hi
+                        if (!DBG || !(dbgf & 1)) ptx::mma_f16_ss2(d1, a16, a_hi_word, b16_tap + ks * 2, b_hi_word, idesc_2n, acc);
+                        if (!DBG || !(dbgf & 2)) ptx::mma_f16_ss2(d1 + n_tile, a16 + LO16, a_hi_word, b16_tap + ks * 2, b_hi_word, idesc_n, 1u);
+                      }
+                      acc = 1u;
                     }
-                    acc = 1u;
                   }
                 }
                 ptx::mma_commit(bar_empty + 8 * s);
+                if (DBG) prof[3] += clock64() - ti0;
+                if (++s == slots) {
+                  s = 0;
+                  ph ^= 1u;
+                }
               }
-              __syncwarp();
-              acc = 1u;
-              if (++s == slots) {
-                s = 0;
-                ph ^= 1u;
+              // the halo tile is free once every MMA that reads it has completed
+              ptx::mma_commit(bar_halo_empty + 8 * hb);
+              if (++hb == halo_bufs) {
+                hb = 0;
+                hph ^= 1u;
               }
-            }
-            // the halo tile is free once every MMA that reads it has completed
-            if (ptx::elect_one()) ptx::mma_commit(bar_halo_empty + 8 * hb);
-            __syncwarp();
-            if (++hb == halo_bufs) {
-              hb = 0;
-              hph ^= 1u;
             }
           }
         }
-      }
-      if (ptx::elect_one()) {
-        for (int j = 0; j < mt; ++j) ptx::mma_commit(bar_tfull + 8 * (slot0 + j));
-      }
-      __syncwarp();
-      slot0 += mt;
-      if (slot0 == n_acc) {
-        slot0 = 0;
-        acc_ph ^= 1u;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) ptx::mma_commit(bar_tfull + 8 * (slot0 + j));
+        slot0 += MT;
+        if (slot0 == n_acc) {
+          slot0 = 0;
+          acc_ph ^= 1u;
+        }
       }
     }
+    __syncwarp();
   } else if (warp >= 4 && warp < 12) {
     // ------------------------------- converters: fp32 halo -> fp16 hi | lo, in place -------
     // One thread per halo pixel: the 4*KC-byte fp32 row becomes [hi fp16 x KC | lo fp16 x KC] with the same
@@ -348,9 +387,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
       for (int j = 0; j < p.n_src; ++j) {
         for (int c = 0; c < p.chunks[j]; ++c) {
           for (int g = 0; g < p.n_groups; ++g) {
-            ptx::mbar_wait(bar_halo_full + 8 * hb, hph);
+            HS_WAIT(0, bar_halo_full + 8 * hb, hph);
+            const long long tc0 = DBG ? clock64() : 0;
             const uint32_t halo = smem_base + static_cast<uint32_t>(hb) * halo_bytes;
-            for (int r = ct; r < halo_rows; r += 256) {
+            for (int r = ct; r < halo_rows && !(dbgf & 4); r += 256) {
               const uint32_t x = halo + static_cast<uint32_t>(r) * ROWB;
               const uint32_t a0 = x | ((x >> 3) & SWZ);
               float4 v[NV];
@@ -372,6 +412,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
             ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar_halo_conv + 8 * hb);
+            if (DBG) prof[1] += clock64() - tc0;
             if (++hb == halo_bufs) {
               hb = 0;
               hph ^= 1u;
@@ -421,13 +462,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
         const long long pix = static_cast<long long>(oy) * Wo + ox;
         if (use_tma) {
           // the staging tile is free once the TMA stores issued from it (this set's previous unit) have read it
+          const long long ts0 = DBG ? clock64() : 0;
           if (store_thread) ptx::bulk_wait_read_all();
           ptx::named_bar_sync(2 + eset, 128);
+          if (DBG) prof[2] += clock64() - ts0;
         }
-        ptx::mbar_wait(bar_tfull + 8 * slot, acc_ph);
+        HS_WAIT(0, bar_tfull + 8 * slot, acc_ph);
+        const long long te0 = DBG ? clock64() : 0;
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slot * 2 * n_tile);
-        for (int n = 0; n < n_tile; n += 16) {
+        for (int n = 0; n < n_tile && !(dbgf & 8); n += 16) {
           const int cg = n0 + n;
           uint32_t r1[16], r2[16];
           ptx::tmem_ld16(t_row + static_cast<uint32_t>(n), r1);
@@ -536,6 +580,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * slot);
+        if (DBG) prof[1] += clock64() - te0;
         if (use_tma) {
           ptx::fence_proxy_async_smem();  // staging writes (generic proxy) -> visible to the TMA store (async proxy)
           ptx::named_bar_sync(4 + eset, 128);
@@ -562,6 +607,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
     if (use_tma && store_thread) ptx::bulk_wait_all();
   }
 
+  if (DBG && p.prof && blockIdx.x == 0 && lane == 0) {
+    // rows: 0 halo producer, 1 MMA issuer, 2 weight producer, 3 converter warp 4, 4 epilogue warp 12, 5 epilogue warp 16
+    const int row = warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 2 : warp == 4 ? 3 : warp == 12 ? 4 : warp == 16 ? 5 : -1;
+    if (row >= 0) {
+      for (int i = 0; i < 6; ++i) p.prof[row * 8 + i] = prof[i];
+      p.prof[row * 8 + 7] = clock64() - t_begin;
+    }
+  }
+#undef HS_WAIT
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -657,7 +711,8 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
   // sub-tiles per tile: 2 (weights shared by 256 pixels) when that still leaves every SM a tile
   const char *mt_str = getenv("LSSVC_HS_MT");  // A/B switch, read per call so tests can flip it
   const int mt_env = mt_str ? atoi(mt_str) : 0;
-  int mt = (lssvc::ceil_div(Wo, 2 * SUB_W) * lssvc::ceil_div(Ho, TILE_H) * p.n_tiles >= g_num_sms) ? 2 : 1;
+  // (wide channel tiles keep MT = 1: two 2 x 128-column accumulators per sub-tile would leave no double buffering)
+  int mt = (n_tile <= 64 && lssvc::ceil_div(Wo, 2 * SUB_W) * lssvc::ceil_div(Ho, TILE_H) * p.n_tiles >= g_num_sms) ? 2 : 1;
   if (mt_env == 1 || mt_env == 2) mt = mt_env;
   p.mt = mt;
   p.n_acc = (mt == 2 && 8 * n_tile <= TMEM_COLS) ? 4 : 2;
@@ -689,7 +744,7 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
           const int dx = s - c->pad, qx = floor_div_h(dx, st);
           if (dx - qx * st != px) continue;
           p.tap_w[n_taps] = static_cast<unsigned char>(r * c->kw + s);
-          p.tap_off[n_taps] = static_cast<unsigned short>((qy - q0y) * halo_w + (qx - q0x));
+          p.tap16[n_taps] = static_cast<unsigned short>((((qy - q0y) * halo_w + (qx - q0x)) * kc * 4) >> 4);
           ++n_taps;
         }
       }
@@ -854,19 +909,48 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
     }
   }
 
+  // Instrumented variant (tools/conv_bench.py): LSSVC_HS_DBG = bit mask, 1 no A_hi MMAs, 2 no A_lo MMAs, 4 no halo
+  // conversion, 8 no epilogue, 16 no halo TMA, 32 no weight TMA (output is garbage when non-zero), 64 = just the
+  // per-role wait counters of CTA 0, printed to stderr after a device sync.  Never set outside profiling.
+  const char *dbg_str = getenv("LSSVC_HS_DBG");
+  const bool dbg_on = dbg_str != nullptr && atoi(dbg_str) != 0;
+  long long *prof_dev = nullptr;
+  if (dbg_on) {
+    p.dbg = atoi(dbg_str);
+    if (p.dbg & 64) {
+      LSSVC_CUDA(cudaMalloc(&prof_dev, 48 * sizeof(long long)));
+      LSSVC_CUDA(cudaMemset(prof_dev, 0, 48 * sizeof(long long)));
+      p.prof = prof_dev;
+    }
+  }
   const int total_tiles = p.tiles_x * p.tiles_y * p.n_tiles;
   const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
   const size_t smem = static_cast<size_t>(p.stage_off) + (use_tma ? 2 * static_cast<size_t>(per_set) : 0) + 1024;
   const int ki = kc == 32 ? 0 : 1;
   cudaStream_t s = lssvc::as_stream(stream);
-  if (!g_attr_set[ki]) {
-    const void *fn = kc == 32 ? reinterpret_cast<const void *>(conv_hs_kernel<32>)
-                              : reinterpret_cast<const void *>(conv_hs_kernel<16>);
-    LSSVC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    g_attr_set[ki] = true;
+  typedef void (*KernelFn)(const HsParams);
+  static const KernelFn fns[8] = {conv_hs_kernel<32, 1, false>, conv_hs_kernel<32, 2, false>, conv_hs_kernel<16, 1, false>,
+                                  conv_hs_kernel<16, 2, false>, conv_hs_kernel<32, 1, true>,  conv_hs_kernel<32, 2, true>,
+                                  conv_hs_kernel<16, 1, true>,  conv_hs_kernel<16, 2, true>};
+  if (!g_attr_set[0]) {
+    for (KernelFn fn : fns)
+      LSSVC_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    g_attr_set[0] = true;
   }
-  if (kc == 32) conv_hs_kernel<32><<<grid, NUM_THREADS, smem, s>>>(p);
-  else conv_hs_kernel<16><<<grid, NUM_THREADS, smem, s>>>(p);
+  fns[(dbg_on ? 4 : 0) + ki * 2 + (mt - 1)]<<<grid, NUM_THREADS, smem, s>>>(p);
   LSSVC_LAUNCHED();
+  if (prof_dev) {
+    long long h[48];
+    LSSVC_CUDA(cudaStreamSynchronize(s));
+    LSSVC_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(prof_dev);
+    static const char *names[6] = {"halo_tma  [wait empty]", "mma       [wait tempty, wait halo_conv, wait w_full, issue]",
+                                   "weight_tma[wait empty]", "convert   [wait halo_full, convert]",
+                                   "epilogue0 [wait tfull, work, wait staging]", "epilogue1 [wait tfull, work, wait staging]"};
+    fprintf(stderr, "conv_hs prof (CTA 0, cycles; mt=%d halos=%d slots=%d n_acc=%d tma_store=%d tiles/cta~%d):\n", mt, p.halo_bufs, p.slots,
+            p.n_acc, p.use_tma, (total_tiles + grid - 1) / grid);
+    for (int r = 0; r < 6; ++r)
+      fprintf(stderr, "  %-62s total %8lld | %8lld %8lld %8lld %8lld\n", names[r], h[r * 8 + 7], h[r * 8], h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3]);
+  }
   return LSSVC_OK;
 }
