@@ -144,6 +144,8 @@ int32_t lssvc_device_check(int32_t dev);
 const char *lssvc_last_error(void);
 /* number of kernels this library launched since load (bench.py's gpu_launches) */
 int64_t lssvc_launch_count(void);
+/* kernels launched by replaying a captured CUDA graph are added by the host layer (n per replay) */
+void lssvc_launch_count_add(int64_t n);
 
 /* ---- convolutions ------------------------------------------------------------------------ */
 /* tcgen05 / TMEM / TMA implicit-GEMM (TF32 operands, fp32 accumulate). */

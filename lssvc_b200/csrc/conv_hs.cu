@@ -42,6 +42,7 @@ constexpr int STAGE_K = 64;    // input channels x taps of one weight stage: KC 
 constexpr int NUM_THREADS = 640;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_ACC = 4;
+constexpr int MAX_ENTRIES = 32;  // weight stages per chunk (7x7 stride 2: 25)
 
 struct alignas(64) HsParams {
   CUtensorMap a_map[LSSVC_MAX_SRC];
@@ -61,6 +62,11 @@ struct alignas(64) HsParams {
   int halo_rows;               // pixels of one halo box
   unsigned char tap_w[MAX_TAPS];     // weight tap index r * kw + s
   unsigned short tap16[MAX_TAPS + 7];  // (byte offset of the tap's window origin inside the halo) >> 4, zero padded
+  // one entry per weight stage of a chunk (identical for every chunk): x = tap16[0] | tap16[1] << 16, y = tap16[2] | tap16[3] << 16,
+  // z = items | FIRST_OF_HALO << 8 | LAST_OF_HALO << 9, w = weight tap indices (4 x u8).  Copied to shared memory at start so
+  // that the single-thread producers walk it with one LDS per stage instead of chains of parameter-space loads.
+  uint4 stage_tab[MAX_ENTRIES];
+  int n_entries, total_chunks;
   int mt;                      // sub-tiles per tile (1 or 2)
   int n_acc;                   // accumulator slots in TMEM (2 or 4), each 2 * n_tile columns
   int Ho, Wo;
@@ -135,7 +141,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
   const long long t_begin = DBG ? clock64() : 0;
 #define HS_WAIT(slot, bar, parity)                    \
   do {                                                \
-    if (DBG) {                                        \
+    if (DBG && (dbgf & 2048)) {                       \
+      ptx::mbar_spin(bar, parity);                    \
+    } else if (DBG && (dbgf & 64)) {                  \
       const long long t0__ = clock64();               \
       ptx::mbar_wait(bar, parity);                    \
       prof[slot] += clock64() - t0__;                 \
@@ -163,6 +171,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
   __shared__ uint64_t tfull_bar[MAX_ACC];
   __shared__ uint64_t tempty_bar[MAX_ACC];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ uint4 stage_tab_s[MAX_ENTRIES];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -199,6 +208,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
     ptx::tmem_alloc(ptx::smem_u32(&tmem_base_slot), TMEM_COLS);
     ptx::tmem_relinquish();
   }
+  if (warp == 3 && lane < p.n_entries) stage_tab_s[lane] = p.stage_tab[lane];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -248,30 +258,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
       int s = 0;
       uint32_t ph = 0;
       const uint32_t tile_bytes = static_cast<uint32_t>(2 * p.n_tile) * B_ROWB;
+      const int n_entries = p.n_entries;
+      const uint32_t tab = ptx::smem_u32(stage_tab_s);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile / tiles_per_n) * p.n_tile;
         for (int j = 0; j < p.n_src; ++j) {
           for (int c = 0; c < p.chunks[j]; ++c) {
             const int k0 = p.coff[j] + c * KC;
-            for (int g = 0; g < p.n_groups; ++g) {
-              const int t1 = p.g_tap0[g + 1];
-              const int step = p.g_step[g];
-              for (int t = p.g_tap0[g]; t < t1; t += step) {
-                const int items = t1 - t < step ? t1 - t : step;
-                const uint32_t full = bar_full + 8 * s;
-                HS_WAIT(0, bar_empty + 8 * s, ph ^ 1u);
-                if (dbgf & 32) {
-                  ptx::mbar_arrive(full);
-                } else {
-                  ptx::mbar_expect_tx(full, tile_bytes * static_cast<uint32_t>(items));
-                  for (int i = 0; i < items; ++i)
-                    ptx::tma_load_4d(b_base + static_cast<uint32_t>(s * p.b_bytes) + static_cast<uint32_t>(i) * tile_bytes,
-                                     &p.b_map, full, k0, n0, 0, static_cast<int>(p.tap_w[t + i]));
-                }
-                if (++s == p.slots) {
-                  s = 0;
-                  ph ^= 1u;
-                }
+            for (int e = 0; e < n_entries; ++e) {
+              uint32_t e_x, e_y, e_z, e_w;
+              ptx::lds_u4(tab + 16u * static_cast<uint32_t>(e), e_x, e_y, e_z, e_w);
+              const int items = static_cast<int>(e_z & 0xffu);
+              const uint32_t full = bar_full + 8 * s;
+              HS_WAIT(0, bar_empty + 8 * s, ph ^ 1u);
+              if (dbgf & 32) {
+                ptx::mbar_arrive(full);
+              } else {
+                ptx::mbar_expect_tx(full, tile_bytes * static_cast<uint32_t>(items));
+#pragma unroll
+                for (int i = 0; i < TAPS_PER_STAGE; ++i)
+                  if (i < items)
+                    ptx::tma_load_4d(b_base + static_cast<uint32_t>(s * p.b_bytes) + static_cast<uint32_t>(i) * tile_bytes, &p.b_map,
+                                     full, k0, n0, 0, static_cast<int>((e_w >> (8 * i)) & 0xffu));
+              }
+              if (++s == p.slots) {
+                s = 0;
+                ph ^= 1u;
               }
             }
           }
@@ -303,57 +315,63 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
       constexpr uint32_t b_hi_word = (B_SBO >> 4) | (1u << 14) | (B_LAYOUT << 29);
       const uint32_t a16_base = (smem_base >> 4) | DESC_LO, b16_base = (b_base >> 4) | DESC_LO;
       constexpr uint32_t SUB16 = (SUB_W * ROWB) >> 4, LO16 = LO_OFF >> 4;
-      const int n_src = p.n_src, n_groups = p.n_groups;
+      const int n_entries = p.n_entries, total_chunks = p.total_chunks;
+      const uint32_t tab = ptx::smem_u32(stage_tab_s);
+      uint32_t e_x, e_y, e_z, e_w;
+      ptx::lds_u4(tab, e_x, e_y, e_z, e_w);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 #pragma unroll
         for (int j = 0; j < MT; ++j) HS_WAIT(0, bar_tempty + 8 * (slot0 + j), acc_ph ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tile = tmem_base + static_cast<uint32_t>(slot0) * 2u * n_tile;
         uint32_t acc = 0;  // 0 only for the first K slice of the tile
-        for (int js = 0; js < n_src; ++js) {
-          for (int c = 0; c < p.chunks[js]; ++c) {
-            for (int g = 0; g < n_groups; ++g) {
-              const int t1 = p.g_tap0[g + 1];
-              const int step = p.g_step[g];
-              const int t0 = p.g_tap0[g];
+        uint32_t a16_halo = 0;
+        for (int ch = 0; ch < total_chunks; ++ch) {
+          for (int e = 0; e < n_entries; ++e) {
+            const uint32_t c_x = e_x, c_y = e_y, c_z = e_z;
+            {  // next stage's entry: in flight while this stage's barrier wait and MMAs are issued
+              const int en = e + 1 == n_entries ? 0 : e + 1;
+              ptx::lds_u4(tab + 16u * static_cast<uint32_t>(en), e_x, e_y, e_z, e_w);
+            }
+            if (c_z & 0x100u) {  // first stage of a halo tile
               HS_WAIT(1, bar_halo_conv + 8 * hb, hph);
-              const uint32_t a16_halo = a16_base + static_cast<uint32_t>(hb) * halo16;
-              for (int t = t0; t < t1; t += step) {
-                const int items = t1 - t < step ? t1 - t : step;
-                uint32_t tap16[TAPS_PER_STAGE];
+              a16_halo = a16_base + static_cast<uint32_t>(hb) * halo16;
+            }
+            const int items = static_cast<int>(c_z & 0xffu);
+            uint32_t tap16[4] = {c_x & 0xffffu, c_x >> 16, c_y & 0xffffu, c_y >> 16};
+            HS_WAIT(2, bar_full + 8 * s, ph);
+            ptx::tc_fence_after();
+            const long long ti0 = (DBG && (dbgf & 64)) ? clock64() : 0;
+            const uint32_t b16_s = b16_base + static_cast<uint32_t>(s) * b16_stage;
 #pragma unroll
-                for (int i = 0; i < TAPS_PER_STAGE; ++i) tap16[i] = p.tap16[t + i];  // the table is padded: no bound check
-                HS_WAIT(2, bar_full + 8 * s, ph);
-                ptx::tc_fence_after();
-                const long long ti0 = DBG ? clock64() : 0;
-                const uint32_t b16_s = b16_base + static_cast<uint32_t>(s) * b16_stage;
+            for (int i = 0; i < TAPS_PER_STAGE; ++i) {
+              if (i < items) {
+                const uint32_t a16_tap = a16_halo + tap16[i];
+                const uint32_t b16_tap = b16_s + static_cast<uint32_t>(i) * tile16;
 #pragma unroll
-                for (int i = 0; i < TAPS_PER_STAGE; ++i) {
-                  if (i < items) {
-                    const uint32_t a16_tap = a16_halo + tap16[i];
-                    const uint32_t b16_tap = b16_s + static_cast<uint32_t>(i) * tile16;
+                for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-#pragma unroll
-                      for (int j = 0; j < MT; ++j) {
-                        const uint32_t a16 = a16_tap + j * SUB16 + ks * 2;
-                        const uint32_t d1 = d_tile + static_cast<uint32_t>(j) * 2u * n_tile;
-                        // [D1 | D2] (+)= A_hi * [W_hi | W_lo]   then   D2 += A_lo * W_hi
-                        if (!DBG || !(dbgf & 1)) ptx::mma_f16_ss2(d1, a16, a_hi_word, b16_tap + ks * 2, b_hi_word, idesc_2n, acc);
-                        if (!DBG || !(dbgf & 2)) ptx::mma_f16_ss2(d1 + n_tile, a16 + LO16, a_hi_word, b16_tap + ks * 2, b_hi_word, idesc_n, 1u);
-                      }
-                      acc = 1u;
-                    }
+                  for (int j = 0; j < MT; ++j) {
+                    const uint32_t a16 = a16_tap + j * SUB16 + ks * 2;
+                    const uint32_t d1 = d_tile + static_cast<uint32_t>(j) * 2u * n_tile;
+                    // [D1 | D2] (+)= A_hi * [W_hi | W_lo]   then   D2 += A_lo * W_hi
+                    if (!DBG || !(dbgf & 1))
+                      ptx::mma_f16_ss2(d1, a16, a_hi_word, b16_tap + ks * 2, b_hi_word, (DBG && (dbgf & 256)) ? idesc_n : idesc_2n, acc);
+                    if (!DBG || !(dbgf & 2))
+                      ptx::mma_f16_ss2(d1 + n_tile, (DBG && (dbgf & 512)) ? a16 : a16 + LO16, a_hi_word, b16_tap + ks * 2, b_hi_word,
+                                       (DBG && (dbgf & 1024)) ? idesc_2n : idesc_n, 1u);
                   }
-                }
-                ptx::mma_commit(bar_empty + 8 * s);
-                if (DBG) prof[3] += clock64() - ti0;
-                if (++s == slots) {
-                  s = 0;
-                  ph ^= 1u;
+                  acc = 1u;
                 }
               }
-              // the halo tile is free once every MMA that reads it has completed
+            }
+            ptx::mma_commit(bar_empty + 8 * s);
+            if (DBG && (dbgf & 64)) prof[3] += clock64() - ti0;
+            if (++s == slots) {
+              s = 0;
+              ph ^= 1u;
+            }
+            if (c_z & 0x200u) {  // last stage of the halo tile: it is free once every MMA that reads it has completed
               ptx::mma_commit(bar_halo_empty + 8 * hb);
               if (++hb == halo_bufs) {
                 hb = 0;
@@ -388,7 +406,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
         for (int c = 0; c < p.chunks[j]; ++c) {
           for (int g = 0; g < p.n_groups; ++g) {
             HS_WAIT(0, bar_halo_full + 8 * hb, hph);
-            const long long tc0 = DBG ? clock64() : 0;
+            const long long tc0 = (DBG && (dbgf & 64)) ? clock64() : 0;
             const uint32_t halo = smem_base + static_cast<uint32_t>(hb) * halo_bytes;
             for (int r = ct; r < halo_rows && !(dbgf & 4); r += 256) {
               const uint32_t x = halo + static_cast<uint32_t>(r) * ROWB;
@@ -412,7 +430,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
             ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar_halo_conv + 8 * hb);
-            if (DBG) prof[1] += clock64() - tc0;
+            if (DBG && (dbgf & 64)) prof[1] += clock64() - tc0;
             if (++hb == halo_bufs) {
               hb = 0;
               hph ^= 1u;
@@ -462,13 +480,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
         const long long pix = static_cast<long long>(oy) * Wo + ox;
         if (use_tma) {
           // the staging tile is free once the TMA stores issued from it (this set's previous unit) have read it
-          const long long ts0 = DBG ? clock64() : 0;
+          const long long ts0 = (DBG && (dbgf & 64)) ? clock64() : 0;
           if (store_thread) ptx::bulk_wait_read_all();
           ptx::named_bar_sync(2 + eset, 128);
-          if (DBG) prof[2] += clock64() - ts0;
+          if (DBG && (dbgf & 64)) prof[2] += clock64() - ts0;
         }
         HS_WAIT(0, bar_tfull + 8 * slot, acc_ph);
-        const long long te0 = DBG ? clock64() : 0;
+        const long long te0 = (DBG && (dbgf & 64)) ? clock64() : 0;
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slot * 2 * n_tile);
         for (int n = 0; n < n_tile && !(dbgf & 8); n += 16) {
@@ -580,7 +598,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * slot);
-        if (DBG) prof[1] += clock64() - te0;
+        if (DBG && (dbgf & 64)) prof[1] += clock64() - te0;
         if (use_tma) {
           ptx::fence_proxy_async_smem();  // staging writes (generic proxy) -> visible to the TMA store (async proxy)
           ptx::named_bar_sync(4 + eset, 128);
@@ -809,6 +827,28 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
     const int nt = p.g_tap0[g + 1] - p.g_tap0[g];
     const int n_st = (nt + tps - 1) / tps;
     p.g_step[g] = (nt + n_st - 1) / n_st;
+  }
+  {
+    int ne = 0, total_chunks = 0;
+    for (int j = 0; j < c->n_src; ++j) total_chunks += p.chunks[j];
+    for (int g = 0; g < p.n_groups; ++g) {
+      const int t1 = p.g_tap0[g + 1], step = p.g_step[g];
+      for (int t = p.g_tap0[g]; t < t1; t += step) {
+        const int items = t1 - t < step ? t1 - t : step;
+        LSSVC_REQUIRE(ne < MAX_ENTRIES && items <= 4, "conv_hs: stage table overflow");
+        uint32_t t16[4] = {0, 0, 0, 0}, tw = 0;
+        for (int i = 0; i < items; ++i) {
+          t16[i] = p.tap16[t + i];
+          tw |= static_cast<uint32_t>(p.tap_w[t + i]) << (8 * i);
+        }
+        uint32_t flags = static_cast<uint32_t>(items);
+        if (t == p.g_tap0[g]) flags |= 0x100u;
+        if (t + step >= t1) flags |= 0x200u;
+        p.stage_tab[ne++] = make_uint4(t16[0] | (t16[1] << 16), t16[2] | (t16[3] << 16), flags, tw);
+      }
+    }
+    p.n_entries = ne;
+    p.total_chunks = total_chunks;
   }
   p.Ho = Ho; p.Wo = Wo;
   p.tiles_x = lssvc::ceil_div(Wo, SUB_W * mt);

@@ -14,6 +14,10 @@ class Engine(nets.ParamBag):
     def __init__(self, spec, model_tag, seed=None):
         super().__init__(spec, seed=seed, gains=nets.model_gains(model_tag))
         self._packs = {}
+        self._graphs = {}
+        # whole-frame CUDA graphs (models.py), opt in with LSSVC_CUDA_GRAPH=1: measured equal to eager launches on one
+        # B200 (the GPU never waits for the host: tools/graph_ab.py), useful when the host is the bottleneck
+        self.use_graphs = os.environ.get("LSSVC_CUDA_GRAPH", "0") == "1"
         self.fuse_ffn = os.environ.get("LSSVC_FUSE_FFN", "1") != "0"
         self.fuse_pw = os.environ.get("LSSVC_FUSE_PW", "1") != "0"
         self.shape_hr = (256, 256)
@@ -26,6 +30,7 @@ class Engine(nets.ParamBag):
         self.scale_factor = scale
         self.shape_hr = tuple(shape_hr)
         self.pad_size = tuple(pad_size)
+        self._graphs = {}
         if any(int(p) != 0 for p in self.pad_size):
             # the reference's test.py always passes (0, 0, 0, 0) (test.py:212-213)
             raise NotImplementedError("inter-layer de-padding with a non-zero pad_size is not implemented")
@@ -33,6 +38,7 @@ class Engine(nets.ParamBag):
     # ---- weight cache ---------------------------------------------------------------------------------------
     def _invalidate(self):
         self._packs = {}
+        self._graphs = {}
 
     def _apply(self, fn, *a, **k):
         self._invalidate()

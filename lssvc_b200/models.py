@@ -12,7 +12,7 @@ import math
 
 import torch
 
-from . import entropy, ops
+from . import _lib, entropy, ops
 from .engine import Engine
 from .nets import intra_ss_spec, lssvc_spec
 from .ops import View
@@ -631,27 +631,26 @@ class LSSVC(Engine):
         return self.depth_conv_block(name + ".up_conv2", cat2)
 
     # ---- forward ------------------------------------------------------------------------------------------------
-    def _dpb_view(self, dpb, key, image):
+    def _dpb_view(self, dpb, key, image, as_view_of=None):
+        """NHWC view of a DPB entry.  as_view_of: a static view to convert into (graph replay) when no valid native
+        view travels with the tensor."""
         t = dpb.get(key)
         if t is None:
             return None
         native = dpb.get("_native", {}).get(key)
         if native is not None and native[1] is t and native[2] == t._version:
-            return native[0]
+            token = native[3] if len(native) > 3 else None
+            if token is None or token[0]["gen"] == token[1]:    # a graph's static output is valid until its next replay
+                return native[0]
+        if as_view_of is not None:
+            if t.device != self.device:
+                t = t.to(self.device)
+            return View.from_nchw(t.float(), out=as_view_of)
         return self.image_view(t) if image else self.feature_view(t)
 
-    @torch.no_grad()
-    def forward_one_frame(self, x_bl, x_el, ref_frame_bl, ref_frame_el, ref_feature_bl, ref_feature_el, _dpb=None,
-                          _write=None):
-        """LSSVC.forward_one_frame (LSSVC_net.py:445-528)."""
-        self._require_cuda()
-        dpb = _dpb if _dpb is not None else {"ref_frame_bl": ref_frame_bl, "ref_frame_el": ref_frame_el,
-                                             "ref_feature_bl": ref_feature_bl, "ref_feature_el": ref_feature_el}
-        bits = _Bits(self.device)
-        w = _write
-        xb, xe = self.image_view(x_bl), self.image_view(x_el)
-        rb, re = self._dpb_view(dpb, "ref_frame_bl", True), self._dpb_view(dpb, "ref_frame_el", True)
-        fb, fe = self._dpb_view(dpb, "ref_feature_bl", False), self._dpb_view(dpb, "ref_feature_el", False)
+    def _frame_core(self, xb, xe, rb, re, fb, fe, bits, w):
+        """The kernel launches of one P-frame on NHWC views (no host synchronisation, no host-side state besides the
+        weight caches): what a CUDA graph of the frame captures."""
         bl = self._base_layer(xb, rb, fb, bits, w)
         # EL motion
         mv_ctx_prior, mv_ctx = self._mv_contexts(bl["mv_hat"])
@@ -681,14 +680,98 @@ class LSSVC(Engine):
         feature, recon = self._res_decode(y_hat, c1, c2, c3)
         _dbg(self, mv=mv, mv_y=mv_y, mv_y_hat=mv_y_hat, mv_prm=mv_prm, mv_z_hat=mv_z_hat, z_hat=z_hat, y=y, y_hat=y_hat,
              params=params, c1=c1, c2=c2, c3=c3)
-        bit_bl, bit_el = bits.read()
-        out = {"ref_frame_bl": bl["recon"].to_nchw(), "ref_feature_bl": bl["feature"].to_nchw(),
-               "ref_frame_el": recon.to_nchw(), "ref_feature_el": feature.to_nchw()}
-        out["_native"] = {"ref_feature_bl": (bl["feature"], out["ref_feature_bl"], out["ref_feature_bl"]._version),
-                          "ref_feature_el": (feature, out["ref_feature_el"], out["ref_feature_el"]._version)}
+        return {"bl_recon": bl["recon"], "bl_feature": bl["feature"], "recon": recon, "feature": feature, "mv_hat": mv_hat,
+                "warp_frame": warp_frame}
+
+    def _frame_result(self, v, bit_bl, bit_el, token=None):
+        """Views of one coded frame -> the reference's result dict (fresh NCHW tensors the caller may mutate)."""
+        out = {"ref_frame_bl": v["bl_recon"].to_nchw(), "ref_feature_bl": v["bl_feature"].to_nchw(),
+               "ref_frame_el": v["recon"].to_nchw(), "ref_feature_el": v["feature"].to_nchw()}
+        # NHWC originals of the features: the next frame reads them directly when the caller passes the tensors back
+        # untouched.  token: (graph entry, generation) when the views are a graph's static outputs, valid until its next replay.
+        out["_native"] = {"ref_feature_bl": (v["bl_feature"], out["ref_feature_bl"], out["ref_feature_bl"]._version, token),
+                          "ref_feature_el": (v["feature"], out["ref_feature_el"], out["ref_feature_el"]._version, token)}
         return {"dpb": out, "bit_bl": bit_bl, "bit_el": bit_el, "encoding_time_EL": 0.0, "decoding_time_EL": 0.0,
-                "encoding_time_BL": 0.0, "decoding_time_BL": 0.0, "mv_hat": mv_hat.to_nchw(),
-                "warp_frame": warp_frame.to_nchw()}
+                "encoding_time_BL": 0.0, "decoding_time_BL": 0.0, "mv_hat": v["mv_hat"].to_nchw(),
+                "warp_frame": v["warp_frame"].to_nchw()}
+
+    @torch.no_grad()
+    def forward_one_frame(self, x_bl, x_el, ref_frame_bl, ref_frame_el, ref_feature_bl, ref_feature_el, _dpb=None,
+                          _write=None):
+        """LSSVC.forward_one_frame (LSSVC_net.py:445-528)."""
+        self._require_cuda()
+        dpb = _dpb if _dpb is not None else {"ref_frame_bl": ref_frame_bl, "ref_frame_el": ref_frame_el,
+                                             "ref_feature_bl": ref_feature_bl, "ref_feature_el": ref_feature_el}
+        if (self.use_graphs and _write is None and getattr(self, "_debug", None) is None and not getattr(self, "_force", None)
+                and ops.TRACE is None and not _lib.DRY_RUN):
+            return self._forward_graphed(x_bl, x_el, dpb)
+        bits = _Bits(self.device)
+        xb, xe = self.image_view(x_bl), self.image_view(x_el)
+        rb, re = self._dpb_view(dpb, "ref_frame_bl", True), self._dpb_view(dpb, "ref_frame_el", True)
+        fb, fe = self._dpb_view(dpb, "ref_feature_bl", False), self._dpb_view(dpb, "ref_feature_el", False)
+        v = self._frame_core(xb, xe, rb, re, fb, fe, bits, _write)
+        bit_bl, bit_el = bits.read()
+        return self._frame_result(v, bit_bl, bit_el)
+
+    # ---- whole-frame CUDA graph ---------------------------------------------------------------------------------
+    # A P-frame is ~530 kernel launches with static shapes: after one eager frame per input signature (which packs the
+    # weights and warms the allocator) the launches are captured once and replayed; inputs are staged into static
+    # buffers, results leave as fresh tensors, the only host<->device sync stays the read of the two bit counters.
+    def _forward_graphed(self, x_bl, x_el, dpb):
+        fbt, fet = dpb.get("ref_feature_bl"), dpb.get("ref_feature_el")
+        key = (tuple(x_bl.shape), tuple(x_el.shape), None if fbt is None else tuple(fbt.shape),
+               None if fet is None else tuple(fet.shape))
+        g = self._graphs.get(key)
+        if g is None or g == "warm":
+            if g is None:
+                self._graphs[key] = "warm"
+                bits = _Bits(self.device)
+                v = self._frame_core(self.image_view(x_bl), self.image_view(x_el), self._dpb_view(dpb, "ref_frame_bl", True),
+                                     self._dpb_view(dpb, "ref_frame_el", True), self._dpb_view(dpb, "ref_feature_bl", False),
+                                     self._dpb_view(dpb, "ref_feature_el", False), bits, None)
+                bit_bl, bit_el = bits.read()
+                return self._frame_result(v, bit_bl, bit_el)
+            g = self._graphs[key] = self._capture_frame(x_bl, x_el, dpb)
+        # ---- stage the inputs
+        for name, t in (("x_bl", x_bl), ("x_el", x_el), ("ref_frame_bl", dpb["ref_frame_bl"]), ("ref_frame_el", dpb["ref_frame_el"])):
+            g["in"][name].copy_(t, non_blocking=True)
+        for name in ("ref_feature_bl", "ref_feature_el"):
+            dst = g["in"][name]
+            if dst is None:
+                continue
+            src = self._dpb_view(dpb, name, False, as_view_of=dst)
+            if src is not dst:
+                dst.buf.copy_(src.buf)
+        g["gen"] += 1
+        g["graph"].replay()
+        _lib.load().lssvc_launch_count_add(g["launches"])
+        bit_bl, bit_el = g["bits"].read()
+        return self._frame_result(g["out"], bit_bl, bit_el, token=(g, g["gen"]))
+
+    def _capture_frame(self, x_bl, x_el, dpb):
+        dev = self.device
+        new_like = lambda t: torch.empty(tuple(t.shape), dtype=torch.float32, device=dev)
+        static = {"x_bl": new_like(x_bl), "x_el": new_like(x_el), "ref_frame_bl": new_like(dpb["ref_frame_bl"]),
+                  "ref_frame_el": new_like(dpb["ref_frame_el"])}
+        for name in ("ref_feature_bl", "ref_feature_el"):
+            t = dpb.get(name)
+            if t is None:
+                static[name] = None
+            else:
+                C = t.shape[1]
+                v = View.alloc(t.shape[2], t.shape[3], ops.round_up(C, 8), dev, zero=True)
+                v.real = C
+                static[name] = v
+        bits = _Bits(dev)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            bits.t.zero_()
+            v = self._frame_core(self.image_view(static["x_bl"]), self.image_view(static["x_el"]),
+                                 self.image_view(static["ref_frame_bl"]), self.image_view(static["ref_frame_el"]),
+                                 static["ref_feature_bl"], static["ref_feature_el"], bits, None)
+        return {"graph": graph, "in": static, "out": v, "bits": bits, "gen": 0, "launches": _lib.launch_count() - l0}
 
     def encode_decode_extend(self, *args, **kwargs):
         raise NotImplementedError("bitstream writing needs LSSVC_extend")

@@ -252,3 +252,38 @@ def test_write_stream_roundtrip(setup, tmp_path):
         assert real_p[k] % 8 == 0 and 0.7 * est_p[k] < real_p[k] < 1.1 * est_p[k] + 400
     from lssvc_b200 import stream
     assert stream.filesize(str(tmp_path / "p_el.bin")) * 8 == real_p["bit_el"]
+
+
+def test_cuda_graph_frames_match_eager(cuda_device):
+    """Whole-frame CUDA graphs (models.LSSVC._forward_graphed): a GOP coded with graph replay must reproduce the eager
+    launches exactly (same kernels, same order): reconstructions bit-identical, bits equal up to the order of the
+    double-precision atomic adds."""
+    from lssvc_b200 import IntraSS, LSSVC_extend, synth
+    net_i = IntraSS(seed=0).to(cuda_device)
+    frames = synth.make_sequence(H, W, 6, seed=3)
+
+    def run(use_graphs):
+        net_p = LSSVC_extend(seed=1).to(cuda_device)
+        net_p.use_graphs = use_graphs
+        for n in (net_i, net_p):
+            n.set_scale_information(2.0, (H, W), (0, 0, 0, 0))
+        r = net_i.encode_decode(frames[0][0].to(cuda_device), frames[0][1].to(cuda_device), None, None, H // 2, W // 2, H, W)
+        dpb = {"ref_frame_bl": r["x_hat_bl"], "ref_frame_el": r["x_hat_el"], "ref_feature_bl": None, "ref_feature_el": r["feature_el"]}
+        rows = []
+        for x_bl, x_el in frames[1:]:
+            dpb["ref_frame_bl"].clamp_(0, 1)
+            dpb["ref_frame_el"].clamp_(0, 1)
+            r = net_p.encode_decode(x_bl.to(cuda_device), x_el.to(cuda_device), dpb, None, None, W, H, W // 2, H // 2)
+            dpb = r["dpb"]
+            rows.append((r["bit_bl"], r["bit_el"], dpb["ref_frame_bl"].clone(), dpb["ref_frame_el"].clone(), r["mv_hat"].clone()))
+        return rows, net_p
+
+    eager, _ = run(False)
+    graphed, net_p = run(True)
+    assert any(isinstance(g, dict) for g in net_p._graphs.values()), "no frame graph was captured"
+    for i, (e, g) in enumerate(zip(eager, graphed)):
+        assert abs(e[0] - g[0]) <= 1e-9 * abs(e[0]) and abs(e[1] - g[1]) <= 1e-9 * abs(e[1]), (i, e[:2], g[:2])
+        for a, b in zip(e[2:], g[2:]):
+            assert torch.equal(a, b), f"P-frame {i + 1}: graph replay differs from eager"
+    # a stale DPB (the graph has been replayed since) must not be read through its native views
+    print("graph replay == eager over", len(eager), "P-frames; bits", [round(g[1]) for g in graphed])

@@ -32,6 +32,13 @@ SHAPES = [
     ("3x3 64->3 @1", [64], 3, 3, 1, 1152, 1920, False),
     ("3x3 128->128 @1/16", [128], 128, 3, 1, 72, 120, False),
 ]
+# extra shapes for kernel studies, selected with CONV_BENCH_ONLY (not part of the default table)
+EXTRA = [
+    ("study 3x3 64->128 @1/2", [64], 128, 3, 1, 576, 960, False),
+    ("study 3x3 64->32 @1/2", [64], 32, 3, 1, 576, 960, False),
+    ("study 3x3 64->16 @1/2", [64], 16, 3, 1, 576, 960, False),
+    ("study 3x3 64->96 @1/2", [64], 96, 3, 1, 576, 960, False),
+]
 
 
 def run(engine, shape, dev, check_rows=64):
@@ -77,7 +84,7 @@ def run(engine, shape, dev, check_rows=64):
 def main():
     only = os.environ.get("CONV_BENCH_ONLY")
     if only:
-        SHAPES[:] = [s for s in SHAPES if only in s[0]]
+        SHAPES[:] = [s for s in SHAPES + EXTRA if only in s[0]]
     engines = sys.argv[1:] or ["h2", "tc3"]
     dev = torch.device("cuda:0")
     _lib.check(_lib.load().lssvc_device_check(0), "device_check")

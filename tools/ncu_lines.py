@@ -80,7 +80,7 @@ def main():
         if cur and r[2].startswith("0x"):
             stalls = {h[6:]: num(r[i]) for i, h in enumerate(hdr2) if h.startswith("stall_") and "Not Issued" not in h}
             sass.append((int(r[2], 16), cur[0], cur[1], num(r[idx["# Samples"]]), num(r[idx["Instructions Executed"]]), stalls, r[3].strip()))
-    sass.sort()
+    sass.sort(key=lambda t: t[0])
     def role_of_line(n):
         role = "prologue"
         for ln, name in banners:
