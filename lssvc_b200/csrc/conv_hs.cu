@@ -48,6 +48,8 @@ struct alignas(64) HsParams {
   CUtensorMap a_map[LSSVC_MAX_SRC];
   CUtensorMap b_map;
   CUtensorMap out_map, out2_map;  // TMA-store epilogue (use_tma)
+  CUtensorMap res1_map, res2_map;  // residual tiles TMA-loaded into the staging buffers ahead of the accumulator (res_tma bits 0, 1)
+  int res_tma, res_tx;  // res_tx: number of residual tensors fetched by TMA (0..2)
   int use_tma, slab_w, n_slabs, stage_off, stage2_delta, stage_stride;  // staging per epilogue set: [out, out2][n_slabs][128 px][slab_w]
   int n_src;
   int chunks[LSSVC_MAX_SRC];  // ceil(C / KC) per source
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
   __shared__ uint64_t halo_conv[MAX_HALO];
   __shared__ uint64_t tfull_bar[MAX_ACC];
   __shared__ uint64_t tempty_bar[MAX_ACC];
+  __shared__ uint64_t res_full[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ uint4 stage_tab_s[MAX_ENTRIES];
 
@@ -183,10 +186,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
   const uint32_t bar_halo_full = ptx::pin(ptx::smem_u32(halo_full)), bar_halo_empty = ptx::pin(ptx::smem_u32(halo_empty));
   const uint32_t bar_halo_conv = ptx::pin(ptx::smem_u32(halo_conv));
   const uint32_t bar_tfull = ptx::pin(ptx::smem_u32(tfull_bar)), bar_tempty = ptx::pin(ptx::smem_u32(tempty_bar));
+  const uint32_t bar_res = ptx::pin(ptx::smem_u32(res_full));
 
   if (warp == 0 && lane == 0) {
     for (int j = 0; j < p.n_src; ++j) ptx::prefetch_tensormap(&p.a_map[j]);
     ptx::prefetch_tensormap(&p.b_map);
+    if (p.res_tma & 1) ptx::prefetch_tensormap(&p.res1_map);
+    if (p.res_tma & 2) ptx::prefetch_tensormap(&p.res2_map);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.slots; ++s) {
@@ -202,6 +208,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
       ptx::mbar_init(bar_tfull + 8 * b, 1);
       ptx::mbar_init(bar_tempty + 8 * b, 4);
     }
+    ptx::mbar_init(bar_res, 1);
+    ptx::mbar_init(bar_res + 8, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -458,13 +466,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
     const float *const res2 = p.res2;
     const float *const gdn_x = p.gdn_x;
     const float *const bias = p.bias;
-    const long long out_pitch = p.out_pitch, out2_pitch = p.out2_pitch, res1_pitch = p.res1_pitch,
-                    res2_pitch = p.res2_pitch, gdn_pitch = p.gdn_pitch;
+    const int out_pitch = p.out_pitch, out2_pitch = p.out2_pitch, res1_pitch = p.res1_pitch, res2_pitch = p.res2_pitch,
+              gdn_pitch = p.gdn_pitch;
     const bool use_tma = p.use_tma != 0 && fast && chunk_uniform;
     const uint32_t slab_w = static_cast<uint32_t>(p.slab_w);
     const uint32_t stage = smem_base + static_cast<uint32_t>(p.stage_off) + static_cast<uint32_t>(eset * p.stage_stride);
     const uint32_t stage2 = stage + static_cast<uint32_t>(p.stage2_delta);
     const bool store_thread = q == 0 && lane == 0;
+    // residual tiles fetched by TMA into the staging buffers (res1 -> out staging, res2 -> out2 staging) while the
+    // unit's MMAs are still running: the accumulator is then added in place, no global-load latency in the epilogue
+    const bool r1_tma = use_tma && (p.res_tma & 1), r2_tma = use_tma && (p.res_tma & 2);
+    uint32_t res_ph = 0;
     int u = 0;  // running unit counter (all units, both sets)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile / tiles_per_n;
@@ -481,11 +493,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
         if (use_tma) {
           // the staging tile is free once the TMA stores issued from it (this set's previous unit) have read it
           const long long ts0 = (DBG && (dbgf & 64)) ? clock64() : 0;
-          if (store_thread) ptx::bulk_wait_read_all();
+          if (store_thread) {
+            ptx::bulk_wait_read_all();
+            if (r1_tma || r2_tma) {
+              const uint32_t bar = bar_res + 8 * eset;
+              const int oy0 = ty * TILE_H, ox0 = tx * tile_w + j * SUB_W;
+              int live = (cout - n0 + static_cast<int>(slab_w) - 1) / static_cast<int>(slab_w);  // slabs of this channel tile that hold real channels
+              live = live < p.n_slabs ? live : p.n_slabs;
+              ptx::mbar_expect_tx(bar, static_cast<uint32_t>(live) * (128u * slab_w * 4u) * static_cast<uint32_t>(p.res_tx));
+              for (int k = 0; k < p.n_slabs; ++k) {
+                const int pc = n0 + k * static_cast<int>(slab_w);
+                if (pc >= cout) break;
+                const uint32_t dst = static_cast<uint32_t>(k) * (128u * slab_w * 4u);
+                if (r1_tma) ptx::tma_load_3d(stage + dst, &p.res1_map, bar, pc, ox0, oy0);
+                if (r2_tma) ptx::tma_load_3d(stage2 + dst, &p.res2_map, bar, pc, ox0, oy0);
+              }
+            }
+          }
           ptx::named_bar_sync(2 + eset, 128);
           if (DBG && (dbgf & 64)) prof[2] += clock64() - ts0;
         }
         HS_WAIT(0, bar_tfull + 8 * slot, acc_ph);
+        if (r1_tma || r2_tma) {
+          HS_WAIT(0, bar_res + 8 * eset, res_ph);
+          res_ph ^= 1u;
+        }
         const long long te0 = (DBG && (dbgf & 64)) ? clock64() : 0;
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slot * 2 * n_tile);
@@ -509,13 +541,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
             for (int g = 0; g < 4; ++g)
               b4v[g] = (live && cg + 4 * g < cout) ? __ldg(reinterpret_cast<const float4 *>(bias + cg) + g)
                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            // residuals that do not ride the staging buffers: all loads of the chunk in flight before the accumulator wait
+            const float4 *const q1 = (live && res1 && valid && !r1_tma) ? reinterpret_cast<const float4 *>(res1 + opix * res1_pitch + c0) : nullptr;
+            const float4 *const q2 = (live && res2 && valid && !r2_tma) ? reinterpret_cast<const float4 *>(res2 + opix * res2_pitch + c0) : nullptr;
+            const float4 *const gq = (live && epi != LSSVC_EPI_PLAIN && valid) ? reinterpret_cast<const float4 *>(gdn_x + pix * gdn_pitch + cg) : nullptr;
+            float4 q1v[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) q1v[g] = (q1 && cg + 4 * g < cout) ? __ldg(q1 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
             ptx::tmem_ld_wait();
             if (live) {
               float4 *const o = reinterpret_cast<float4 *>(out + opix * out_pitch + c0);
               float4 *const o2 = out2 ? reinterpret_cast<float4 *>(out2 + opix * out2_pitch + c0) : nullptr;
-              const float4 *const q1 = (res1 && valid) ? reinterpret_cast<const float4 *>(res1 + opix * res1_pitch + c0) : nullptr;
-              const float4 *const q2 = (res2 && valid) ? reinterpret_cast<const float4 *>(res2 + opix * res2_pitch + c0) : nullptr;
-              const float4 *const gq = (epi != LSSVC_EPI_PLAIN && valid) ? reinterpret_cast<const float4 *>(gdn_x + pix * gdn_pitch + cg) : nullptr;
               // staging row of this pixel for the slab holding channels n .. n+15 (TMA-store path)
               const uint32_t srow = static_cast<uint32_t>(n / slab_w) * (128u * slab_w * 4u) + static_cast<uint32_t>(m) * (slab_w * 4u);
               const uint32_t sswz = (slab_w == 32 ? static_cast<uint32_t>(m & 7) : static_cast<uint32_t>((m >> 1) & 3)) << 4;
@@ -546,14 +582,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
 #pragma unroll
                   for (int e = 0; e < 4; ++e) v[e] *= out_scale;
                   if (q1) {
-                    const float4 t = q1[g];
+                    const float4 t = q1v[g];
                     v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
                   }
                   if (q2) {
-                    const float4 t = q2[g];
+                    const float4 t = __ldg(q2 + g);
                     v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
                   }
                   const uint32_t soff = srow + ((spiece + 16u * g) ^ sswz);
+                  if (r1_tma) {
+                    const float4 t = ptx::lds_f4(stage + soff);
+                    v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                  }
+                  if (r2_tma) {
+                    const float4 t = ptx::lds_f4(stage2 + soff);
+                    v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                  }
                   if (use_tma) {
                     ptx::sts_u4(stage + soff, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
                   } else {
@@ -903,11 +947,18 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
   p.slab_w = slab_w;
   p.n_slabs = (n_tile + slab_w - 1) / slab_w;
   const int stage_bytes = p.n_slabs * 128 * slab_w * 4;
-  const int per_set = stage_bytes * (p.out2 ? 2 : 1);
+  // residuals ride the staging buffers: res1 lands in the out staging, res2 in the out2 staging when that one is free
+  const bool r1_tma = use_tma && p.res1 && !c->pixel_shuffle;
+  bool r2_tma = use_tma && p.res2 && !c->pixel_shuffle && !p.out2;
+  int per_set = stage_bytes * ((p.out2 || r2_tma) ? 2 : 1);
   const int smem_budget = 225 * 1024;
   auto fits = [&](int halos, int slots, bool staging) {
     return halos * p.halo_bytes + slots * p.b_bytes + (staging ? 2 * per_set : 0) + 1024 <= smem_budget;
   };
+  if (r2_tma && !fits(2, 3, true)) {  // no room for a second staging buffer: res2 is read from global in the epilogue
+    r2_tma = false;
+    per_set = stage_bytes * (p.out2 ? 2 : 1);
+  }
   if (use_tma && !fits(2, 2, true)) use_tma = false;
   LSSVC_REQUIRE(fits(2, 2, use_tma), "conv_hs: pipeline does not fit in shared memory (halo %d B, weight stage %d B, staging %d B)",
                 p.halo_bytes, p.b_bytes, use_tma ? 2 * per_set : 0);
@@ -942,6 +993,9 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
     };
     CUresult r = make_out_map(&p.out_map, c->out);
     if (r == CUDA_SUCCESS && p.out2) r = make_out_map(&p.out2_map, c->out2);
+    if (r == CUDA_SUCCESS && r1_tma && use_tma) { r = make_out_map(&p.res1_map, c->res1); p.res_tma |= 1; }
+    if (r == CUDA_SUCCESS && r2_tma && use_tma) { r = make_out_map(&p.res2_map, c->res2); p.res_tma |= 2; }
+    p.res_tx = (p.res_tma & 1) + ((p.res_tma >> 1) & 1);  // residual tensors loaded per slab
     if (r != CUDA_SUCCESS) {
       lssvc::set_error("conv_hs: cuTensorMapEncodeTiled(out) failed with %d (C=%d pitch=%d %dx%d ps=%d)", static_cast<int>(r),
                        c->out.C, c->out.pitch, Ho, Wo, c->pixel_shuffle);

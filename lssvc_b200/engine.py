@@ -20,6 +20,7 @@ class Engine(nets.ParamBag):
         self.use_graphs = os.environ.get("LSSVC_CUDA_GRAPH", "0") == "1"
         self.fuse_ffn = os.environ.get("LSSVC_FUSE_FFN", "1") != "0"
         self.fuse_pw = os.environ.get("LSSVC_FUSE_PW", "1") != "0"
+        self.lazy_act = os.environ.get("LSSVC_LAZY_ACT", "1") != "0"
         self.shape_hr = (256, 256)
         self.scale_factor = 2.0
         self.pad_size = (0, 0, 0, 0)
@@ -83,6 +84,13 @@ class Engine(nets.ParamBag):
         """conv (+PixelShuffle) with fused epilogue.  Returns the output view, or (out, lrelu(out, act_copy))."""
         if isinstance(srcs, View):
             srcs = [srcs]
+        # un-materialised activations (ops.LazyAct): one common slope -> LeakyReLU in the conv's operand path, else write them out
+        lazy = [s.slope if isinstance(s, ops.LazyAct) else None for s in srcs]
+        if any(l is not None for l in lazy):
+            if len(set(lazy)) == 1 and in_lrelu is None:
+                in_lrelu, srcs = lazy[0], [s.base for s in srcs]
+            else:
+                srcs = [self.lrelu(s.base, s.slope) if isinstance(s, ops.LazyAct) else s for s in srcs]
         pc = self.pack(name, srcs, stride, ps, transposed, pad)
         Hi, Wi = srcs[0].H, srcs[0].W
         Ho = (Hi + 2 * pc.pad - pc.kh) // stride + 1
@@ -92,13 +100,16 @@ class Engine(nets.ParamBag):
         if out is None:
             out = self.new(Ho * f, Wo * f, C)
         out2 = None
-        if act_copy is not None:
+        lazy_copy = act_copy is not None and act_copy_out is None and self.lazy_act and ops.default_engine() == "h2"
+        if act_copy is not None and not lazy_copy:
             out2 = act_copy_out if act_copy_out is not None else self.new(Ho * f, Wo * f, C)
         ex = lambda v: None if v is None else v.exact()
         ops.TRACE_NAME = name
         kw = {} if in_lrelu is None else {"in_transform": _lib.IN_LRELU, "in_slope": float(in_lrelu)}
         ops.conv(pc, srcs, out.exact(), act=act, res1=ex(res1), res2=ex(res2), out2=ex(out2),
                  slope2=0.0 if act_copy is None else act_copy, out_scale=out_scale, engine=engine, **kw)
+        if lazy_copy:
+            return out, ops.LazyAct(out, act_copy)      # the consumer conv applies the activation on the fly
         return (out, out2) if act_copy is not None else out
 
     def lrelu(self, x, slope, out=None):

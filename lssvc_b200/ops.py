@@ -100,6 +100,23 @@ class View:
         return out
 
 
+class LazyAct(View):
+    """lrelu(base, slope) that has NOT been written anywhere: the consuming convolution applies the LeakyReLU in its
+    operand path (in_transform).  Handing it to a kernel directly is a wiring error, so c() refuses."""
+
+    __slots__ = ("base", "slope")
+
+    def __init__(self, base, slope):
+        super().__init__(base.buf, base.H, base.W, base.C, base.pitch, base.coff, real=base.real)
+        self.base, self.slope = base, float(slope)
+
+    def c(self):
+        raise RuntimeError("LazyAct view reached a kernel: it must be consumed by Engine.conv (or materialised)")
+
+    def exact(self):
+        raise RuntimeError("LazyAct view reached a kernel: it must be consumed by Engine.conv (or materialised)")
+
+
 def _cv(v):
     return v.c() if v is not None else _NULL_VIEW
 
@@ -281,6 +298,8 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
         Ho, Wo = (out.H // 2, out.W // 2) if pc.pixel_shuffle else (out.H, out.W)
         TRACE.append({"name": TRACE_NAME, "engine": engine if engine != "h2" else impl, "k": pc.kh, "stride": pc.stride, "cin": pc.cin_total,
                       "src_c": list(pc.src_c), "cout": pc.cout, "Ho": Ho, "Wo": Wo, "ps": bool(pc.pixel_shuffle),
+                      "extras": ("r" if res1 is not None else "") + ("s" if res2 is not None else "") + ("o" if out2 is not None else "")
+                                + ("l" if in_transform == _lib.IN_LRELU else "") + ("g" if epi != _lib.EPI_PLAIN else ""),
                       "flops": 2.0 * Ho * Wo * pc.kh * pc.kw * sum(s.real for s in srcs) * pc.cout})
     if engine == "simt":
         _lib.check(lib.lssvc_conv_simt(byref(d), _stream()), "conv_simt")

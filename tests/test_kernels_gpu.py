@@ -85,12 +85,14 @@ def _run_conv_case(case, engine, device, with_extras):
         res = [r1, r2]
         kw = dict(res1=make_view(r1, ops), res2=make_view(r2, ops), out2=ops.View.alloc(Ho * f, Wo * f, c_out, device),
                   slope2=0.2, out_scale=1.5)
+        if with_extras == "res":      # both residuals, no second output (conv_hs: both ride the staging buffers)
+            del kw["out2"], kw["slope2"]
     ops.conv(pc, srcs, out, act=act, engine=engine, **kw)
     torch.cuda.synchronize()
     ref = ref_conv(xs, w, b, stride, pad, act=act, ps=ps, res=res, out_scale=1.5 if with_extras else 1.0)
     got = out.to_nchw()
     err = rel_err(got, ref)
-    if with_extras:
+    if with_extras and "out2" in kw:
         got2 = kw["out2"].to_nchw()
         err = max(err, rel_err(got2, F.leaky_relu(ref, 0.2)))
     return err
@@ -131,7 +133,7 @@ def test_conv_h2(case, extras, cuda_device):
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-@pytest.mark.parametrize("extras", [False, True], ids=["plain", "epilogue"])
+@pytest.mark.parametrize("extras", [False, True, "res"], ids=["plain", "epilogue", "residuals"])
 def test_conv_hs(case, extras, cuda_device):
     """Split-fp16 conv with the activation operand read from shared memory through shifted descriptors (csrc/conv_hs.cu)."""
     err = _run_conv_case(case, "hs", cuda_device, extras)
@@ -148,7 +150,9 @@ def test_conv_hs_large_persistent(cuda_device, mt, monkeypatch):
                          (("big256", [128], [128], 256, 3, 1, 96, 160, True), False),
                          (("big_s2", [64, 8], [64, 8], 96, 3, 2, 192, 320, False), True),
                          (("big_7x7", [32], [32], 64, 7, 1, 128, 256, False), False),
-                         (("big_1x1", [64], [64], 256, 1, 1, 160, 264, False), True)):
+                         (("big_1x1", [64], [64], 256, 1, 1, 160, 264, False), True),
+                         (("big_res", [64], [64], 64, 3, 1, 250, 330, False), "res"),
+                         (("big48_res", [48], [48], 48, 3, 1, 200, 312, False), "res")):
         err = _run_conv_case(case, "hs", cuda_device, extras)
         print(f"conv_hs {case[0]}: rel err {err:.3e}")
         assert err < 5e-6, (case[0], err)

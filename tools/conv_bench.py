@@ -54,6 +54,18 @@ def run(engine, shape, dev, check_rows=64):
     co = cout // 4 if ps else cout
     out = ops.View.alloc(Ho * f, Wo * f, co, dev)
     bufs = [[ops.View(torch.randn(H * W * c, device=dev), H, W, c, c) for c in cins] for _ in range(3)]
+    extras = os.environ.get("CONV_BENCH_EXTRAS", "")      # any of: r (res1), s (res2), o (out2), l (input LeakyReLU): timing only
+    kw = {}
+    if extras:
+        mk = lambda: ops.View(torch.randn(Ho * f * Wo * f * co, device=dev), Ho * f, Wo * f, co, co)
+        if "r" in extras:
+            kw["res1"] = mk()
+        if "s" in extras:
+            kw["res2"] = mk()
+        if "o" in extras:
+            kw["out2"], kw["slope2"] = mk(), 0.01
+        if "l" in extras:
+            kw["in_transform"], kw["in_slope"] = _lib.IN_LRELU, 0.01
     # ---- accuracy on the top rows (fp64 reference)
     ops.conv(pc, bufs[0], out, act=0.01, engine=engine)
     torch.cuda.synchronize()
@@ -67,13 +79,13 @@ def run(engine, shape, dev, check_rows=64):
     err = ((got - ref[:, :, :rows_out]).abs().max() / ref.abs().max()).item()
     # ---- time
     for i in range(3):
-        ops.conv(pc, bufs[i], out, act=0.01, engine=engine)
+        ops.conv(pc, bufs[i], out, act=0.01, engine=engine, **kw)
     torch.cuda.synchronize()
     n = 12
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(n):
-        ops.conv(pc, bufs[i % 3], out, act=0.01, engine=engine)
+        ops.conv(pc, bufs[i % 3], out, act=0.01, engine=engine, **kw)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n

@@ -76,7 +76,7 @@ def main():
     convs = [(i, t) for n, i, t in rows if n == "conv"]
     groups = defaultdict(lambda: [0, 0.0, 0.0])
     for c, t in convs:
-        key = (c["k"], c["stride"], c["cin"], c["cout"], c["Ho"], c["Wo"], c["ps"])
+        key = (c["k"], c["stride"], c["cin"], c["cout"], c["Ho"], c["Wo"], c["ps"], c.get("extras", ""))
         g = groups[key]
         g[0] += 1
         g[1] += t
@@ -85,9 +85,9 @@ def main():
     print(f"convs: {len(convs)} launches, {ctot:.2f} ms, {sum(c['flops'] for c, _ in convs) / ctot / 1e9:.1f} TFLOP/s")
     print(f"{'k':>2s} {'s':>1s} {'cin':>4s} {'cout':>4s} {'Ho':>5s} {'Wo':>5s} ps {'n':>3s} {'ms':>8s} {'share':>6s} {'TF/s':>7s} {'GB/s(min)':>9s}")
     for key, (n, t, fl) in sorted(groups.items(), key=lambda kv: -kv[1][1])[:args.top]:
-        k, s, cin, cout, Ho, Wo, ps = key
-        gb = 4.0 * (Ho * s * Wo * s * cin + Ho * Wo * cout) * n / 1e9
-        print(f"{k:2d} {s:1d} {cin:4d} {cout:4d} {Ho:5d} {Wo:5d} {int(ps):2d} {n:3d} {t:8.3f} {100 * t / ctot:5.1f}% {fl / t / 1e9:7.1f} {gb / t * 1e3:9.0f}")
+        k, s, cin, cout, Ho, Wo, ps, ex = key
+        gb = 4.0 * (Ho * s * Wo * s * cin + Ho * Wo * cout * (1 + sum(ex.count(x) for x in "rso"))) * n / 1e9
+        print(f"{k:2d} {s:1d} {cin:4d} {cout:4d} {Ho:5d} {Wo:5d} {int(ps):2d} {n:3d} {t:8.3f} {100 * t / ctot:5.1f}% {fl / t / 1e9:7.1f} {gb / t * 1e3:9.0f} {ex}")
     mods = defaultdict(lambda: [0, 0.0, 0.0])
     for c, t in convs:
         m = re.sub(r"^base_layer_model\.", "BL.", c["name"] or "?")
