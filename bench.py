@@ -158,8 +158,17 @@ def conv_roofline(torch, device, shape_hr, peaks):
     info = ops.engine_info(engine)
     peak = peaks["bf16_tflops"] * info["peak_vs_bf16"]
     achieved = flops / sec / 1e12
+    # DRAM bytes per launch of this very layer from the committed ncu --set full capture (profiles/), if there is one
+    traffic = None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "conv_roofline_traffic.json")) as f:
+            t = json.load(f)
+        if t.get("kernel") == info["kernel"] and t.get("shape") == [H, W, 64, 64, 3]:
+            traffic = int(t["dram_bytes_read"] + t["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        pass
     return {"bound": "tensor", "kernel": info["kernel"], "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s",
-            "frac": round(achieved / peak, 4), "traffic": None,
+            "frac": round(achieved / peak, 4), "traffic": traffic,
             "note": f"{info['note']}; peak = {info['peak_vs_bf16']} x bf16 dense GEMM peak ({peaks['source']}); "
                     f"3x3 64->64 conv at {H}x{W}, {flops / 1e9:.1f} GFLOP (algorithmic) per launch, {sec * 1e3:.3f} ms per launch"}
 

@@ -210,9 +210,10 @@ ENGINES = {
            "note": "tcgen05.mma kind::tf32, fp32 accumulate in TMEM"},
     "tc3": {"kernel": "conv_tc_kernel(3xTF32)", "dtype": "tf32x3", "peak_vs_bf16": 0.5,
             "note": "tcgen05.mma kind::tf32 error-compensated 3xTF32 (3 MMAs per algorithmic MAC); FLOPs counted are algorithmic"},
-    "h2": {"kernel": "conv_h2_kernel", "dtype": "f16x2-split", "peak_vs_bf16": 1.0,
-           "note": "tcgen05.mma kind::f16 on split-fp16 operands (x = x_hi + x_lo; 3 MMAs per algorithmic MAC, A operand in "
-                   "TMEM, hi*hi and cross terms in separate fp32 accumulators); FLOPs counted are algorithmic"},
+    "h2": {"kernel": "conv_hs_kernel", "dtype": "f16x2-split", "peak_vs_bf16": 1.0,
+           "note": "tcgen05.mma kind::f16 on split-fp16 operands (x = x_hi + x_lo; 3 MMAs per algorithmic MAC, both operands "
+                   "read from shared memory, taps = shifted descriptors on one converted halo tile, hi*hi and cross terms in "
+                   "separate fp32 TMEM accumulators); FLOPs counted are algorithmic, so the kernel's own ceiling is peak/3"},
 }
 _ENGINE = os.environ.get("LSSVC_CONV_ENGINE", "h2")
 assert _ENGINE in ENGINES, _ENGINE
@@ -235,7 +236,12 @@ def set_engine(name):
 
 
 def engine_info(name):
-    return ENGINES[name]
+    info = dict(ENGINES[name])
+    if name == "h2" and _H2_IMPL == "h2t":
+        info["kernel"] = "conv_h2_kernel"
+        info["note"] = info["note"].replace("both operands read from shared memory, taps = shifted descriptors on one converted halo tile",
+                                            "A operand staged in TMEM per tap")
+    return info
 
 
 def force_simt(flag):
