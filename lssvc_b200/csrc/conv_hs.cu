@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
                     if (!DBG || !(dbgf & 1))
                       ptx::mma_f16_ss2(d1, a16, a_hi_word, b16_tap + ks * 2, b_hi_word, (DBG && (dbgf & 256)) ? idesc_n : idesc_2n, acc);
                     if (!DBG || !(dbgf & 2))
-                      ptx::mma_f16_ss2(d1 + n_tile, (DBG && (dbgf & 512)) ? a16 : a16 + LO16, a_hi_word, b16_tap + ks * 2, b_hi_word,
+                      ptx::mma_f16_ss2((DBG && (dbgf & 4096)) ? ((d1 + n_tile + 256u) & 0xffff01ffu) : d1 + n_tile,
+                                       (DBG && (dbgf & 512)) ? a16 : a16 + LO16, a_hi_word, b16_tap + ks * 2, b_hi_word,
                                        (DBG && (dbgf & 1024)) ? idesc_2n : idesc_n, 1u);
                   }
                   acc = 1u;

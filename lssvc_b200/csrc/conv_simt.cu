@@ -178,6 +178,49 @@ __global__ void dwconv3x3_kernel(const float *__restrict__ in, int in_pitch, con
   *reinterpret_cast<float4 *>(out + pix * out_pitch + c) = acc;
 }
 
+// same, two horizontally adjacent output pixels per thread: the 3 x 4 input window is loaded once (12 float4 loads, all
+// in flight, for 2 outputs instead of 18) — the kernel is HBM/L2-bound, so bytes in flight per thread are what count
+__global__ void __launch_bounds__(256) dwconv3x3_x2_kernel(const float *__restrict__ in, uint32_t in_pitch,
+                                                           const float *__restrict__ w, const float *__restrict__ bias,
+                                                           float *__restrict__ out, uint32_t out_pitch, int H, int W, int C,
+                                                           uint32_t total) {
+  const uint32_t c4 = static_cast<uint32_t>(C) >> 2, W2 = static_cast<uint32_t>(W + 1) >> 1;
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const uint32_t pp = idx / c4, c = (idx - pp * c4) * 4;
+  const int y = static_cast<int>(pp / W2), x0 = static_cast<int>(pp - static_cast<uint32_t>(y) * W2) * 2;
+  float4 v[3][4];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = y + r - 1;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int ix = x0 + s - 1;
+      v[r][s] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                    ? __ldg(reinterpret_cast<const float4 *>(in + (static_cast<size_t>(iy) * W + ix) * in_pitch + c))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + c));
+  float4 a0 = b, a1 = b;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const float4 k = __ldg(reinterpret_cast<const float4 *>(w + (r * 3 + s) * C + c));
+      // the taps of out-of-image pixels are skipped in the one-pixel kernel; here they multiply an exact zero (same sum:
+      // fmaf(0, k, acc) == acc), so both kernels produce identical results
+      a0.x = fmaf(v[r][s].x, k.x, a0.x); a0.y = fmaf(v[r][s].y, k.y, a0.y);
+      a0.z = fmaf(v[r][s].z, k.z, a0.z); a0.w = fmaf(v[r][s].w, k.w, a0.w);
+      a1.x = fmaf(v[r][s + 1].x, k.x, a1.x); a1.y = fmaf(v[r][s + 1].y, k.y, a1.y);
+      a1.z = fmaf(v[r][s + 1].z, k.z, a1.z); a1.w = fmaf(v[r][s + 1].w, k.w, a1.w);
+    }
+  }
+  float *o = out + (static_cast<size_t>(y) * W + x0) * out_pitch + c;
+  *reinterpret_cast<float4 *>(o) = a0;
+  if (x0 + 1 < W) *reinterpret_cast<float4 *>(o + out_pitch) = a1;
+}
+
 // ConvTranspose2d(k=3, s=2, p=1, output_padding=1): out[oy, ox] gathers in[(oy + 1 - ky) / 2, ...] where
 // (oy + 1 - ky) is even.  weight [9][cin][cout].  One block = 32 output pixels x 32 output channels.
 __global__ void __launch_bounds__(256) deconv3x3_s2_kernel(const float *__restrict__ in, int in_pitch, int Hi, int Wi,
@@ -280,6 +323,16 @@ extern "C" int32_t lssvc_dwconv3x3(const lssvc_view *in, const float *weight, co
   LSSVC_REQUIRE(in->H == out->H && in->W == out->W && in->C == out->C, "dwconv3x3: shape mismatch");
   LSSVC_REQUIRE(in->C % 4 == 0 && in->pitch % 4 == 0 && out->pitch % 4 == 0, "dwconv3x3: channels must be 4-aligned");
   const long long total = static_cast<long long>(in->H) * in->W * (in->C / 4);
+  const int pitch_max = in->pitch > out->pitch ? in->pitch : out->pitch;
+  if (static_cast<long long>(in->H) * in->W * pitch_max < (1LL << 31) && (reinterpret_cast<uintptr_t>(in->ptr) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out->ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(bias) & 15) == 0) {
+    const uint32_t tot2 = static_cast<uint32_t>(in->H) * static_cast<uint32_t>((in->W + 1) / 2) * static_cast<uint32_t>(in->C / 4);
+    dwconv3x3_x2_kernel<<<(tot2 + 255) / 256, 256, 0, lssvc::as_stream(stream)>>>(in->ptr, in->pitch, weight, bias, out->ptr,
+                                                                                 out->pitch, in->H, in->W, in->C, tot2);
+    LSSVC_LAUNCHED();
+    return LSSVC_OK;
+  }
   const int blocks = static_cast<int>((total + 255) / 256);
   dwconv3x3_kernel<<<blocks, 256, 0, lssvc::as_stream(stream)>>>(in->ptr, in->pitch, weight, bias, out->ptr, out->pitch,
                                                                 in->H, in->W, in->C);

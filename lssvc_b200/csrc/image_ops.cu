@@ -74,6 +74,66 @@ __global__ void softmax2_blend_kernel(const float *__restrict__ logits, int l_pi
   out[pix * o_pitch + c] = a[pix * a_pitch + c] * (e0 * inv) + b[pix * b_pitch + c] * (e1 * inv);
 }
 
+// ---- 128-bit variants ---------------------------------------------------------------------------------------
+// The streaming kernels below are HBM-bound: each thread moves UNROLL float4 elements that are a whole block apart
+// (coalesced 4 KB per block and step), all loads issued before the first use, 32-bit index arithmetic.
+constexpr int UNROLL = 4;
+
+__global__ void __launch_bounds__(TPB) lrelu_copy4_kernel(const float4 *__restrict__ in, uint32_t ip4, float slope,
+                                                          float4 *__restrict__ out, uint32_t op4, uint32_t cv, uint32_t total) {
+  const uint32_t base = blockIdx.x * (TPB * UNROLL) + threadIdx.x;
+  float4 v[UNROLL];
+  uint32_t o[UNROLL];
+#pragma unroll
+  for (int k = 0; k < UNROLL; ++k) {
+    const uint32_t i = base + k * TPB;
+    if (i < total) {
+      const uint32_t pix = i / cv, c = i - pix * cv;
+      v[k] = __ldg(in + static_cast<size_t>(pix) * ip4 + c);
+      o[k] = pix * op4 + c;   // < 2^32 / 4 elements: checked on the host
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < UNROLL; ++k) {
+    if (base + k * TPB < total)
+      out[o[k]] = make_float4(lrelu(v[k].x, slope), lrelu(v[k].y, slope), lrelu(v[k].z, slope), lrelu(v[k].w, slope));
+  }
+}
+
+__global__ void __launch_bounds__(TPB) softmax2_blend4_kernel(const float *__restrict__ logits, uint32_t l_pitch,
+                                                              const float4 *__restrict__ a, uint32_t ap4,
+                                                              const float4 *__restrict__ b, uint32_t bp4,
+                                                              float4 *__restrict__ out, uint32_t op4, uint32_t cv, uint32_t total) {
+  const uint32_t base = blockIdx.x * (TPB * UNROLL) + threadIdx.x;
+  float4 va[UNROLL], vb[UNROLL];
+  float l0[UNROLL], l1[UNROLL];
+  uint32_t o[UNROLL];
+#pragma unroll
+  for (int k = 0; k < UNROLL; ++k) {
+    const uint32_t i = base + k * TPB;
+    if (i < total) {
+      const uint32_t pix = i / cv, c = i - pix * cv;
+      va[k] = __ldg(a + static_cast<size_t>(pix) * ap4 + c);
+      vb[k] = __ldg(b + static_cast<size_t>(pix) * bp4 + c);
+      l0[k] = __ldg(logits + static_cast<size_t>(pix) * l_pitch);
+      l1[k] = __ldg(logits + static_cast<size_t>(pix) * l_pitch + 1);
+      o[k] = pix * op4 + c;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < UNROLL; ++k) {
+    if (base + k * TPB < total) {
+      // softmax over two logits, computed the way torch does (subtract the max, exp, normalise)
+      const float mx = fmaxf(l0[k], l1[k]);
+      const float e0 = expf(l0[k] - mx), e1 = expf(l1[k] - mx);
+      const float inv = 1.f / (e0 + e1);
+      const float wa = e0 * inv, wb = e1 * inv;
+      out[o[k]] = make_float4(va[k].x * wa + vb[k].x * wb, va[k].y * wa + vb[k].y * wb, va[k].z * wa + vb[k].z * wb,
+                              va[k].w * wa + vb[k].w * wb);
+    }
+  }
+}
+
 // ---- warping -----------------------------------------------------------------------------
 // grid_sample(bilinear, border, align_corners=True) on grid = base + flow / ((W-1)/2): the sample
 // position in pixels is x + fx (up to the fp32 normalise/denormalise round trip the reference does,
@@ -108,6 +168,43 @@ __device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v
   // ATen grid_sampler_2d corner weights: nw = (x_se - ix)(y_se - iy), ne = (ix - x_sw)(y_sw - iy), ...
   const float ex = 1.f - wx, ey = 1.f - wy;
   return v00 * (ex * ey) + v01 * (wx * ey) + v10 * (ex * wy) + v11 * (wx * wy);
+}
+
+// float4 variant: two (pixel, 4-channel) elements per thread, the 8 corner loads in flight together
+__global__ void __launch_bounds__(TPB) flow_warp4_kernel(const float *__restrict__ src, uint32_t s_pitch,
+                                                         const float *__restrict__ flow, uint32_t f_pitch, float fscale,
+                                                         float *__restrict__ out, uint32_t o_pitch, int H, int W, uint32_t cv,
+                                                         uint32_t total) {
+  constexpr int U = 2;
+  const uint32_t base = blockIdx.x * (TPB * U) + threadIdx.x;
+  float4 a[U], b[U], d[U], e[U];
+  float wx[U], wy[U];
+  size_t o[U];
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const uint32_t i = base + k * TPB;
+    if (i < total) {
+      const uint32_t pix = i / cv, c = (i - pix * cv) * 4;
+      const int y = static_cast<int>(pix / static_cast<uint32_t>(W)), x = static_cast<int>(pix - static_cast<uint32_t>(y) * W);
+      const float fx = __ldg(flow + static_cast<size_t>(pix) * f_pitch) * fscale;
+      const float fy = __ldg(flow + static_cast<size_t>(pix) * f_pitch + 1) * fscale;
+      int x0, x1, y0, y1;
+      warp_coords(x, y, fx, fy, W, H, x0, x1, y0, y1, wx[k], wy[k]);
+      const size_t r0 = static_cast<size_t>(y0) * W, r1 = static_cast<size_t>(y1) * W;
+      a[k] = __ldg(reinterpret_cast<const float4 *>(src + (r0 + x0) * s_pitch + c));
+      b[k] = __ldg(reinterpret_cast<const float4 *>(src + (r0 + x1) * s_pitch + c));
+      d[k] = __ldg(reinterpret_cast<const float4 *>(src + (r1 + x0) * s_pitch + c));
+      e[k] = __ldg(reinterpret_cast<const float4 *>(src + (r1 + x1) * s_pitch + c));
+      o[k] = static_cast<size_t>(pix) * o_pitch + c;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    if (base + k * TPB < total)
+      *reinterpret_cast<float4 *>(out + o[k]) =
+          make_float4(bilerp(a[k].x, b[k].x, d[k].x, e[k].x, wx[k], wy[k]), bilerp(a[k].y, b[k].y, d[k].y, e[k].y, wx[k], wy[k]),
+                      bilerp(a[k].z, b[k].z, d[k].z, e[k].z, wx[k], wy[k]), bilerp(a[k].w, b[k].w, d[k].w, e[k].w, wx[k], wy[k]));
+  }
 }
 
 template <int VEC>
@@ -176,6 +273,77 @@ __global__ void bilinear_resize_kernel(const float *__restrict__ in, int i_pitch
   }
 }
 
+// float4 variants (two elements per thread)
+__global__ void __launch_bounds__(TPB) bilinear_resize4_kernel(const float *__restrict__ in, uint32_t i_pitch, int Hi, int Wi,
+                                                               float *__restrict__ out, uint32_t o_pitch, int Wo, uint32_t cv,
+                                                               uint32_t total, float rh, float rw, float mul) {
+  constexpr int U = 2;
+  const uint32_t base = blockIdx.x * (TPB * U) + threadIdx.x;
+  float4 a[U], b[U], d[U], e[U];
+  float wx[U], wy[U];
+  size_t o[U];
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const uint32_t i = base + k * TPB;
+    if (i < total) {
+      const uint32_t pix = i / cv, c = (i - pix * cv) * 4;
+      const int y = static_cast<int>(pix / static_cast<uint32_t>(Wo)), x = static_cast<int>(pix - static_cast<uint32_t>(y) * Wo);
+      int x0, x1, y0, y1;
+      resize_coord(x, rw, Wi, x0, x1, wx[k]);
+      resize_coord(y, rh, Hi, y0, y1, wy[k]);
+      const size_t r0 = static_cast<size_t>(y0) * Wi, r1 = static_cast<size_t>(y1) * Wi;
+      a[k] = __ldg(reinterpret_cast<const float4 *>(in + (r0 + x0) * i_pitch + c));
+      b[k] = __ldg(reinterpret_cast<const float4 *>(in + (r0 + x1) * i_pitch + c));
+      d[k] = __ldg(reinterpret_cast<const float4 *>(in + (r1 + x0) * i_pitch + c));
+      e[k] = __ldg(reinterpret_cast<const float4 *>(in + (r1 + x1) * i_pitch + c));
+      o[k] = static_cast<size_t>(pix) * o_pitch + c;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    if (base + k * TPB < total) {
+      const float hx = 1.f - wx[k], hy = 1.f - wy[k], ax = wx[k], ay = wy[k];
+      // ATen upsample_bilinear2d: h0l * (w0l * v00 + w1l * v01) + h1l * (w0l * v10 + w1l * v11)
+      *reinterpret_cast<float4 *>(out + o[k]) =
+          make_float4((hy * (hx * a[k].x + ax * b[k].x) + ay * (hx * d[k].x + ax * e[k].x)) * mul,
+                      (hy * (hx * a[k].y + ax * b[k].y) + ay * (hx * d[k].y + ax * e[k].y)) * mul,
+                      (hy * (hx * a[k].z + ax * b[k].z) + ay * (hx * d[k].z + ax * e[k].z)) * mul,
+                      (hy * (hx * a[k].w + ax * b[k].w) + ay * (hx * d[k].w + ax * e[k].w)) * mul);
+    }
+  }
+}
+
+template <bool MAX>
+__global__ void __launch_bounds__(TPB) pool2_4_kernel(const float *__restrict__ in, uint32_t i_pitch, int Wi,
+                                                      float *__restrict__ out, uint32_t o_pitch, int Wo, uint32_t cv, uint32_t total) {
+  constexpr int U = 2;
+  const uint32_t base = blockIdx.x * (TPB * U) + threadIdx.x;
+  float4 a[U], b[U], d[U], e[U];
+  size_t o[U];
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const uint32_t i = base + k * TPB;
+    if (i < total) {
+      const uint32_t pix = i / cv, c = (i - pix * cv) * 4;
+      const uint32_t y = pix / static_cast<uint32_t>(Wo), x = pix - y * Wo;
+      const float *p = in + (static_cast<size_t>(2 * y) * Wi + 2 * x) * i_pitch + c;
+      a[k] = __ldg(reinterpret_cast<const float4 *>(p));
+      b[k] = __ldg(reinterpret_cast<const float4 *>(p + i_pitch));
+      d[k] = __ldg(reinterpret_cast<const float4 *>(p + static_cast<size_t>(Wi) * i_pitch));
+      e[k] = __ldg(reinterpret_cast<const float4 *>(p + static_cast<size_t>(Wi) * i_pitch + i_pitch));
+      o[k] = static_cast<size_t>(pix) * o_pitch + c;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    if (base + k * TPB < total) {
+      auto f = [](float p, float q, float r, float t) { return MAX ? fmaxf(fmaxf(p, q), fmaxf(r, t)) : (p + q + r + t) * 0.25f; };
+      *reinterpret_cast<float4 *>(out + o[k]) = make_float4(f(a[k].x, b[k].x, d[k].x, e[k].x), f(a[k].y, b[k].y, d[k].y, e[k].y),
+                                                            f(a[k].z, b[k].z, d[k].z, e[k].z), f(a[k].w, b[k].w, d[k].w, e[k].w));
+    }
+  }
+}
+
 template <bool MAX>
 __global__ void pool2_kernel(const float *__restrict__ in, int i_pitch, int Wi, float *__restrict__ out, int o_pitch,
                              int Ho, int Wo, int C) {
@@ -232,8 +400,8 @@ __global__ void spynet_prep_kernel(const float *__restrict__ im1, int p1, const 
 // channels (2n, 2n+1) of the 2*G*O-channel tensor; mask n is channel n of the mask chunk; warp n acts on
 // x-group (n mod G) ("x.repeat(offset_num)") and its output lands in channels n*cg .. n*cg+cg-1 of the
 // (C*O)-channel tensor, which the grouped 1x1 fusion conv (groups=G, 2*cg inputs per group) consumes.
-template <int CG, int O>
-__global__ void offset_diversity_kernel(const float *__restrict__ xin, int xp, const float *__restrict__ off, int op,
+template <int CG, int O, bool VEC_OFF>
+__global__ void __launch_bounds__(TPB) offset_diversity_kernel(const float *__restrict__ xin, int xp, const float *__restrict__ off, int op,
                                         const float *__restrict__ flow, int fp, const float *__restrict__ fw,
                                         const float *__restrict__ fb, int G, float mag, float *__restrict__ out,
                                         int outp, int H, int W) {
@@ -251,7 +419,28 @@ __global__ void offset_diversity_kernel(const float *__restrict__ xin, int xp, c
   const float hx = 1.f - bwx, hy = 1.f - bwy;
   const float *q00 = off + (static_cast<long long>(by0) * Wc + bx0) * op, *q01 = off + (static_cast<long long>(by0) * Wc + bx1) * op;
   const float *q10 = off + (static_cast<long long>(by1) * Wc + bx0) * op, *q11 = off + (static_cast<long long>(by1) * Wc + bx1) * op;
-  auto up = [&](int ch) { return hy * (hx * q00[ch] + bwx * q01[ch]) + bwy * (hx * q10[ch] + bwx * q11[ch]); };
+  // this thread's 2*O offset channels (2n, 2n+1 for n = g*O .. g*O+O-1) and O mask channels are contiguous: with O == 2
+  // one float4 + one float2 per corner of the x2 upsampling instead of 6 scalar loads
+  float upv[3 * O];
+  if (O == 2 && VEC_OFF) {
+    const float4 a4 = __ldg(reinterpret_cast<const float4 *>(q00 + 4 * g)), b4 = __ldg(reinterpret_cast<const float4 *>(q01 + 4 * g));
+    const float4 d4 = __ldg(reinterpret_cast<const float4 *>(q10 + 4 * g)), e4 = __ldg(reinterpret_cast<const float4 *>(q11 + 4 * g));
+    const float2 a2 = __ldg(reinterpret_cast<const float2 *>(q00 + 2 * n_off + 2 * g)), b2 = __ldg(reinterpret_cast<const float2 *>(q01 + 2 * n_off + 2 * g));
+    const float2 d2 = __ldg(reinterpret_cast<const float2 *>(q10 + 2 * n_off + 2 * g)), e2 = __ldg(reinterpret_cast<const float2 *>(q11 + 2 * n_off + 2 * g));
+    auto up4 = [&](float v00, float v01, float v10, float v11) { return hy * (hx * v00 + bwx * v01) + bwy * (hx * v10 + bwx * v11); };
+    upv[0] = up4(a4.x, b4.x, d4.x, e4.x); upv[1] = up4(a4.y, b4.y, d4.y, e4.y);
+    upv[2] = up4(a4.z, b4.z, d4.z, e4.z); upv[3] = up4(a4.w, b4.w, d4.w, e4.w);
+    upv[4] = up4(a2.x, b2.x, d2.x, e2.x); upv[5] = up4(a2.y, b2.y, d2.y, e2.y);
+  } else {
+    auto up1 = [&](int ch) { return hy * (hx * q00[ch] + bwx * q01[ch]) + bwy * (hx * q10[ch] + bwx * q11[ch]); };
+#pragma unroll
+    for (int t = 0; t < O; ++t) {
+      upv[2 * t] = up1(2 * (g * O + t));
+      upv[2 * t + 1] = up1(2 * (g * O + t) + 1);
+      upv[2 * O + t] = up1(2 * n_off + g * O + t);
+    }
+  }
+  auto up = [&](int ch) { return ch >= 2 * n_off ? upv[2 * O + (ch - 2 * n_off - g * O)] : upv[ch - 2 * g * O]; };
   const float flx = flow[pix * fp], fly = flow[pix * fp + 1];
 
   // fusion group g consumes channels [g*2cg, (g+1)*2cg) of the warped tensor, i.e. warps
@@ -305,6 +494,12 @@ __global__ void sse_kernel(const float *__restrict__ a, int ap, const float *__r
   }
 }
 
+// 32-bit element indexing is safe: pixels * pitch below 2^31 for both pitches
+bool fits32(long long pixels, int pitch_a, int pitch_b) {
+  const long long m = pitch_a > pitch_b ? pitch_a : pitch_b;
+  return pixels * m < (1LL << 31);
+}
+
 bool aligned4(const lssvc_view *v) { return v->C % 4 == 0 && v->pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0; }
 
 }  // namespace
@@ -331,6 +526,13 @@ extern "C" int32_t lssvc_lrelu_copy(const lssvc_view *in, float slope, const lss
   LSSVC_REQUIRE(lssvc::view_ok(in) && lssvc::view_ok(out), "lrelu_copy: bad view");
   LSSVC_REQUIRE(in->H == out->H && in->W == out->W && in->C == out->C, "lrelu_copy: shape mismatch");
   const long long pixels = static_cast<long long>(in->H) * in->W;
+  if (aligned4(in) && aligned4(out) && fits32(pixels, in->pitch, out->pitch)) {
+    const uint32_t cv = in->C / 4, total = static_cast<uint32_t>(pixels) * cv;
+    lrelu_copy4_kernel<<<(total + TPB * UNROLL - 1) / (TPB * UNROLL), TPB, 0, lssvc::as_stream(stream)>>>(
+        reinterpret_cast<const float4 *>(in->ptr), in->pitch / 4, slope, reinterpret_cast<float4 *>(out->ptr), out->pitch / 4, cv, total);
+    LSSVC_LAUNCHED();
+    return LSSVC_OK;
+  }
   lrelu_copy_kernel<<<blocks_for(pixels * in->C), TPB, 0, lssvc::as_stream(stream)>>>(in->ptr, in->pitch, slope, out->ptr,
                                                                                        out->pitch, in->C, pixels);
   LSSVC_LAUNCHED();
@@ -346,6 +548,14 @@ extern "C" int32_t lssvc_softmax2_blend(const lssvc_view *logits, const lssvc_vi
                     logits->W == out->W,
                 "softmax2_blend: size mismatch");
   const long long pixels = static_cast<long long>(out->H) * out->W;
+  if (aligned4(a) && aligned4(b) && aligned4(out) && fits32(pixels, a->pitch, out->pitch) && fits32(pixels, b->pitch, logits->pitch)) {
+    const uint32_t cv = out->C / 4, total = static_cast<uint32_t>(pixels) * cv;
+    softmax2_blend4_kernel<<<(total + TPB * UNROLL - 1) / (TPB * UNROLL), TPB, 0, lssvc::as_stream(stream)>>>(
+        logits->ptr, logits->pitch, reinterpret_cast<const float4 *>(a->ptr), a->pitch / 4, reinterpret_cast<const float4 *>(b->ptr),
+        b->pitch / 4, reinterpret_cast<float4 *>(out->ptr), out->pitch / 4, cv, total);
+    LSSVC_LAUNCHED();
+    return LSSVC_OK;
+  }
   softmax2_blend_kernel<<<blocks_for(pixels * out->C), TPB, 0, lssvc::as_stream(stream)>>>(
       logits->ptr, logits->pitch, a->ptr, a->pitch, b->ptr, b->pitch, out->ptr, out->pitch, out->C, pixels);
   LSSVC_LAUNCHED();
@@ -360,7 +570,11 @@ extern "C" int32_t lssvc_flow_warp(const lssvc_view *src, const lssvc_view *flow
                 "flow_warp: shape mismatch");
   const long long pixels = static_cast<long long>(out->H) * out->W;
   cudaStream_t s = lssvc::as_stream(stream);
-  if (aligned4(src) && aligned4(out)) {
+  if (aligned4(src) && aligned4(out) && fits32(pixels, src->pitch, out->pitch)) {
+    const uint32_t cv = src->C / 4, total = static_cast<uint32_t>(pixels) * cv;
+    flow_warp4_kernel<<<(total + TPB * 2 - 1) / (TPB * 2), TPB, 0, s>>>(src->ptr, src->pitch, flow->ptr, flow->pitch, flow_scale,
+                                                                       out->ptr, out->pitch, out->H, out->W, cv, total);
+  } else if (aligned4(src) && aligned4(out)) {
     flow_warp_kernel<4><<<blocks_for(pixels * (src->C / 4)), TPB, 0, s>>>(src->ptr, src->pitch, flow->ptr, flow->pitch,
                                                                          flow_scale, out->ptr, out->pitch, out->H, out->W,
                                                                          src->C);
@@ -378,7 +592,11 @@ extern "C" int32_t lssvc_bilinear_resize(const lssvc_view *in, float scale, cons
   const float rw = static_cast<float>(in->W) / static_cast<float>(out->W);
   const long long pixels = static_cast<long long>(out->H) * out->W;
   cudaStream_t s = lssvc::as_stream(stream);
-  if (aligned4(in) && aligned4(out)) {
+  if (aligned4(in) && aligned4(out) && fits32(pixels, in->pitch, out->pitch)) {
+    const uint32_t cv = in->C / 4, total = static_cast<uint32_t>(pixels) * cv;
+    bilinear_resize4_kernel<<<(total + TPB * 2 - 1) / (TPB * 2), TPB, 0, s>>>(in->ptr, in->pitch, in->H, in->W, out->ptr, out->pitch,
+                                                                             out->W, cv, total, rh, rw, scale);
+  } else if (aligned4(in) && aligned4(out)) {
     bilinear_resize_kernel<4><<<blocks_for(pixels * (in->C / 4)), TPB, 0, s>>>(in->ptr, in->pitch, in->H, in->W, out->ptr,
                                                                               out->pitch, out->H, out->W, in->C, rh, rw, scale);
   } else {
@@ -394,6 +612,14 @@ static int32_t pool2(const lssvc_view *in, const lssvc_view *out, void *stream, 
   LSSVC_REQUIRE(out->H == in->H / 2 && out->W == in->W / 2, "pool2: output must be half the input");
   const long long total = static_cast<long long>(out->H) * out->W * out->C;
   cudaStream_t s = lssvc::as_stream(stream);
+  if (aligned4(in) && aligned4(out) && fits32(static_cast<long long>(in->H) * in->W, in->pitch, out->pitch)) {
+    const uint32_t cv = out->C / 4, tot = static_cast<uint32_t>(out->H) * out->W * cv;
+    const int blocks = static_cast<int>((tot + TPB * 2 - 1) / (TPB * 2));
+    if (is_max) pool2_4_kernel<true><<<blocks, TPB, 0, s>>>(in->ptr, in->pitch, in->W, out->ptr, out->pitch, out->W, cv, tot);
+    else pool2_4_kernel<false><<<blocks, TPB, 0, s>>>(in->ptr, in->pitch, in->W, out->ptr, out->pitch, out->W, cv, tot);
+    LSSVC_LAUNCHED();
+    return LSSVC_OK;
+  }
   if (is_max) pool2_kernel<true><<<blocks_for(total), TPB, 0, s>>>(in->ptr, in->pitch, in->W, out->ptr, out->pitch, out->H, out->W, out->C);
   else pool2_kernel<false><<<blocks_for(total), TPB, 0, s>>>(in->ptr, in->pitch, in->W, out->ptr, out->pitch, out->H, out->W, out->C);
   LSSVC_LAUNCHED();
@@ -437,9 +663,15 @@ extern "C" int32_t lssvc_offset_diversity(const lssvc_view *x, const lssvc_view 
   LSSVC_REQUIRE(flow->C >= 2 && flow->H == x->H && flow->W == x->W && out->H == x->H && out->W == x->W && out->C == x->C,
                 "offset_diversity: size mismatch");
   const long long total = static_cast<long long>(x->H) * x->W * groups;
-  offset_diversity_kernel<3, 2><<<blocks_for(total), TPB, 0, lssvc::as_stream(stream)>>>(
-      x->ptr, x->pitch, off->ptr, off->pitch, flow->ptr, flow->pitch, fusion_w, fusion_b, groups, magnitude, out->ptr,
-      out->pitch, x->H, x->W);
+  const bool vec_off = off->pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(off->ptr) & 15) == 0;
+  if (vec_off)
+    offset_diversity_kernel<3, 2, true><<<blocks_for(total), TPB, 0, lssvc::as_stream(stream)>>>(
+        x->ptr, x->pitch, off->ptr, off->pitch, flow->ptr, flow->pitch, fusion_w, fusion_b, groups, magnitude, out->ptr,
+        out->pitch, x->H, x->W);
+  else
+    offset_diversity_kernel<3, 2, false><<<blocks_for(total), TPB, 0, lssvc::as_stream(stream)>>>(
+        x->ptr, x->pitch, off->ptr, off->pitch, flow->ptr, flow->pitch, fusion_w, fusion_b, groups, magnitude, out->ptr,
+        out->pitch, x->H, x->W);
   LSSVC_LAUNCHED();
   return LSSVC_OK;
 }

@@ -386,6 +386,9 @@ def ffn(pf, x, out, slope1=0.1, slope2=0.1, res2=None):
     d.hidden = pf.hidden
     d.w1, d.w2, d.b1, d.b2 = pf.w1.data_ptr(), pf.w2.data_ptr(), pf.b1.data_ptr(), pf.b2.data_ptr()
     d.scale1, d.scale2, d.slope1, d.slope2 = pf.scale1, pf.scale2, float(slope1), float(slope2)
+    if TRACE is not None:
+        TRACE.append({"name": TRACE_NAME, "engine": "ffn", "k": 1, "stride": 1, "cin": pf.C, "src_c": [pf.C], "cout": pf.C,
+                      "hidden": pf.hidden, "Ho": out.H, "Wo": out.W, "ps": False, "flops": 4.0 * out.H * out.W * pf.C * pf.hidden})
     lib = _lib.load()
     _lib.check(lib.lssvc_conv_ffn(byref(d), _stream()), "conv_ffn")
     return out

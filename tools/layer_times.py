@@ -44,7 +44,7 @@ def main():
             e0.record()
             r = fn(*a, **k)
             e1.record()
-            info = ops.TRACE[-1] if (name == "conv" and len(ops.TRACE) > n_before) else None
+            info = ops.TRACE[-1] if (name in ("conv", "pw", "ffn") and len(ops.TRACE) > n_before) else None
             records.append((name, info, e0, e1))
             return r
         return inner
@@ -73,6 +73,16 @@ def main():
         fam[key][1] += t
     for k, (n, t) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
         print(f"  {k:24s} {n:4d} {t:8.3f} ms {100 * t / tsum:5.1f}%")
+    for fam_name in ("pw", "ffn"):
+        g2 = defaultdict(lambda: [0, 0.0])
+        for n, i, t in rows:
+            if n == fam_name and i is not None:
+                k = (i["cin"], i["cout"], i["Ho"], i["Wo"], i.get("dw", False), i.get("hidden", 0))
+                g2[k][0] += 1
+                g2[k][1] += t
+        for (cin, cout, Ho, Wo, dw, hidden), (n, t) in sorted(g2.items(), key=lambda kv: -kv[1][1]):
+            gb = 4.0 * Ho * Wo * (cin + cout) * n / 1e9
+            print(f"  {fam_name:4s} {cin:4d}->{cout:4d} hidden {hidden:4d} dw={int(dw)} {Ho:5d}x{Wo:<5d} n={n:3d} {t:8.3f} ms  {gb / t * 1e3:6.0f} GB/s(min, in+out once)")
     convs = [(i, t) for n, i, t in rows if n == "conv"]
     groups = defaultdict(lambda: [0, 0.0, 0.0])
     for c, t in convs:
