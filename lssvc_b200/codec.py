@@ -1,0 +1,232 @@
+"""Real bitstream coding of P-frames: compress / decompress of the base layer (DMCExtend.compress / decompress,
+dmc_net_extend.py:55-147) and of the enhancement layer (LSSVC_extend.compress / decompress / decompress_four_part_prior,
+LSSVC_net_extend.py:24-142, 200-263), on the CUDA kernels.
+
+The encoder is the forward pass with the symbol / CDF-index dumps switched on (one pass, no host round trip before the
+end), then the host rANS coder.  The decoder is a genuine decoder: it only sees the string and the DPB; synthesis
+networks run on the GPU, and at every point where the reference calls `decode_stream` the CDF indices of the scales just
+computed go to the host (int32, NCHW order), the rANS decoder returns the symbols, and they come back as an NHWC view
+(`symbols_to_view`, `four_part_dec_step`).  Same kernels, same order => the decoder's reconstruction is bit-identical
+to the encoder's (tests/test_parity_gpu.py::test_bitstream_round_trip).
+
+Stream order per layer (one string, one flush): BL [mv_z | mv_y | z | y], EL [mv_z | mv_y | z | y_w0 | y_w1 | y_w2 | y_w3].
+"""
+import numpy as np
+import torch
+
+from . import entropy, ops, stream
+from .ops import View
+
+
+class _Dump:
+    """model._write hook: int32 device buffers for symbols / CDF indices (NCHW order) next to the NHWC outputs."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+        self.shapes = {}
+
+    def buf(self, name, view, C=None):
+        C = view.real if C is None else C
+        t = torch.empty(C * view.H * view.W, dtype=torch.int32, device=self.device)
+        self.bufs[name] = t
+        self.shapes[name] = (C, view.H, view.W)
+        return t
+
+    def host(self, name):
+        return self.bufs[name].cpu().numpy()
+
+    def channel_index(self, name):
+        C, H, W = self.shapes[name]
+        return _channel_index(C, H, W)
+
+
+def _channel_index(C, H, W):
+    """BitEstimator.build_indexes (video_entropy_models.py:225-230): the CDF row is the channel."""
+    return np.repeat(np.arange(C, dtype=np.int32), H * W)
+
+
+def _encode(parts):
+    enc = entropy.RansEncoder()
+    for sym, idx, table in parts:
+        enc.encode_with_indexes(sym, idx, table)
+    return enc.flush()
+
+
+def _bits_scratch(model):
+    from .models import _Bits
+    return _Bits(model.device)
+
+
+def _to_view(model, t, image=False):
+    """NCHW tensor (or an NHWC View handed over natively) -> NHWC view."""
+    if isinstance(t, View) or t is None:
+        return t
+    return model.image_view(t) if image else model.feature_view(t)
+
+
+class _Reader:
+    """Decoder-side glue: rANS decoder + device<->host hops of the symbol / index tensors."""
+
+    def __init__(self, model, string):
+        self.m = model
+        self.dec = entropy.RansDecoder()
+        self.dec.set_stream(string)
+
+    def _view(self, sym, C, H, W, add=None):
+        t = torch.from_numpy(np.ascontiguousarray(sym, dtype=np.int32)).to(self.m.device)
+        out = self.m.new(H, W, C)
+        ops.symbols_to_view(t, None if add is None else add.exact(), out.exact())
+        return out
+
+    def factorized(self, table, H, W):
+        """BitEstimator.decode_stream(size) (video_entropy_models.py:232-241): z_hat = the decoded integers."""
+        C = int(table.cdf.shape[0])
+        return self._view(self.dec.decode_stream(_channel_index(C, H, W), table), C, H, W)
+
+    def laplace(self, params, table):
+        """GaussianEncoder.decode_stream(scales) + means (LSSVC_net_extend.py:120-123): params = (scales | means)."""
+        C = params.real // 2
+        scale, mean = params.slice(0, C), params.slice(C, 2 * C)
+        idx = torch.empty(C * params.H * params.W, dtype=torch.int32, device=self.m.device)
+        ops.scale_index(scale, idx, self.m._thr())
+        sym = self.dec.decode_stream(idx.cpu().numpy(), table)
+        return self._view(sym, C, params.H, params.W, add=mean)
+
+    def four_part(self, common, table):
+        """decompress_four_part_prior (LSSVC_net_extend.py:200-263)."""
+        m = self.m
+        C = common.real // 2
+        y_hat = View.alloc(common.H, common.W, C, m.device, zero=True)
+        n = (C // 4) * common.H * common.W
+        prm = common
+        for step in range(4):
+            idx = torch.empty(n, dtype=torch.int32, device=m.device)
+            ops.four_part_index(prm, step, idx, m._thr())
+            sym = torch.from_numpy(self.dec.decode_stream(idx.cpu().numpy(), table)).to(m.device)
+            ops.four_part_dec_step(sym, prm, step, y_hat)
+            if step < 3:
+                prm = m._spatial_prior(step + 1, y_hat, common)
+        return y_hat
+
+
+# ---- base layer -------------------------------------------------------------------------------------------------
+def bl_compress(model, x, dpb):
+    """DMCExtend.compress(x, dpb) -> {"string", "dpb": {ref_frame_bl, ref_feature_bl, y_hat_bl, mv_hat_bl}}."""
+    model.update()
+    t = model._tables
+    dump = _Dump(model.device)
+    bl = model._base_layer(model.image_view(x), _to_view(model, dpb["ref_frame_bl"], image=True),
+                           _to_view(model, dpb.get("ref_feature_bl")), _bits_scratch(model), dump)
+    h = dump.host
+    string = _encode([(h("bl_mv_z"), dump.channel_index("bl_mv_z"), t["bl_mv_z"]), (h("bl_mv_y"), h("bl_mv_y_idx"), t["laplace"]),
+                      (h("bl_z"), dump.channel_index("bl_z"), t["bl_z"]), (h("bl_y"), h("bl_y_idx"), t["laplace"])])
+    return {"string": string, "dpb": _bl_dpb(bl, clamp=False)}
+
+
+def bl_decompress(model, string, height, width, dpb):
+    """DMCExtend.decompress(string, height, width, dpb): the reconstruction is clamped to [0, 1] (dmc_net_extend.py:138)."""
+    model.update()
+    t = model._tables
+    p = "base_layer_model."
+    rd = _Reader(model, string)
+    ref = _to_view(model, dpb["ref_frame_bl"], image=True)
+    ref_feature = _to_view(model, dpb.get("ref_feature_bl"))
+    zh, zw = stream.get_downsampled_shape(height, width, 64)
+    mv_z_hat = rd.factorized(t["bl_mv_z"], zh, zw)
+    mv_y_hat = rd.laplace(model._bl_mv_params(p, mv_z_hat), t["laplace"])
+    mv_hat = model._bl_mv_decode(p, mv_y_hat)
+    c1, c2, c3 = model._bl_contexts(p, ref, ref_feature, mv_hat)
+    z_hat = rd.factorized(t["bl_z"], zh, zw)
+    y_hat = rd.laplace(model._bl_res_params(p, z_hat, c1, c2, c3), t["laplace"])
+    rec_feat = model._res_decoder_gdn(p + "res_decoder", y_hat, c2, c3, intra=False)
+    feature, recon = model._recon_generation(p + "recon_generation_net", rec_feat, c1)
+    return {"dpb": _bl_dpb({"recon": recon, "feature": feature, "y_hat": y_hat, "mv_hat": mv_hat}, clamp=True)}
+
+
+def _bl_dpb(bl, clamp):
+    rec = bl["recon"].to_nchw()
+    if clamp:
+        rec.clamp_(0, 1)
+    return {"ref_frame_bl": rec, "ref_feature_bl": bl["feature"].to_nchw(), "y_hat_bl": bl["y_hat"].to_nchw(),
+            "mv_hat_bl": bl["mv_hat"].to_nchw()}
+
+
+def bl_encode_decode_extend(model, x, dpb, output_path=None, pic_width=None, pic_height=None):
+    """DMCExtend.encode_decode_extend (dmc_net_extend.py:149-173): compress, write, read back, decompress."""
+    import time
+    torch.cuda.synchronize(model.device)
+    t0 = time.time()
+    encoded = bl_compress(model, x, dpb)
+    stream.encode_p(encoded["string"], output_path)
+    bits = stream.filesize(output_path) * 8
+    torch.cuda.synchronize(model.device)
+    t1 = time.time()
+    decoded = bl_decompress(model, stream.decode_p(output_path), pic_height, pic_width, dpb)
+    torch.cuda.synchronize(model.device)
+    t2 = time.time()
+    return {"dpb": decoded["dpb"], "bit": bits, "encoding_time": t1 - t0, "decoding_time": t2 - t1}
+
+
+# ---- enhancement layer ------------------------------------------------------------------------------------------
+def el_compress(model, x, dpb):
+    """LSSVC_extend.compress(x, dpb): dpb carries the decoded base layer as 'texture', 'y_hat_bl', 'mv_hat_bl'."""
+    model.update()
+    t = model._tables
+    dump = _Dump(model.device)
+    el = model._el_layer(model.image_view(x), _to_view(model, dpb["ref_frame_el"], image=True),
+                         _to_view(model, dpb.get("ref_feature_el")), _to_view(model, dpb["texture"]),
+                         _to_view(model, dpb["y_hat_bl"]), _to_view(model, dpb["mv_hat_bl"]), _bits_scratch(model), dump)
+    h = dump.host
+    parts = [(h("el_mv_z"), dump.channel_index("el_mv_z"), t["el_mv_z"]), (h("el_mv_y"), h("el_mv_y_idx"), t["laplace"]),
+             (h("el_z"), dump.channel_index("el_z"), t["el_z"])]
+    parts += [(h(f"el_y{k}"), h(f"el_y{k}_idx"), t["laplace"]) for k in range(4)]
+    return {"string": _encode(parts),
+            "dpb": {"ref_frame_el": el["recon"].to_nchw(), "ref_feature_el": el["feature"].to_nchw(),
+                    "warp_frame": el["warp_frame"].to_nchw(), "mv_hat": el["mv_hat"].to_nchw()}}
+
+
+def el_decompress(model, string, height, width, dpb):
+    """LSSVC_extend.decompress(string, height, width, dpb) -> {"dpb": {ref_frame_el, ref_feature_el}}."""
+    model.update()
+    t = model._tables
+    rd = _Reader(model, string)
+    ref = _to_view(model, dpb["ref_frame_el"], image=True)
+    ref_feature = _to_view(model, dpb.get("ref_feature_el"))
+    mv_ctx_prior, mv_ctx = model._mv_contexts(_to_view(model, dpb["mv_hat_bl"]))
+    zh, zw = stream.get_downsampled_shape(height, width, 64)
+    mv_z_hat = rd.factorized(t["el_mv_z"], zh, zw)
+    mv_y_hat = rd.laplace(model._mv_params(mv_z_hat, mv_ctx_prior), t["laplace"])
+    mv_hat = model._mv_decode(mv_y_hat, mv_ctx)
+    c1, c2, c3, _ = model._hybrid_contexts(_to_view(model, dpb["texture"]), mv_hat, ref, ref_feature)
+    z_hat = rd.factorized(t["el_z"], zh, zw)
+    params = model._res_params(z_hat, c3, _to_view(model, dpb["y_hat_bl"]))
+    y_hat = rd.four_part(params, t["laplace"])
+    feature, recon = model._res_decode(y_hat, c1, c2, c3)
+    return {"dpb": {"ref_frame_el": recon.to_nchw(), "ref_feature_el": feature.to_nchw()}}
+
+
+def encode_decode_extend(model, x_bl, x_el, dpb, output_path_bl=None, output_path_el=None, pic_width=None, pic_height=None,
+                         pic_width_bl=None, pic_height_bl=None):
+    """LSSVC_extend.encode_decode_extend (LSSVC_net_extend.py:144-191): every layer is compressed, written, read back and
+    DECODED; the DPB of the next frame is the decoder's output, as in the reference."""
+    import time
+    bl = bl_encode_decode_extend(model, x_bl, dpb, output_path_bl, pic_width_bl, pic_height_bl)
+    layer = bl["dpb"]
+    dpb = dict(dpb)
+    dpb["texture"], dpb["y_hat_bl"], dpb["mv_hat_bl"] = layer["ref_feature_bl"], layer["y_hat_bl"], layer["mv_hat_bl"]
+    torch.cuda.synchronize(model.device)
+    t0 = time.time()
+    encoded = el_compress(model, x_el, dpb)
+    stream.encode_p(encoded["string"], output_path_el)
+    bits = stream.filesize(output_path_el) * 8
+    torch.cuda.synchronize(model.device)
+    t1 = time.time()
+    decoded = el_decompress(model, stream.decode_p(output_path_el), pic_height, pic_width, dpb)
+    torch.cuda.synchronize(model.device)
+    t2 = time.time()
+    out = {"ref_frame_bl": layer["ref_frame_bl"], "ref_feature_bl": layer["ref_feature_bl"],
+           "ref_frame_el": decoded["dpb"]["ref_frame_el"], "ref_feature_el": decoded["dpb"]["ref_feature_el"]}
+    return {"dpb": out, "bit_bl": bl["bit"], "bit_el": bits, "encoding_time_EL": t1 - t0, "decoding_time_EL": t2 - t1,
+            "encoding_time_BL": bl["encoding_time"], "decoding_time_BL": bl["decoding_time"],
+            "mv_hat": encoded["dpb"]["mv_hat"], "warp_frame": encoded["dpb"]["warp_frame"]}

@@ -652,8 +652,14 @@ class LSSVC(Engine):
         """The kernel launches of one P-frame on NHWC views (no host synchronisation, no host-side state besides the
         weight caches): what a CUDA graph of the frame captures."""
         bl = self._base_layer(xb, rb, fb, bits, w)
+        el = self._el_layer(xe, re, fe, bl["feature"], bl["y_hat"], bl["mv_hat"], bits, w)
+        return {"bl_recon": bl["recon"], "bl_feature": bl["feature"], "recon": el["recon"], "feature": el["feature"],
+                "mv_hat": el["mv_hat"], "warp_frame": el["warp_frame"]}
+
+    def _el_layer(self, xe, re, fe, texture_bl, y_hat_bl, mv_hat_bl, bits, w):
+        """Enhancement layer of one P-frame given the decoded base layer (LSSVC_net.py:455-508, LSSVC_net_extend.py:24-86)."""
         # EL motion
-        mv_ctx_prior, mv_ctx = self._mv_contexts(bl["mv_hat"])
+        mv_ctx_prior, mv_ctx = self._mv_contexts(mv_hat_bl)
         mv = self.spynet("optic_flow", xe, re)
         mv_y, mv_z = self._mv_encode(mv, mv_ctx)
         mv_z_hat = self.new(mv_z.H, mv_z.W, mv_z.real)
@@ -669,19 +675,18 @@ class LSSVC(Engine):
         _force(self, "mv_y_q", mv_y_hat, mean=mv_prm.slice(C, 2 * C))
         mv_hat = self._mv_decode(mv_y_hat, mv_ctx)
         # contexts, residual coding
-        c1, c2, c3, warp_frame = self._hybrid_contexts(bl["feature"], mv_hat, re, fe)
+        c1, c2, c3, warp_frame = self._hybrid_contexts(texture_bl, mv_hat, re, fe)
         y, z = self._res_encode(xe, c1, c2, c3)
         z_hat = self.new(z.H, z.W, z.real)
         ops.bitparm_quant(z, self._bitparm_coef("bit_estimator_z."), z_hat, bits.ptr(1),
                           sym=w.buf("el_z", z) if w else None)
         _force(self, "z_hat", z_hat)
-        params = self._res_params(z_hat, c3, bl["y_hat"])
+        params = self._res_params(z_hat, c3, y_hat_bl)
         y_hat = self._four_part(y, params, bits, w)
         feature, recon = self._res_decode(y_hat, c1, c2, c3)
         _dbg(self, mv=mv, mv_y=mv_y, mv_y_hat=mv_y_hat, mv_prm=mv_prm, mv_z_hat=mv_z_hat, z_hat=z_hat, y=y, y_hat=y_hat,
              params=params, c1=c1, c2=c2, c3=c3)
-        return {"bl_recon": bl["recon"], "bl_feature": bl["feature"], "recon": recon, "feature": feature, "mv_hat": mv_hat,
-                "warp_frame": warp_frame}
+        return {"recon": recon, "feature": feature, "mv_hat": mv_hat, "warp_frame": warp_frame}
 
     def _frame_result(self, v, bit_bl, bit_el, token=None):
         """Views of one coded frame -> the reference's result dict (fresh NCHW tensors the caller may mutate)."""
@@ -791,6 +796,11 @@ class LSSVC_extend(LSSVC):
 
     def __init__(self, seed=None):
         super().__init__(seed=seed)
+        # the reference's `model.base_layer_model` is a DMCExtend with its own compress / decompress / encode_decode_extend
+        # / update (dmc_net_extend.py:49-173): the parameter container of the same name gets those entry points
+        api = _BaseLayerAPI(self)
+        for name in ("compress", "decompress", "encode_decode_extend", "update"):
+            object.__setattr__(self.base_layer_model, name, getattr(api, name))
 
     def update(self, force=False):
         """LSSVC_extend.update + DMCExtend.update (LSSVC_net_extend.py:17-22, dmc_net_extend.py:49-53)."""
@@ -802,8 +812,61 @@ class LSSVC_extend(LSSVC):
             t[tag] = entropy.bitparm_table(self._bitparm_coef(p).cpu())
         self._tables = t
 
+    # ---- real bitstreams: codec.py -------------------------------------------------------------------------------
+    single_pass_streams = False     # True: one encoder pass + stream verification (streams.py) instead of encode + decode
+
+    @torch.no_grad()
+    def compress(self, x, dpb):
+        """LSSVC_extend.compress(x, dpb) (LSSVC_net_extend.py:24-86): EL of one P-frame -> {"string", "dpb"}."""
+        from . import codec
+        self._require_cuda()
+        return codec.el_compress(self, x, dpb)
+
+    @torch.no_grad()
+    def decompress(self, string, height, width, dpb):
+        """LSSVC_extend.decompress(string, height, width, dpb) (LSSVC_net_extend.py:88-142)."""
+        from . import codec
+        self._require_cuda()
+        return codec.el_decompress(self, string, height, width, dpb)
+
+    @torch.no_grad()
     def encode_decode_extend(self, x_bl, x_el, dpb, output_path_bl=None, output_path_el=None, pic_width=None,
                              pic_height=None, pic_width_bl=None, pic_height_bl=None):
-        from .streams import inter_encode_decode
-        return inter_encode_decode(self, x_bl, x_el, dpb, output_path_bl, output_path_el, pic_width, pic_height,
-                                   pic_width_bl, pic_height_bl)
+        """LSSVC_extend.encode_decode_extend (LSSVC_net_extend.py:144-191): per layer compress -> file -> decompress; the
+        next frame's DPB is what the DECODER reconstructed."""
+        self._require_cuda()
+        if self.single_pass_streams:
+            from .streams import inter_encode_decode
+            return inter_encode_decode(self, x_bl, x_el, dpb, output_path_bl, output_path_el, pic_width, pic_height,
+                                       pic_width_bl, pic_height_bl)
+        from . import codec
+        return codec.encode_decode_extend(self, x_bl, x_el, dpb, output_path_bl, output_path_el, pic_width, pic_height,
+                                          pic_width_bl, pic_height_bl)
+
+
+class _BaseLayerAPI:
+    """DMCExtend's public calls (dmc_net_extend.py:49-173) bound to an LSSVC model."""
+
+    def __init__(self, model):
+        self._m = model
+
+    def update(self, force=False):
+        self._m.update(force=force)
+
+    @torch.no_grad()
+    def compress(self, x, dpb):
+        from . import codec
+        self._m._require_cuda()
+        return codec.bl_compress(self._m, x, dpb)
+
+    @torch.no_grad()
+    def decompress(self, string, height, width, dpb):
+        from . import codec
+        self._m._require_cuda()
+        return codec.bl_decompress(self._m, string, height, width, dpb)
+
+    @torch.no_grad()
+    def encode_decode_extend(self, x, dpb, output_path=None, pic_width=None, pic_height=None):
+        from . import codec
+        self._m._require_cuda()
+        return codec.bl_encode_decode_extend(self._m, x, dpb, output_path, pic_width, pic_height)

@@ -287,3 +287,53 @@ def test_cuda_graph_frames_match_eager(cuda_device):
             assert torch.equal(a, b), f"P-frame {i + 1}: graph replay differs from eager"
     # a stale DPB (the graph has been replayed since) must not be read through its native views
     print("graph replay == eager over", len(eager), "P-frames; bits", [round(g[1]) for g in graphed])
+
+
+def test_bitstream_round_trip(setup, tmp_path):
+    """compress -> string -> decompress for both layers of a P-frame through the reference's stream-mode entry points
+    (DMCExtend.compress/decompress via model.base_layer_model, LSSVC_extend.compress/decompress): the decoder sees only
+    the string and the DPB and must rebuild exactly what the encoder reconstructed (bit-identical tensors), as a real
+    codec has to.  encode_decode_extend (compress -> file -> decompress) must then agree with the single-pass
+    encoder + stream verification of streams.py byte for byte."""
+    s = setup
+    dev = s["dev"]
+    net_i, net_p = s["net_i"], s["net_p"]
+    x_bl, x_el = (t.to(dev) for t in s["frames"][0])
+    est = net_i.encode_decode(x_bl, x_el, None, None, H // 2, W // 2, H, W)
+    dpb = {"ref_frame_bl": est["x_hat_bl"].clamp(0, 1), "ref_frame_el": est["x_hat_el"].clamp(0, 1), "ref_feature_bl": None,
+           "ref_feature_el": est["feature_el"]}
+    net_p.update(force=True)
+    for frame in (1, 2):            # P after I (no BL feature, 64-ch EL feature), then P after P
+        x_bl, x_el = (t.to(dev) for t in s["frames"][frame])
+        enc_bl = net_p.base_layer_model.compress(x_bl, dpb)
+        assert isinstance(enc_bl["string"], (bytes, bytearray)) and len(enc_bl["string"]) > 16
+        dec_bl = net_p.base_layer_model.decompress(enc_bl["string"], H // 2, W // 2, dpb)
+        for k in ("ref_feature_bl", "y_hat_bl", "mv_hat_bl"):
+            assert torch.equal(dec_bl["dpb"][k], enc_bl["dpb"][k]), f"frame {frame}: BL decoder differs from the encoder in {k}"
+        assert torch.equal(dec_bl["dpb"]["ref_frame_bl"], enc_bl["dpb"]["ref_frame_bl"].clamp(0, 1))
+        el_dpb = dict(dpb)
+        el_dpb["texture"], el_dpb["y_hat_bl"], el_dpb["mv_hat_bl"] = (dec_bl["dpb"][k] for k in ("ref_feature_bl", "y_hat_bl", "mv_hat_bl"))
+        enc_el = net_p.compress(x_el, el_dpb)
+        dec_el = net_p.decompress(enc_el["string"], H, W, el_dpb)
+        for k in ("ref_frame_el", "ref_feature_el"):
+            assert torch.equal(dec_el["dpb"][k], enc_el["dpb"][k]), f"frame {frame}: EL decoder differs from the encoder in {k}"
+        # the frame loop of test.py through both stream paths: same files, same DPB
+        outs = []
+        for single in (False, True):
+            net_p.single_pass_streams = single
+            tag = "s" if single else "d"
+            r = net_p.encode_decode(x_bl, x_el, dict(dpb), str(tmp_path / f"bl{frame}{tag}.bin"), str(tmp_path / f"el{frame}{tag}.bin"),
+                                    W, H, W // 2, H // 2)
+            outs.append(r)
+        net_p.single_pass_streams = False
+        for layer in ("bl", "el"):
+            a = (tmp_path / f"{layer}{frame}d.bin").read_bytes()
+            b = (tmp_path / f"{layer}{frame}s.bin").read_bytes()
+            assert a == b and len(a) * 8 == outs[0][f"bit_{layer}"], f"frame {frame}: {layer} streams differ between the two paths"
+        assert torch.equal(outs[0]["dpb"]["ref_frame_el"], outs[1]["dpb"]["ref_frame_el"])
+        assert torch.equal(outs[0]["dpb"]["ref_frame_el"], dec_el["dpb"]["ref_frame_el"])
+        print(f"P-frame {frame}: BL {len(enc_bl['string'])} B, EL {len(enc_el['string'])} B; decoder == encoder, "
+              f"decode time BL {outs[0]['decoding_time_BL'] * 1e3:.0f} ms EL {outs[0]['decoding_time_EL'] * 1e3:.0f} ms")
+        dpb = outs[0]["dpb"]
+        dpb["ref_frame_bl"].clamp_(0, 1)
+        dpb["ref_frame_el"].clamp_(0, 1)
