@@ -230,3 +230,139 @@ def encode_decode_extend(model, x_bl, x_el, dpb, output_path_bl=None, output_pat
     return {"dpb": out, "bit_bl": bl["bit"], "bit_el": bits, "encoding_time_EL": t1 - t0, "decoding_time_EL": t2 - t1,
             "encoding_time_BL": bl["encoding_time"], "decoding_time_BL": bl["decoding_time"],
             "mv_hat": encoded["dpb"]["mv_hat"], "warp_frame": encoded["dpb"]["warp_frame"]}
+
+
+# =================================================================================================================
+# I-frames: IntraNoAR (base layer, priors.py:368-452) and IntraSS (IntraSS.py:239-336)
+# =================================================================================================================
+def _thr_img(model):
+    return model.cached("thr_img", lambda: entropy.image_scale_thresholds().to(model.device))
+
+
+def _eb_encode(model, z, prefix, table):
+    """EntropyBottleneck.compress (img_entropy_models.py:286-313 with medians): z view -> (string, z_hat view)."""
+    dump = _Dump(model.device)
+    z_hat = model.new(z.H, z.W, z.real)
+    ops.eb_quant(z, model._eb_coef(prefix), z_hat, None, sym=dump.buf("z", z))
+    return _encode([(dump.host("z"), dump.channel_index("z"), table)]), z_hat
+
+
+def _eb_decode(model, string, prefix, table, H, W):
+    """EntropyBottleneck.decompress(strings, size): z_hat = decoded integers + medians."""
+    C = int(table.cdf.shape[0])
+    dec = entropy.RansDecoder()
+    dec.set_stream(string)
+    sym = dec.decode_stream(_channel_index(C, H, W), table).reshape(C, H * W)
+    med = model._eb_coef(prefix)[:, 58].float().cpu().numpy()
+    z = (sym.astype(np.float32) + med[:, None]).reshape(1, C, H, W)
+    return model.feature_view(torch.from_numpy(z).to(model.device))
+
+
+def _gaussian_encode(model, y, prm, table):
+    """GaussianConditional.compress(y, build_indexes(scales), means) -> (string, y_hat view); prm = (scales | means)."""
+    C = y.real
+    dump = _Dump(model.device)
+    y_hat = model.new(y.H, y.W, C)
+    ops.gaussian_quant(y, prm.slice(C, 2 * C), prm.slice(0, C), y_hat, None, sym=dump.buf("y", y), index=dump.buf("y_idx", y),
+                       thresholds=_thr_img(model))
+    return _encode([(dump.host("y"), dump.host("y_idx"), table)]), y_hat
+
+
+def _gaussian_decode(model, string, prm, table):
+    C = prm.real // 2
+    idx = torch.empty(C * prm.H * prm.W, dtype=torch.int32, device=model.device)
+    ops.scale_index(prm.slice(0, C), idx, _thr_img(model))
+    dec = entropy.RansDecoder()
+    dec.set_stream(string)
+    sym = torch.from_numpy(dec.decode_stream(idx.cpu().numpy(), table)).to(model.device)
+    y_hat = model.new(prm.H, prm.W, C)
+    ops.symbols_to_view(sym, prm.slice(C, 2 * C), y_hat.exact())
+    return y_hat
+
+
+_BL_EB = "base_layer_model.entropy_bottleneck."
+
+
+def intra_bl_get_y_z(model, x):
+    """IntraNoAR.get_y_z(x)."""
+    y, z = model._bl_analysis(model.image_view(x))
+    return y.to_nchw(), z.to_nchw()
+
+
+def intra_bl_compress(model, x, y, z):
+    """IntraNoAR.compress(x, y, z) (priors.py:420-435) -> {"strings": [[y], [z]], "shape"}."""
+    model.update()
+    t = model._tables
+    z_string, z_hat = _eb_encode(model, _to_view(model, z), _BL_EB, t["bl_z"])
+    y_string, _ = _gaussian_encode(model, _to_view(model, y), model._bl_params(z_hat), t["gaussian"])
+    return {"strings": [[y_string], [z_string]], "shape": tuple(z.shape[-2:])}
+
+
+def intra_bl_get_y_hat_recon(model, y, z):
+    """IntraNoAR.get_y_hat_recon(y, z): the encoder-side reconstruction {x_hat, y_hat, z_hat}."""
+    model.update()
+    t = model._tables
+    _, z_hat = _eb_encode(model, _to_view(model, z), _BL_EB, t["bl_z"])
+    _, y_hat = _gaussian_encode(model, _to_view(model, y), model._bl_params(z_hat), t["gaussian"])
+    return {"x_hat": model._bl_synthesis(y_hat).to_nchw(), "y_hat": y_hat.to_nchw(), "z_hat": z_hat.to_nchw()}
+
+
+def intra_bl_decompress(model, strings, shape):
+    """IntraNoAR.decompress(strings, shape) (priors.py:437-452) -> {"x_hat", "y_hat"}."""
+    model.update()
+    t = model._tables
+    z_hat = _eb_decode(model, strings[1][0], _BL_EB, t["bl_z"], int(shape[0]), int(shape[1]))
+    y_hat = _gaussian_decode(model, strings[0][0], model._bl_params(z_hat), t["gaussian"])
+    return {"x_hat": model._bl_synthesis(y_hat).to_nchw(), "y_hat": y_hat.to_nchw()}
+
+
+def intra_get_y_z_ctx(model, x_hat_bl, x_el):
+    """IntraSS.get_y_z_ctx (IntraSS.py:239-243)."""
+    c1, c2, c3 = model._context_mining(model.image_view(x_hat_bl))
+    y, z = model._el_analysis(model.image_view(x_el), c1, c2, c3)
+    return y.to_nchw(), z.to_nchw(), (c1.to_nchw(), c2.to_nchw(), c3.to_nchw())
+
+
+def intra_compress(model, y=None, z=None, ctx3=None, y_hat_bl=None):
+    """IntraSS.compress(y, z, ctx3, y_hat_bl) (IntraSS.py:304-314)."""
+    model.update()
+    t = model._tables
+    z_string, z_hat = _eb_encode(model, _to_view(model, z), "entropy_bottleneck.", t["el_z"])
+    prm = model._el_params(z_hat, _to_view(model, y_hat_bl), _to_view(model, ctx3))
+    y_string, _ = _gaussian_encode(model, _to_view(model, y), prm, t["gaussian"])
+    return {"strings": [[y_string], [z_string]], "shape": tuple(z.shape[-2:])}
+
+
+def intra_decompress(model, strings, DPB_layer, shape):
+    """IntraSS.decompress(strings, DPB_layer, shape) (IntraSS.py:316-336) -> {"x_hat", "feature"}."""
+    model.update()
+    t = model._tables
+    c1, c2, c3 = model._context_mining(model.image_view(DPB_layer["x_hat_bl"]))
+    z_hat = _eb_decode(model, strings[1][0], "entropy_bottleneck.", t["el_z"], int(shape[0]), int(shape[1]))
+    prm = model._el_params(z_hat, _to_view(model, DPB_layer["y_hat_bl"]), c3)
+    y_hat = _gaussian_decode(model, strings[0][0], prm, t["gaussian"])
+    res_hat = model._res_decoder_gdn("g_s", y_hat, c2, c3, intra=True)
+    feature, x_hat = model._recon_generation("recon_net", res_hat, c1)
+    return {"x_hat": x_hat.to_nchw(), "feature": feature.to_nchw()}
+
+
+def intra_encode_decode(model, x_bl, x_el, bin_path_bl, bin_path_el, pic_height_bl, pic_width_bl, pic_height_el, pic_width_el):
+    """IntraSS.encode_decode with bitstreams (IntraSS.py:245-302): encode BL and EL, then decode both from the files; the
+    returned reconstructions are the DECODER's."""
+    # ---- encode
+    y_bl, z_bl = intra_bl_get_y_z(model, x_bl)
+    comp = intra_bl_compress(model, None, y_bl, z_bl)
+    stream.encode_i(pic_height_bl, pic_width_bl, comp["strings"][0][0], comp["strings"][1][0], bin_path_bl)
+    bit_bl = stream.filesize(bin_path_bl) * 8
+    enc = intra_bl_get_y_hat_recon(model, y_bl, z_bl)
+    y_el, z_el, ctx = intra_get_y_z_ctx(model, enc["x_hat"], x_el)
+    comp = intra_compress(model, y=y_el, z=z_el, ctx3=ctx[2], y_hat_bl=enc["y_hat"])
+    stream.encode_i(pic_height_el, pic_width_el, comp["strings"][0][0], comp["strings"][1][0], bin_path_el)
+    bit_el = stream.filesize(bin_path_el) * 8
+    # ---- decode
+    h, w, y_string, z_string = stream.decode_i(bin_path_bl)
+    dec_bl = intra_bl_decompress(model, [[y_string], [z_string]], stream.get_downsampled_shape(h, w, 64))
+    h, w, y_string, z_string = stream.decode_i(bin_path_el)
+    dec = intra_decompress(model, [[y_string], [z_string]], {"x_hat_bl": dec_bl["x_hat"], "y_hat_bl": dec_bl["y_hat"]},
+                           stream.get_downsampled_shape(h, w, 64))
+    return {"bit_bl": bit_bl, "bit_el": bit_el, "x_hat_bl": dec_bl["x_hat"], "x_hat_el": dec["x_hat"], "feature_el": dec["feature"]}

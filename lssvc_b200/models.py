@@ -78,6 +78,11 @@ class IntraSS(Engine):
         super().__init__(intra_ss_spec(channel_BL, channel_N, channel_M), "I", seed=kwargs.pop("seed", None))
         self.N, self.M, self.channel_BL = int(channel_N), int(channel_M), int(channel_BL)
         self._tables = None
+        # the reference's `model.base_layer_model` is an IntraNoAR with get_y_z / compress / decompress / get_y_hat_recon
+        # (priors.py:390-452): the parameter container of the same name gets those entry points
+        api = _IntraBaseLayerAPI(self)
+        for name in ("get_y_z", "compress", "decompress", "get_y_hat_recon", "update"):
+            object.__setattr__(self.base_layer_model, name, getattr(api, name))
         if base_layer_model_path is not None:
             self.load_bl_pretrain(base_layer_model_path)
 
@@ -292,9 +297,36 @@ class IntraSS(Engine):
         """IntraSS.encode_decode (IntraSS.py:245-302)."""
         if bin_path_bl is None:
             return self.forward(x_bl, x_el)
-        from .streams import intra_encode_decode
-        return intra_encode_decode(self, x_bl, x_el, bin_path_bl, bin_path_el, pic_height_bl, pic_width_bl,
-                                   pic_height_el, pic_width_el)
+        self._require_cuda()
+        if self.single_pass_streams:
+            from .streams import intra_encode_decode
+            return intra_encode_decode(self, x_bl, x_el, bin_path_bl, bin_path_el, pic_height_bl, pic_width_bl,
+                                       pic_height_el, pic_width_el)
+        from . import codec
+        with torch.no_grad():
+            return codec.intra_encode_decode(self, x_bl, x_el, bin_path_bl, bin_path_el, pic_height_bl, pic_width_bl,
+                                             pic_height_el, pic_width_el)
+
+    # ---- stream-mode entry points of the reference (IntraSS.py:239-243, 304-336); real coder + decoder in codec.py ----
+    single_pass_streams = False     # True: one forward pass + stream verification (streams.py) instead of encode + decode
+
+    @torch.no_grad()
+    def get_y_z_ctx(self, x_bl, x_el):
+        from . import codec
+        self._require_cuda()
+        return codec.intra_get_y_z_ctx(self, x_bl, x_el)
+
+    @torch.no_grad()
+    def compress(self, y=None, z=None, ctx3=None, y_hat_bl=None):
+        from . import codec
+        self._require_cuda()
+        return codec.intra_compress(self, y=y, z=z, ctx3=ctx3, y_hat_bl=y_hat_bl)
+
+    @torch.no_grad()
+    def decompress(self, strings, DPB_layer, shape):
+        from . import codec
+        self._require_cuda()
+        return codec.intra_decompress(self, strings, DPB_layer, shape)
 
     def update(self, force=False):
         """Build the CDF tables of both layers (IntraSS.py:234-237)."""
@@ -306,6 +338,40 @@ class IntraSS(Engine):
             t[tag] = entropy.eb_table([g(p, f"_matrices.{i}") for i in range(5)], [g(p, f"_biases.{i}") for i in range(5)],
                                       [g(p, f"_factors.{i}") for i in range(4)], g(p, "quantiles"))
         self._tables = t
+
+
+class _IntraBaseLayerAPI:
+    """IntraNoAR's stream-mode calls (priors.py:390-452) bound to an IntraSS model."""
+
+    def __init__(self, model):
+        self._m = model
+
+    def update(self, force=False):
+        self._m.update(force=force)
+
+    @torch.no_grad()
+    def get_y_z(self, x):
+        from . import codec
+        self._m._require_cuda()
+        return codec.intra_bl_get_y_z(self._m, x)
+
+    @torch.no_grad()
+    def compress(self, x, y, z):
+        from . import codec
+        self._m._require_cuda()
+        return codec.intra_bl_compress(self._m, x, y, z)
+
+    @torch.no_grad()
+    def decompress(self, strings, shape):
+        from . import codec
+        self._m._require_cuda()
+        return codec.intra_bl_decompress(self._m, strings, shape)
+
+    @torch.no_grad()
+    def get_y_hat_recon(self, y, z):
+        from . import codec
+        self._m._require_cuda()
+        return codec.intra_bl_get_y_hat_recon(self._m, y, z)
 
 
 # =============================================================================================================

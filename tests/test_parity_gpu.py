@@ -302,6 +302,27 @@ def test_bitstream_round_trip(setup, tmp_path):
     est = net_i.encode_decode(x_bl, x_el, None, None, H // 2, W // 2, H, W)
     dpb = {"ref_frame_bl": est["x_hat_bl"].clamp(0, 1), "ref_frame_el": est["x_hat_el"].clamp(0, 1), "ref_feature_bl": None,
            "ref_feature_el": est["feature_el"]}
+    # ---- I-frame: IntraNoAR / IntraSS stream-mode entry points, decoder against the forward pass
+    net_i.update(force=True)
+    y_bl, z_bl = net_i.base_layer_model.get_y_z(x_bl)
+    comp = net_i.base_layer_model.compress(None, y_bl, z_bl)
+    dec_bl = net_i.base_layer_model.decompress(comp["strings"], comp["shape"])
+    assert torch.equal(dec_bl["x_hat"], est["x_hat_bl"]), "I-frame: BL decoder differs from the forward pass"
+    y_el, z_el, ctx = net_i.get_y_z_ctx(dec_bl["x_hat"], x_el)
+    comp = net_i.compress(y=y_el, z=z_el, ctx3=ctx[2], y_hat_bl=dec_bl["y_hat"])
+    dec_el = net_i.decompress(comp["strings"], {"x_hat_bl": dec_bl["x_hat"], "y_hat_bl": dec_bl["y_hat"]}, comp["shape"])
+    assert torch.equal(dec_el["x_hat"], est["x_hat_el"]) and torch.equal(dec_el["feature"], est["feature_el"]), \
+        "I-frame: EL decoder differs from the forward pass"
+    files = {}
+    for single in (False, True):
+        net_i.single_pass_streams = single
+        tag = "s" if single else "d"
+        r = net_i.encode_decode(x_bl, x_el, str(tmp_path / f"i_bl{tag}.bin"), str(tmp_path / f"i_el{tag}.bin"), H // 2, W // 2, H, W)
+        files[single] = ((tmp_path / f"i_bl{tag}.bin").read_bytes(), (tmp_path / f"i_el{tag}.bin").read_bytes())
+        assert torch.equal(r["x_hat_el"], est["x_hat_el"]) and torch.equal(r["x_hat_bl"], est["x_hat_bl"])
+    net_i.single_pass_streams = False
+    assert files[False] == files[True], "I-frame: the two stream paths write different files"
+    print(f"I-frame: BL {len(files[False][0])} B, EL {len(files[False][1])} B; decoder == forward pass")
     net_p.update(force=True)
     for frame in (1, 2):            # P after I (no BL feature, 64-ch EL feature), then P after P
         x_bl, x_el = (t.to(dev) for t in s["frames"][frame])
