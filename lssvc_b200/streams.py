@@ -7,10 +7,11 @@ NCHW buffers next to their NHWC outputs), then the host rANS coder (csrc/rans.cp
         [mv_z | mv_y | z | y]  (EL: y as the four parts y_w0..y_w3 of the 4-step prior), file = >I length + string
   I-frame, per layer (IntraSS.py:251-274, priors.py:420-435): y-string and z-string, file = >4I (H, W, len y, len z)
 
-Decoder side: the reference re-runs the synthesis networks on the decoded symbols and uses THAT reconstruction for the
-DPB (LSSVC_net_extend.py:168-178); reconstructions of the two paths are identical, so here the
-streams are decoded with the CDF rows of the dumped indices and required to return exactly the coded symbols, and the
-DPB comes from the encoder-side pass.  The GPU-side progressive decoder (decompress_four_part_prior) is SURVEY §8f-1.
+This module is the SINGLE-PASS variant (model.single_pass_streams = True): one encoder pass codes both layers, the streams
+are decoded with the CDF rows of the dumped indices and required to return exactly the coded symbols, and the DPB comes
+from the encoder-side pass.  The default path (codec.py) runs the genuine decoder — synthesis networks on the decoded
+symbols, progressive four-part decode — and takes the DPB from it as the reference does (LSSVC_net_extend.py:168-178);
+both paths write byte-identical files and bit-identical reconstructions (tests/test_parity_gpu.py).
 """
 import time
 
