@@ -135,6 +135,53 @@ __device__ __forceinline__ void transform_row(float4 (&v)[NV], int in_transform,
   }
 }
 
+// Epilogue of one 128-pixel accumulator on the common path (plain epilogue, TMA store, residuals — if any — already in the
+// staging buffers): no per-element branches.  LeakyReLU is max(v, slope * v) (exact for 0 <= slope <= 1; slope = 1 when
+// the layer has no activation), the output scale is always applied (x 1.0 is exact), so the only compile-time variants
+// are the two residual sources.  ~35 instructions per float4 instead of the ~120 of the general path below, which is
+// what bounds the HBM-bound 1x1 layers (the epilogue warps are instruction-latency bound).
+template <bool R1, bool R2>
+__device__ __forceinline__ void epilogue_lean(uint32_t t_row, int n_tile, int n0, int cout, const float *__restrict__ bias,
+                                              float acc_scale, float slope, float out_scale, uint32_t stage, uint32_t stage2,
+                                              uint32_t slab_w, int m) {
+  const uint32_t sswz = (slab_w == 32 ? static_cast<uint32_t>(m & 7) : static_cast<uint32_t>((m >> 1) & 3)) << 4;
+  const uint32_t row_b = static_cast<uint32_t>(m) * (slab_w * 4u);
+  for (int n = 0; n < n_tile; n += 16) {
+    const int cg = n0 + n;
+    if (cg >= cout) break;
+    uint32_t r1[16], r2[16];
+    ptx::tmem_ld16(t_row + static_cast<uint32_t>(n), r1);
+    ptx::tmem_ld16(t_row + static_cast<uint32_t>(n_tile + n), r2);
+    float4 b4v[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) b4v[g] = __ldg(reinterpret_cast<const float4 *>(bias + cg) + g);  // bias is padded to n_pad
+    const uint32_t srow = static_cast<uint32_t>(n / static_cast<int>(slab_w)) * (128u * slab_w * 4u) + row_b;
+    const uint32_t spiece = static_cast<uint32_t>(n % static_cast<int>(slab_w)) << 2;
+    float4 a1[4], a2[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t soff = srow + ((spiece + 16u * g) ^ sswz);
+      if (R1) a1[g] = ptx::lds_f4(stage + soff);
+      if (R2) a2[g] = ptx::lds_f4(stage2 + soff);
+    }
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float v[4];
+      v[0] = (__uint_as_float(r1[4 * g + 0]) + __uint_as_float(r2[4 * g + 0])) * acc_scale + b4v[g].x;
+      v[1] = (__uint_as_float(r1[4 * g + 1]) + __uint_as_float(r2[4 * g + 1])) * acc_scale + b4v[g].y;
+      v[2] = (__uint_as_float(r1[4 * g + 2]) + __uint_as_float(r2[4 * g + 2])) * acc_scale + b4v[g].z;
+      v[3] = (__uint_as_float(r1[4 * g + 3]) + __uint_as_float(r2[4 * g + 3])) * acc_scale + b4v[g].w;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], v[e] * slope) * out_scale;
+      if (R1) { v[0] += a1[g].x; v[1] += a1[g].y; v[2] += a1[g].z; v[3] += a1[g].w; }
+      if (R2) { v[0] += a2[g].x; v[1] += a2[g].y; v[2] += a2[g].z; v[3] += a2[g].w; }
+      const uint32_t soff = srow + ((spiece + 16u * g) ^ sswz);
+      ptx::sts_u4(stage + soff, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+    }
+  }
+}
+
 // DBG = true: the instrumented variant (LSSVC_HS_DBG switches + per-role wait-time counters), never on the product path
 template <int KC, int MT, bool DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_constant__ HsParams p) {
@@ -478,6 +525,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
     // unit's MMAs are still running: the accumulator is then added in place, no global-load latency in the epilogue
     const bool r1_tma = use_tma && (p.res_tma & 1), r2_tma = use_tma && (p.res_tma & 2);
     uint32_t res_ph = 0;
+    // the common case runs the branch-free epilogue_lean: TMA store, plain epilogue, one output, residuals only via staging,
+    // LeakyReLU slope within [0, 1] (max(v, slope v) form)
+    const bool lean = use_tma && epi == LSSVC_EPI_PLAIN && out2 == nullptr && (res1 == nullptr || r1_tma) && (res2 == nullptr || r2_tma) &&
+                      !(r2_tma && !r1_tma) && (!has_act || (slope >= 0.f && slope <= 1.f)) && (cout & 3) == 0;
     int u = 0;  // running unit counter (all units, both sets)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile / tiles_per_n;
@@ -522,7 +573,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
         const long long te0 = (DBG && (dbgf & 64)) ? clock64() : 0;
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slot * 2 * n_tile);
-        for (int n = 0; n < n_tile && !(dbgf & 8); n += 16) {
+        if (lean && !(dbgf & 8)) {
+          const float sl = has_act ? slope : 1.f;
+          if (r1_tma && r2_tma) epilogue_lean<true, true>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m);
+          else if (r1_tma) epilogue_lean<true, false>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m);
+          else epilogue_lean<false, false>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m);
+        }
+        for (int n = 0; n < n_tile && !(dbgf & 8) && !lean; n += 16) {
           const int cg = n0 + n;
           uint32_t r1[16], r2[16];
           ptx::tmem_ld16(t_row + static_cast<uint32_t>(n), r1);
