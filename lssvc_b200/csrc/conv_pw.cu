@@ -29,6 +29,8 @@ constexpr int TMEM_COLS = 512;
 struct alignas(64) PwParams {
   CUtensorMap in_map;   // x [H][W][Cin] fp32, box (slab_w, 16 (+2), 8 (+2))
   CUtensorMap out_map;  // y [H][W][Cout]
+  CUtensorMap res_map;  // res1 [H][W][Cout], TMA-loaded into the staging tile ahead of the accumulator (res_tma)
+  int res_tma;
   const void *w;        // fp16 [Cin/16][2 (hi, lo)][Cout][16], 32-byte rows pre-swizzled (SWIZZLE_32B)
   const float *bias;    // [Cout]
   const float *dw_w;    // [9][Cin] (tap-major) or null
@@ -64,7 +66,7 @@ __device__ __forceinline__ uint32_t slab_addr(uint32_t base, int slab_w, uint32_
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_constant__ PwParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t in_full[MAX_IN_BUFS], in_empty[MAX_IN_BUFS];
-  __shared__ uint64_t a_full[2], a_empty[2], d_full[2], d_empty[2], w_full;
+  __shared__ uint64_t a_full[2], a_empty[2], d_full[2], d_empty[2], w_full, res_full;
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -80,10 +82,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_co
   const uint32_t b_a_full = ptx::pin(ptx::smem_u32(a_full)), b_a_empty = ptx::pin(ptx::smem_u32(a_empty));
   const uint32_t b_d_full = ptx::pin(ptx::smem_u32(d_full)), b_d_empty = ptx::pin(ptx::smem_u32(d_empty));
   const uint32_t b_w_full = ptx::pin(ptx::smem_u32(&w_full));
+  const uint32_t b_res_full = ptx::pin(ptx::smem_u32(&res_full));
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.in_map);
     ptx::prefetch_tensormap(&p.out_map);
+    if (p.res_tma) ptx::prefetch_tensormap(&p.res_map);
   }
   if (warp == 1 && lane == 0) {
     for (int b = 0; b < p.in_bufs; ++b) {
@@ -97,6 +101,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_co
       ptx::mbar_init(b_d_empty + 8 * b, 8);
     }
     ptx::mbar_init(b_w_full, 1);
+    ptx::mbar_init(b_res_full, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -251,15 +256,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_co
     const bool store_thread = warp == 20 && lane == 0;
     const uint32_t out_slab_stride = 128u * static_cast<uint32_t>(p.out_slab_w) * 4u;
     int b = 0;
-    uint32_t ph = 0;
+    uint32_t ph = 0, res_ph = 0;
+    // LeakyReLU as max(v, slope v) (exact for 0 <= slope <= 1; slope = 1 without activation): no per-element branches.  The
+    // epilogue warps are instruction-latency bound, so the lean form is what lets the kernel follow HBM.
+    const float sl = has_act ? slope : 1.f;
+    const bool lean_act = !has_act || (slope >= 0.f && slope <= 1.f);
+    const bool r_tma = p.res_tma != 0;
+    const float *const res1 = r_tma ? nullptr : p.res1;
+    const float *const res2 = p.res2;
+    const int out_slab_w = p.out_slab_w;
+    const uint32_t sswz = (out_slab_w == 32 ? static_cast<uint32_t>(m & 7) : static_cast<uint32_t>((m >> 1) & 3)) << 4;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
       const int oy = ty * TILE_H + h, ox = tx * TILE_W + w;
       const bool valid = oy < p.H && ox < p.W;
       const long long pix = static_cast<long long>(oy) * p.W + ox;
-      if (store_thread) ptx::bulk_wait_read_all();  // staging free: the previous tile's TMA store has read it
+      if (store_thread) {
+        ptx::bulk_wait_read_all();  // staging free: the previous tile's TMA store has read it
+        if (r_tma) {                // the residual tile lands in the staging buffer while the MMAs of this tile run
+          ptx::mbar_expect_tx(b_res_full, static_cast<uint32_t>(p.out_slabs) * out_slab_stride);
+          for (int s = 0; s < p.out_slabs; ++s)
+            ptx::tma_load_3d(stage_s + static_cast<uint32_t>(s) * out_slab_stride, &p.res_map, b_res_full, s * out_slab_w, tx * TILE_W,
+                             ty * TILE_H);
+        }
+      }
       ptx::named_bar_sync(2, 256);
       ptx::mbar_wait(b_d_full + 8 * b, ph);
+      if (r_tma) {
+        ptx::mbar_wait(b_res_full, res_ph);
+        res_ph ^= 1u;
+      }
       ptx::tc_fence_after();
       const uint32_t src = t_d + static_cast<uint32_t>(b * 2 * Cout) + lane_off;
       for (int n = 16 * eset; n < Cout; n += 32) {
@@ -267,8 +293,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_co
         ptx::tmem_ld16(src + n, r1);
         ptx::tmem_ld16(src + Cout + n, r2);
         float4 bv[4];
+        const uint32_t srow = static_cast<uint32_t>(n / out_slab_w) * out_slab_stride + static_cast<uint32_t>(m) * (out_slab_w * 4u);
+        const uint32_t spiece = static_cast<uint32_t>(n % out_slab_w) << 2;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4 *>(p.bias + n) + i);
+        for (int i = 0; i < 4; ++i) {
+          bv[i] = __ldg(reinterpret_cast<const float4 *>(p.bias + n) + i);
+        }
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -277,22 +307,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_co
           v[1] = (__uint_as_float(r1[4 * i + 1]) + __uint_as_float(r2[4 * i + 1])) * acc_scale + bv[i].y;
           v[2] = (__uint_as_float(r1[4 * i + 2]) + __uint_as_float(r2[4 * i + 2])) * acc_scale + bv[i].z;
           v[3] = (__uint_as_float(r1[4 * i + 3]) + __uint_as_float(r2[4 * i + 3])) * acc_scale + bv[i].w;
-          if (has_act) {
+          if (lean_act) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
+            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], v[e] * sl) * out_scale;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = (v[e] > 0.f ? v[e] : v[e] * slope) * out_scale;
           }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] *= out_scale;
-          if (p.res1 && valid) {
-            const float4 t = *reinterpret_cast<const float4 *>(p.res1 + pix * p.res1_pitch + n + 4 * i);
+          if (r_tma) {
+            const float4 t = ptx::lds_f4(stage_s + srow + ((spiece + 16u * i) ^ sswz));
+            v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+          } else if (res1 && valid) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(res1 + pix * p.res1_pitch + n) + i);
             v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
           }
-          if (p.res2 && valid) {
-            const float4 t = *reinterpret_cast<const float4 *>(p.res2 + pix * p.res2_pitch + n + 4 * i);
+          if (res2 && valid) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(res2 + pix * p.res2_pitch + n) + i);
             v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
           }
-          ptx::sts_u4(slab_addr(stage_s, p.out_slab_w, out_slab_stride, m, n + 4 * i), __float_as_uint(v[0]),
-                      __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+          ptx::sts_u4(stage_s + srow + ((spiece + 16u * i) ^ sswz), __float_as_uint(v[0]), __float_as_uint(v[1]),
+                      __float_as_uint(v[2]), __float_as_uint(v[3]));
         }
       }
       ptx::tc_fence_before();
@@ -409,6 +443,10 @@ extern "C" int32_t lssvc_conv_pw(const lssvc_pw *f, void *stream) {
   };
   CUresult r = make_map(&p.in_map, f->in, p.in_slab_w, p.in_w, dw ? TILE_H + 2 : TILE_H);
   if (r == CUDA_SUCCESS) r = make_map(&p.out_map, f->out, p.out_slab_w, TILE_W, TILE_H);
+  if (r == CUDA_SUCCESS && f->res1.ptr) {
+    r = make_map(&p.res_map, f->res1, p.out_slab_w, TILE_W, TILE_H);
+    p.res_tma = 1;
+  }
   if (r != CUDA_SUCCESS) {
     lssvc::set_error("conv_pw: cuTensorMapEncodeTiled failed with %d", static_cast<int>(r));
     return LSSVC_ERR_CUDA;
