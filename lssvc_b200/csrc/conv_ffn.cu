@@ -161,68 +161,70 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------------------
-    const uint32_t idesc_a1 = ptx::make_idesc_f16_m128(2 * HC), idesc_a2 = ptx::make_idesc_f16_m128(HC);
-    const uint32_t idesc_b1 = ptx::make_idesc_f16_m128(static_cast<uint32_t>(2 * C));
-    const uint32_t idesc_b2 = ptx::make_idesc_f16_m128(static_cast<uint32_t>(C));
-    const uint32_t w1_sub = 2u * HC * 32u;                        // bytes of one W1 sub-tile [2][32][16] fp16
-    const uint32_t w2_sub = 2u * static_cast<uint32_t>(C) * 32u;  // bytes of one W2 sub-tile [2][C][16]
-    uint32_t n_dh[2] = {0, 0}, n_ah[2] = {0, 0};                  // uses of each buffer so far (phase = use & 1)
-    uint32_t tphase = 0;                                          // per-tile barriers (ao_full)
-    int tb = 0;
-    uint32_t dy_ph = 0;
-    ptx::mbar_wait(b_w_full, 0);
-    auto gemm_a = [&](int j) {
-      const int b = j & 1;
-      ptx::mbar_wait(b_dh_empty + 8 * b, (n_dh[b] & 1u) ^ 1u);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t d = t_dh + 64u * b;
-        for (int ks = 0; ks < KS1; ++ks) {
-          const uint64_t bd = ptx::make_kmajor_desc(w1_s + static_cast<uint32_t>(j * KS1 + ks) * w1_sub, 256, 6u);
-          ptx::mma_f16_ts(d, t_ao + ks * 8, bd, idesc_a1, ks != 0 ? 1u : 0u);
-          ptx::mma_f16_ts(d + HC, t_ao + (C >> 1) + ks * 8, bd, idesc_a2, 1u);
-        }
-        ptx::mma_commit(b_dh_full + 8 * b);
-      }
-      __syncwarp();
-      ++n_dh[b];
-    };
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      ptx::mbar_wait(b_ao_full, tphase);
-      ptx::mbar_wait(b_dy_empty + 8 * tb, dy_ph ^ 1u);
-      ptx::tc_fence_after();
-      gemm_a(0);
-      for (int j = 0; j < n_chunks; ++j) {
-        if (j + 1 < n_chunks) {
-          gemm_a(j + 1);
-        } else {
-          if (ptx::elect_one()) ptx::mma_commit(b_ao_empty);  // every GEMM-a of this tile has been issued
-          __syncwarp();
-        }
-        const int b = j & 1;
-        ptx::mbar_wait(b_ah_full + 8 * b, n_ah[b] & 1u);
+    // One elected thread runs the whole loop: a serial instruction stream, so descriptors are (lo, hi) 32-bit words
+    // advanced by adds and buffer phases live in bit masks (see conv_hs.cu).
+    if (ptx::elect_one()) {
+      const uint32_t idesc_a1 = ptx::make_idesc_f16_m128(2 * HC), idesc_a2 = ptx::make_idesc_f16_m128(HC);
+      const uint32_t idesc_b1 = ptx::make_idesc_f16_m128(static_cast<uint32_t>(2 * C));
+      const uint32_t idesc_b2 = ptx::make_idesc_f16_m128(static_cast<uint32_t>(C));
+      constexpr uint32_t B_HI = (256u >> 4) | (1u << 14) | (6u << 29);  // SBO = 256 B, version 1, SWIZZLE_32B
+      const uint32_t w1_sub16 = (2u * HC * 32u) >> 4;                        // one W1 sub-tile [2][32][16] fp16, in 16-byte units
+      const uint32_t w2_sub16 = (2u * static_cast<uint32_t>(C) * 32u) >> 4;  // one W2 sub-tile [2][C][16]
+      const uint32_t w1_16 = (w1_s >> 4) | (1u << 16), w2_16 = (w2_s >> 4) | (1u << 16);
+      const uint32_t half_c = static_cast<uint32_t>(C) >> 1;
+      uint32_t dh_mask = 0, ah_mask = 0;  // bit b: phase of buffer b's next use
+      uint32_t tphase = 0;
+      int tb = 0;
+      uint32_t dy_ph = 0;
+      ptx::mbar_wait(b_w_full, 0);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(b_ao_full, tphase);
+        ptx::mbar_wait(b_dy_empty + 8 * tb, dy_ph ^ 1u);
         ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t d = t_dy + static_cast<uint32_t>(tb * 2 * C);
-          const uint32_t a = t_ah + 32u * b;
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t bd = ptx::make_kmajor_desc(w2_s + static_cast<uint32_t>(j * 2 + ks) * w2_sub, 256, 6u);
-            ptx::mma_f16_ts(d, a + ks * 8, bd, idesc_b1, (j | ks) != 0 ? 1u : 0u);
-            ptx::mma_f16_ts(d + C, a + 16 + ks * 8, bd, idesc_b2, 1u);
+        uint32_t w1p = w1_16, w2p = w2_16;  // running weight descriptors of GEMM-a / GEMM-b
+        const uint32_t dy = t_dy + static_cast<uint32_t>(tb * 2 * C);
+        // GEMM-a of chunk ja runs one chunk ahead of GEMM-b of chunk j
+        for (int ja = 0; ja <= n_chunks; ++ja) {
+          if (ja < n_chunks) {
+            const uint32_t b = static_cast<uint32_t>(ja) & 1u;
+            ptx::mbar_wait(b_dh_empty + 8 * b, ((dh_mask >> b) & 1u) ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d = t_dh + 64u * b;
+            for (int ks = 0; ks < KS1; ++ks) {
+              ptx::mma_f16_ts2(d, t_ao + ks * 8, w1p, B_HI, idesc_a1, ks != 0 ? 1u : 0u);
+              ptx::mma_f16_ts2(d + HC, t_ao + half_c + ks * 8, w1p, B_HI, idesc_a2, 1u);
+              w1p += w1_sub16;
+            }
+            ptx::mma_commit(b_dh_full + 8 * b);
+            dh_mask ^= 1u << b;
+          } else {
+            ptx::mma_commit(b_ao_empty);  // every GEMM-a of this tile has been issued
           }
-          ptx::mma_commit(b_ah_empty + 8 * b);
-          if (j == n_chunks - 1) ptx::mma_commit(b_dy_full + 8 * tb);
+          if (ja > 0) {
+            const int j = ja - 1;
+            const uint32_t b = static_cast<uint32_t>(j) & 1u;
+            ptx::mbar_wait(b_ah_full + 8 * b, (ah_mask >> b) & 1u);
+            ptx::tc_fence_after();
+            const uint32_t a = t_ah + 32u * b;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              ptx::mma_f16_ts2(dy, a + ks * 8, w2p, B_HI, idesc_b1, (j | ks) != 0 ? 1u : 0u);
+              ptx::mma_f16_ts2(dy + C, a + 16 + ks * 8, w2p, B_HI, idesc_b2, 1u);
+              w2p += w2_sub16;
+            }
+            ptx::mma_commit(b_ah_empty + 8 * b);
+            if (j == n_chunks - 1) ptx::mma_commit(b_dy_full + 8 * tb);
+            ah_mask ^= 1u << b;
+          }
         }
-        __syncwarp();
-        ++n_ah[b];
-      }
-      tphase ^= 1u;
-      if (++tb == 2) {
-        tb = 0;
-        dy_ph ^= 1u;
+        tphase ^= 1u;
+        if (++tb == 2) {
+          tb = 0;
+          dy_ph ^= 1u;
+        }
       }
     }
+    __syncwarp();
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------- splitters: o tile -> A_o (TMEM) ----------------------
     const int q = warp & 3;
