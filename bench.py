@@ -239,6 +239,12 @@ def main():
             print(json.dumps(cpu_reference(min(args.steps, 3), 1, args.size, True, n_gpus=args.gpus)), flush=True)
         return
 
+    # the contract is ONE JSON line on stdout: native libraries (NCCL prints its version banner) write to fd 1 directly,
+    # so fd 1 is pointed at stderr for the whole run and the line goes out through the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from lssvc_b200 import _lib, ops
@@ -318,7 +324,8 @@ def main():
         line["roofline"] = conv_roofline(torch, dev, shape_hr, peaks)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference(2, 1, args.size, False)
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
