@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
       const uint32_t halo16 = static_cast<uint32_t>(p.halo_bytes) >> 4;
       const uint32_t tile16 = (2u * n_tile * B_ROWB) >> 4;
       constexpr uint32_t DESC_LO = 1u << 16;  // LBO field = 1 (unused for swizzled K-major)
-      const uint32_t a_hi_word = ((static_cast<uint32_t>(p.halo_w) * ROWB) >> 4) | (1u << 14) | (A_LAYOUT << 29);
+      // DBG 16384: SBO forced to 2048 B (8-row groups on 1024-byte swizzle-atom boundaries; reads the wrong pixels)
+      const uint32_t a_hi_word = ((DBG && (dbgf & 16384)) ? (2048u >> 4) : ((static_cast<uint32_t>(p.halo_w) * ROWB) >> 4)) | (1u << 14) | (A_LAYOUT << 29);
       constexpr uint32_t b_hi_word = (B_SBO >> 4) | (1u << 14) | (B_LAYOUT << 29);
       const uint32_t a16_base = (smem_base >> 4) | DESC_LO, b16_base = (b_base >> 4) | DESC_LO;
       constexpr uint32_t SUB16 = (SUB_W * ROWB) >> 4, LO16 = LO_OFF >> 4;
@@ -394,6 +395,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
             }
             const int items = static_cast<int>(c_z & 0xffu);
             uint32_t tap16[4] = {c_x & 0xffffu, c_x >> 16, c_y & 0xffffu, c_y >> 16};
+            if (DBG && (dbgf & 8192)) {  // tap windows rounded down to 1024-byte swizzle atoms (wrong pixels: timing only)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) tap16[i] &= ~63u;
+            }
             HS_WAIT(2, bar_full + 8 * s, ph);
             ptx::tc_fence_after();
             const long long ti0 = (DBG && (dbgf & 64)) ? clock64() : 0;
@@ -405,13 +410,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
                 const uint32_t b16_tap = b16_s + static_cast<uint32_t>(i) * tile16;
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
+                  // issue order hi(0), hi(1), lo(0), lo(1): consecutive MMAs share the weight operand and never
+                  // target the accumulator the previous one wrote (measured 4-5 % faster than hi/lo per sub-tile)
+                  // [D1 | D2] (+)= A_hi * [W_hi | W_lo]   then   D2 += A_lo * W_hi
+#pragma unroll
+                  for (int j = 0; j < MT; ++j) {
+                    if (!DBG || !(dbgf & 1))
+                      ptx::mma_f16_ss2(d_tile + static_cast<uint32_t>(j) * 2u * n_tile, a16_tap + j * SUB16 + ks * 2, a_hi_word,
+                                       b16_tap + ks * 2, b_hi_word, (DBG && (dbgf & 256)) ? idesc_n : idesc_2n, acc);
+                  }
 #pragma unroll
                   for (int j = 0; j < MT; ++j) {
                     const uint32_t a16 = a16_tap + j * SUB16 + ks * 2;
                     const uint32_t d1 = d_tile + static_cast<uint32_t>(j) * 2u * n_tile;
-                    // [D1 | D2] (+)= A_hi * [W_hi | W_lo]   then   D2 += A_lo * W_hi
-                    if (!DBG || !(dbgf & 1))
-                      ptx::mma_f16_ss2(d1, a16, a_hi_word, b16_tap + ks * 2, b_hi_word, (DBG && (dbgf & 256)) ? idesc_n : idesc_2n, acc);
                     if (!DBG || !(dbgf & 2))
                       ptx::mma_f16_ss2((DBG && (dbgf & 4096)) ? ((d1 + n_tile + 256u) & 0xffff01ffu) : d1 + n_tile,
                                        (DBG && (dbgf & 512)) ? a16 : a16 + LO16, a_hi_word, b16_tap + ks * 2, b_hi_word,
