@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/lssvc_b200.h"
 
@@ -48,5 +49,20 @@ inline bool view_present(const lssvc_view *v) { return v && v->ptr != nullptr; }
   } while (0)
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// The tensor core adds every K = 16 MMA into the fp32 TMEM accumulator with truncation (round towards zero), so a sum of
+// `steps` MMAs comes out SMALLER in magnitude than the exact sum by a nearly deterministic factor: measured on the 15 layer
+// shapes of tools/conv_bench.py (CONV_BENCH_BIAS=1, profiles/r1_accumulation_bias.txt) the mean signed relative error is
+// -(0.264 * steps + 0.6) * 2^-24 for steps = 4 .. 196, and it — not the split-fp16 operands — was ~85 % of the rms error
+// (3x3 64->64: 7.2e-7 against 4.3e-7 for fp32 CUDA cores), coherent from layer to layer.  The kernels undo its expected
+// value by folding (1 + that factor) into the accumulator scale they apply anyway.  LSSVC_ACC_COMP=0 disables it (A/B).
+inline float acc_comp(int steps) {
+  static const bool off = [] {
+    const char *e = getenv("LSSVC_ACC_COMP");
+    return e != nullptr && atoi(e) == 0;
+  }();
+  if (off || steps <= 0) return 1.f;
+  return 1.f + (0.264f * static_cast<float>(steps) + 0.6f) * 5.9604645e-8f;
+}
 
 }  // namespace lssvc

@@ -1,6 +1,8 @@
 // Memory-bound image-space kernels: layout conversion, flow warping, bilinear resampling, pooling,
 // the SpyNet level prologue and the OffsetDiversity tail.  All operate on NHWC fp32 views and are
 // written for coalesced, 128-bit accesses along the channel axis.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -207,6 +209,45 @@ __global__ void __launch_bounds__(TPB) flow_warp4_kernel(const float *__restrict
   }
 }
 
+// Per-pixel-lane variant (the default): `lpp` consecutive threads own one pixel and each moves Q float4 channel quads
+// (quad l + j * lpp for lane l), so the flow load, the grid_sample coordinate arithmetic (4 fp32 divisions) and the pixel
+// index divisions are paid once per Q quads instead of once per quad (the float4 kernel above issues ~120 instructions per
+// 16 output bytes and sits at 65 % issue utilisation, 55 % of the copy bandwidth), and 4 * Q corner loads are in flight
+// per thread.  A lane group reads lpp * 16 contiguous bytes per corner and step.
+template <int Q>
+__global__ void __launch_bounds__(TPB) flow_warp_q_kernel(const float *__restrict__ src, uint32_t s_pitch,
+                                                          const float *__restrict__ flow, uint32_t f_pitch, float fscale,
+                                                          float *__restrict__ out, uint32_t o_pitch, int H, int W, uint32_t lpp,
+                                                          uint32_t n_threads) {
+  const uint32_t gid = blockIdx.x * TPB + threadIdx.x;
+  if (gid >= n_threads) return;
+  const uint32_t pix = gid / lpp, l = gid - pix * lpp;
+  const int y = static_cast<int>(pix / static_cast<uint32_t>(W)), x = static_cast<int>(pix - static_cast<uint32_t>(y) * W);
+  const float fx = __ldg(flow + static_cast<size_t>(pix) * f_pitch) * fscale;
+  const float fy = __ldg(flow + static_cast<size_t>(pix) * f_pitch + 1) * fscale;
+  int x0, x1, y0, y1;
+  float wx, wy;
+  warp_coords(x, y, fx, fy, W, H, x0, x1, y0, y1, wx, wy);
+  const size_t r0 = static_cast<size_t>(y0) * W, r1 = static_cast<size_t>(y1) * W;
+  const float4 *p00 = reinterpret_cast<const float4 *>(src + (r0 + x0) * s_pitch) + l;
+  const float4 *p01 = reinterpret_cast<const float4 *>(src + (r0 + x1) * s_pitch) + l;
+  const float4 *p10 = reinterpret_cast<const float4 *>(src + (r1 + x0) * s_pitch) + l;
+  const float4 *p11 = reinterpret_cast<const float4 *>(src + (r1 + x1) * s_pitch) + l;
+  float4 a[Q], b[Q], d[Q], e[Q];
+#pragma unroll
+  for (int j = 0; j < Q; ++j) {
+    a[j] = __ldg(p00 + j * lpp);
+    b[j] = __ldg(p01 + j * lpp);
+    d[j] = __ldg(p10 + j * lpp);
+    e[j] = __ldg(p11 + j * lpp);
+  }
+  float4 *o = reinterpret_cast<float4 *>(out + static_cast<size_t>(pix) * o_pitch) + l;
+#pragma unroll
+  for (int j = 0; j < Q; ++j)
+    o[j * lpp] = make_float4(bilerp(a[j].x, b[j].x, d[j].x, e[j].x, wx, wy), bilerp(a[j].y, b[j].y, d[j].y, e[j].y, wx, wy),
+                             bilerp(a[j].z, b[j].z, d[j].z, e[j].z, wx, wy), bilerp(a[j].w, b[j].w, d[j].w, e[j].w, wx, wy));
+}
+
 template <int VEC>
 __global__ void flow_warp_kernel(const float *__restrict__ src, int s_pitch, const float *__restrict__ flow,
                                  int f_pitch, float fscale, float *__restrict__ out, int o_pitch, int H, int W, int C) {
@@ -311,6 +352,43 @@ __global__ void __launch_bounds__(TPB) bilinear_resize4_kernel(const float *__re
                       (hy * (hx * a[k].w + ax * b[k].w) + ay * (hx * d[k].w + ax * e[k].w)) * mul);
     }
   }
+}
+
+// per-pixel-lane variant of the resize (see flow_warp_q_kernel)
+template <int Q>
+__global__ void __launch_bounds__(TPB) bilinear_resize_q_kernel(const float *__restrict__ in, uint32_t i_pitch, int Hi, int Wi,
+                                                                float *__restrict__ out, uint32_t o_pitch, int Wo, uint32_t lpp,
+                                                                uint32_t n_threads, float rh, float rw, float mul) {
+  const uint32_t gid = blockIdx.x * TPB + threadIdx.x;
+  if (gid >= n_threads) return;
+  const uint32_t pix = gid / lpp, l = gid - pix * lpp;
+  const int y = static_cast<int>(pix / static_cast<uint32_t>(Wo)), x = static_cast<int>(pix - static_cast<uint32_t>(y) * Wo);
+  int x0, x1, y0, y1;
+  float ax, ay;
+  resize_coord(x, rw, Wi, x0, x1, ax);
+  resize_coord(y, rh, Hi, y0, y1, ay);
+  const size_t r0 = static_cast<size_t>(y0) * Wi, r1 = static_cast<size_t>(y1) * Wi;
+  const float4 *p00 = reinterpret_cast<const float4 *>(in + (r0 + x0) * i_pitch) + l;
+  const float4 *p01 = reinterpret_cast<const float4 *>(in + (r0 + x1) * i_pitch) + l;
+  const float4 *p10 = reinterpret_cast<const float4 *>(in + (r1 + x0) * i_pitch) + l;
+  const float4 *p11 = reinterpret_cast<const float4 *>(in + (r1 + x1) * i_pitch) + l;
+  float4 a[Q], b[Q], d[Q], e[Q];
+#pragma unroll
+  for (int j = 0; j < Q; ++j) {
+    a[j] = __ldg(p00 + j * lpp);
+    b[j] = __ldg(p01 + j * lpp);
+    d[j] = __ldg(p10 + j * lpp);
+    e[j] = __ldg(p11 + j * lpp);
+  }
+  const float hx = 1.f - ax, hy = 1.f - ay;
+  float4 *o = reinterpret_cast<float4 *>(out + static_cast<size_t>(pix) * o_pitch) + l;
+#pragma unroll
+  for (int j = 0; j < Q; ++j)
+    // ATen upsample_bilinear2d: h0l * (w0l * v00 + w1l * v01) + h1l * (w0l * v10 + w1l * v11)
+    o[j * lpp] = make_float4((hy * (hx * a[j].x + ax * b[j].x) + ay * (hx * d[j].x + ax * e[j].x)) * mul,
+                             (hy * (hx * a[j].y + ax * b[j].y) + ay * (hx * d[j].y + ax * e[j].y)) * mul,
+                             (hy * (hx * a[j].z + ax * b[j].z) + ay * (hx * d[j].z + ax * e[j].z)) * mul,
+                             (hy * (hx * a[j].w + ax * b[j].w) + ay * (hx * d[j].w + ax * e[j].w)) * mul);
 }
 
 template <bool MAX>
@@ -502,6 +580,25 @@ bool fits32(long long pixels, int pitch_a, int pitch_b) {
 
 bool aligned4(const lssvc_view *v) { return v->C % 4 == 0 && v->pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0; }
 
+// Channel quads per thread (Q) and lanes per pixel (cv / Q) of the per-pixel-lane gather kernels: the widest Q that still
+// leaves 4 lanes (64 contiguous bytes per corner) per pixel.
+int pick_quads(uint32_t cv, uint32_t *lpp) {
+  for (int q = 4; q >= 2; --q) {
+    if (cv % q == 0 && cv / q >= 4) {
+      *lpp = cv / q;
+      return q;
+    }
+  }
+  *lpp = cv;
+  return 1;
+}
+
+// A/B switch for tools/mem_bench.py: LSSVC_GATHER_LEGACY=1 selects the earlier two-elements-per-thread float4 kernels
+bool legacy_gather() {
+  static const bool on = getenv("LSSVC_GATHER_LEGACY") != nullptr;
+  return on;
+}
+
 }  // namespace
 
 extern "C" int32_t lssvc_nchw_to_nhwc(const float *src, int32_t C, const lssvc_view *out, void *stream) {
@@ -572,8 +669,25 @@ extern "C" int32_t lssvc_flow_warp(const lssvc_view *src, const lssvc_view *flow
   cudaStream_t s = lssvc::as_stream(stream);
   if (aligned4(src) && aligned4(out) && fits32(pixels, src->pitch, out->pitch)) {
     const uint32_t cv = src->C / 4, total = static_cast<uint32_t>(pixels) * cv;
-    flow_warp4_kernel<<<(total + TPB * 2 - 1) / (TPB * 2), TPB, 0, s>>>(src->ptr, src->pitch, flow->ptr, flow->pitch, flow_scale,
-                                                                       out->ptr, out->pitch, out->H, out->W, cv, total);
+    uint32_t lpp = cv;
+    const int q = pick_quads(cv, &lpp);
+    const uint32_t n_threads = static_cast<uint32_t>(pixels) * lpp, grid = (n_threads + TPB - 1) / TPB;
+#define LSSVC_WARP_Q(QQ)                                                                                                   \
+  flow_warp_q_kernel<QQ><<<grid, TPB, 0, s>>>(src->ptr, src->pitch, flow->ptr, flow->pitch, flow_scale, out->ptr, out->pitch, \
+                                              out->H, out->W, lpp, n_threads)
+    if (legacy_gather()) {
+      flow_warp4_kernel<<<(total + TPB * 2 - 1) / (TPB * 2), TPB, 0, s>>>(src->ptr, src->pitch, flow->ptr, flow->pitch, flow_scale,
+                                                                         out->ptr, out->pitch, out->H, out->W, cv, total);
+    } else if (q == 4) {
+      LSSVC_WARP_Q(4);
+    } else if (q == 3) {
+      LSSVC_WARP_Q(3);
+    } else if (q == 2) {
+      LSSVC_WARP_Q(2);
+    } else {
+      LSSVC_WARP_Q(1);
+    }
+#undef LSSVC_WARP_Q
   } else if (aligned4(src) && aligned4(out)) {
     flow_warp_kernel<4><<<blocks_for(pixels * (src->C / 4)), TPB, 0, s>>>(src->ptr, src->pitch, flow->ptr, flow->pitch,
                                                                          flow_scale, out->ptr, out->pitch, out->H, out->W,
@@ -594,8 +708,25 @@ extern "C" int32_t lssvc_bilinear_resize(const lssvc_view *in, float scale, cons
   cudaStream_t s = lssvc::as_stream(stream);
   if (aligned4(in) && aligned4(out) && fits32(pixels, in->pitch, out->pitch)) {
     const uint32_t cv = in->C / 4, total = static_cast<uint32_t>(pixels) * cv;
-    bilinear_resize4_kernel<<<(total + TPB * 2 - 1) / (TPB * 2), TPB, 0, s>>>(in->ptr, in->pitch, in->H, in->W, out->ptr, out->pitch,
-                                                                             out->W, cv, total, rh, rw, scale);
+    uint32_t lpp = cv;
+    const int q = pick_quads(cv, &lpp);
+    const uint32_t n_threads = static_cast<uint32_t>(pixels) * lpp, grid = (n_threads + TPB - 1) / TPB;
+#define LSSVC_RESIZE_Q(QQ)                                                                                               \
+  bilinear_resize_q_kernel<QQ><<<grid, TPB, 0, s>>>(in->ptr, in->pitch, in->H, in->W, out->ptr, out->pitch, out->W, lpp, n_threads, \
+                                                    rh, rw, scale)
+    if (legacy_gather()) {
+      bilinear_resize4_kernel<<<(total + TPB * 2 - 1) / (TPB * 2), TPB, 0, s>>>(in->ptr, in->pitch, in->H, in->W, out->ptr, out->pitch,
+                                                                               out->W, cv, total, rh, rw, scale);
+    } else if (q == 4) {
+      LSSVC_RESIZE_Q(4);
+    } else if (q == 3) {
+      LSSVC_RESIZE_Q(3);
+    } else if (q == 2) {
+      LSSVC_RESIZE_Q(2);
+    } else {
+      LSSVC_RESIZE_Q(1);
+    }
+#undef LSSVC_RESIZE_Q
   } else if (aligned4(in) && aligned4(out)) {
     bilinear_resize_kernel<4><<<blocks_for(pixels * (in->C / 4)), TPB, 0, s>>>(in->ptr, in->pitch, in->H, in->W, out->ptr,
                                                                               out->pitch, out->H, out->W, in->C, rh, rw, scale);

@@ -58,13 +58,13 @@ class Engine(nets.ParamBag):
             raise _lib.LssvcError("lssvc_b200 models run on a CUDA (sm_100a) device only; call .to('cuda') first — "
                                   "there is no CPU fallback")
 
-    def pack(self, name, srcs, stride, ps, transposed, pad):
-        key = (name, tuple((v.real, v.C) for v in srcs), stride, ps, transposed, pad)
+    def pack(self, name, srcs, stride, ps, transposed, pad, exact_in=False):
+        key = (name, tuple((v.real, v.C) for v in srcs), stride, ps, transposed, pad, exact_in)
         pc = self._packs.get(key)
         if pc is None:
             pc = ops.PackedConv(self.tensor(name + ".weight"), self.tensor(name + ".bias"), stride=stride, pad=pad,
                                 src_channels=[(v.real, v.C) for v in srcs], pixel_shuffle=ps, transposed=transposed,
-                                device=self.device)
+                                device=self.device, exact_in=exact_in)
             self._packs[key] = pc
         return pc
 
@@ -80,8 +80,9 @@ class Engine(nets.ParamBag):
         return View.alloc_padded(H, W, C, self.device)
 
     def conv(self, name, srcs, stride=1, act=None, ps=False, transposed=False, pad=None, res1=None, res2=None,
-             out=None, act_copy=None, act_copy_out=None, out_scale=1.0, engine=None, in_lrelu=None):
-        """conv (+PixelShuffle) with fused epilogue.  Returns the output view, or (out, lrelu(out, act_copy))."""
+             out=None, act_copy=None, act_copy_out=None, out_scale=1.0, engine=None, in_lrelu=None, exact_in=False):
+        """conv (+PixelShuffle) with fused epilogue.  Returns the output view, or (out, lrelu(out, act_copy)).
+        exact_in: the source holds quantised symbols (ops.PackedConv)."""
         if isinstance(srcs, View):
             srcs = [srcs]
         # un-materialised activations (ops.LazyAct): one common slope -> LeakyReLU in the conv's operand path, else write them out
@@ -91,7 +92,7 @@ class Engine(nets.ParamBag):
                 in_lrelu, srcs = lazy[0], [s.base for s in srcs]
             else:
                 srcs = [self.lrelu(s.base, s.slope) if isinstance(s, ops.LazyAct) else s for s in srcs]
-        pc = self.pack(name, srcs, stride, ps, transposed, pad)
+        pc = self.pack(name, srcs, stride, ps, transposed, pad, exact_in)
         Hi, Wi = srcs[0].H, srcs[0].W
         Ho = (Hi + 2 * pc.pad - pc.kh) // stride + 1
         Wo = (Wi + 2 * pc.pad - pc.kw) // stride + 1
@@ -176,7 +177,7 @@ class Engine(nets.ParamBag):
         ops.pw(pp, x.exact(), out.exact(), act=act, res1=ex(res1), res2=ex(res2))
         return out
 
-    def deconv_s2(self, name, x, act=None):
+    def deconv_s2(self, name, x, act=None, exact_in=False):
         """nn.ConvTranspose2d(3, stride=2, padding=1, output_padding=1).
 
         On the tensor-core engine it runs as its sub-pixel decomposition: out[2y+i, 2x+j] only involves in[y+a, x+b]
@@ -193,8 +194,8 @@ class Engine(nets.ParamBag):
                     for (j, bb), kx in kmap.items():
                         w3[2 * i + j::4, :, a + 1, bb + 1] = w[:, :, ky, kx].t()
                 return ops.PackedConv(w3, b.repeat_interleave(4), pad=1, src_channels=[(x.real, x.C)], pixel_shuffle=True,
-                                      device=self.device)
-            pc = self.cached(("deconv_ps", name, x.real, x.C), build_ps)
+                                      device=self.device, exact_in=exact_in)
+            pc = self.cached(("deconv_ps", name, x.real, x.C, exact_in), build_ps)
             out = self.new(x.H * 2, x.W * 2, pc.cout // 4)
             ops.TRACE_NAME = name
             ops.conv(pc, [x], out.exact(), act=act)

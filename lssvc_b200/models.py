@@ -163,7 +163,7 @@ class IntraSS(Engine):
 
     def _bl_params(self, z_hat):
         p = "base_layer_model."
-        g = self.conv(p + "h_s.0", z_hat, act=0.01)
+        g = self.conv(p + "h_s.0", z_hat, act=0.01, exact_in=True)
         g = self.conv(p + "h_s.2.0", g, ps=True, act=0.01)
         g = self.conv(p + "h_s.4", g, act=0.01)
         g = self.conv(p + "h_s.6.0", g, ps=True, act=0.01)
@@ -232,7 +232,7 @@ class IntraSS(Engine):
 
     def _el_params(self, z_hat, y_hat_bl, c3):
         H, W = self.shape_hr
-        hyper = self.conv("h_s.0.0", z_hat, ps=True, act=0.01)
+        hyper = self.conv("h_s.0.0", z_hat, ps=True, act=0.01, exact_in=True)
         hyper = self.conv("h_s.2.0", hyper, ps=True, act=0.01)
         hyper = self.conv("h_s.4", hyper)
         lp = self.seq2("layer_prior_resampler.conv_adaptor", y_hat_bl)
@@ -424,7 +424,7 @@ class LSSVC(Engine):
         return mv_y, mv_z
 
     def _bl_mv_params(self, p, mv_z_hat):
-        t = self.deconv_s2(p + "mv_prior_decoder.0", mv_z_hat, act=0.01)
+        t = self.deconv_s2(p + "mv_prior_decoder.0", mv_z_hat, act=0.01, exact_in=True)
         t = self.deconv_s2(p + "mv_prior_decoder.2", t, act=0.01)
         return self.conv(p + "mv_prior_decoder.4", t, transposed=True)
 
@@ -449,7 +449,7 @@ class LSSVC(Engine):
         return self.fusion3(p + "context_fusion_net", c1, c2, c3)
 
     def _bl_res_params(self, p, z_hat, c1, c2, c3):
-        t = self.deconv_s2(p + "res_prior_decoder.0", z_hat, act=0.01)
+        t = self.deconv_s2(p + "res_prior_decoder.0", z_hat, act=0.01, exact_in=True)
         t = self.deconv_s2(p + "res_prior_decoder.2", t, act=0.01)
         hier = self.conv(p + "res_prior_decoder.4", t, transposed=True)
         tp = p + "temporal_prior_encoder"
@@ -548,7 +548,7 @@ class LSSVC(Engine):
         return mv_y, self._prior_encoder("mv_prior_encoder", mv_y)
 
     def _mv_params(self, mv_z_hat, mv_ctx_prior):
-        h = self.conv("mv_prior_decoder.0.0", mv_z_hat, ps=True, act=0.01)
+        h = self.conv("mv_prior_decoder.0.0", mv_z_hat, ps=True, act=0.01, exact_in=True)
         h = self.conv("mv_prior_decoder.2.0", h, ps=True, act=0.01)
         h = self.conv("mv_prior_decoder.4", h)
         g = self.conv("mv_prior_fusion.0", [h, mv_ctx_prior], act=0.01)
@@ -624,7 +624,7 @@ class LSSVC(Engine):
         return self.res_block(name, cat, slope=0.1, start_from_relu=True, end_with_relu=True)
 
     def _res_params(self, z_hat, c3, y_bl_hat):
-        h = self.conv("res_prior_decoder.0", z_hat, act=0.01)
+        h = self.conv("res_prior_decoder.0", z_hat, act=0.01, exact_in=True)
         h = self.conv("res_prior_decoder.2.0", h, ps=True, act=0.01, pad=0)
         h = self.conv("res_prior_decoder.4", h, act=0.01)
         h = self.conv("res_prior_decoder.6.0", h, ps=True, act=0.01, pad=0)

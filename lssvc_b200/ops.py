@@ -121,16 +121,40 @@ def _cv(v):
     return v.c() if v is not None else _NULL_VIEW
 
 
+# The tensor core adds every K = 16 MMA into the fp32 TMEM accumulator with truncation (round towards zero), so a sum of
+# `steps` MMAs comes out SMALLER in magnitude than the exact sum by a nearly deterministic factor: on the 15 layer shapes
+# of tools/conv_bench.py (CONV_BENCH_BIAS=1, profiles/r1_accumulation_bias.txt) the mean signed relative error is
+# -(0.264 * steps + 0.6) * 2^-24 for steps = 4 .. 196, and it — not the split-fp16 operands — was ~85 % of the rms error
+# (3x3 64->64: 7.2e-7 against 4.3e-7 for fp32 CUDA cores), coherent from layer to layer.  Its expected value is undone at
+# pack time: output channel c of the split-fp16 weights is scaled by 1 + (0.264 * steps_c + 0.6) * 2^-24, steps_c = the
+# number of (tap, 16-channel slice) weight blocks of that channel that are not all zero (all-zero blocks — channel
+# padding, the empty taps of a sub-pixel-decomposed ConvTranspose2d — add exact zeros and truncate nothing).
+# LSSVC_ACC_COMP=0 disables it (A/B).
+ACC_COMP = os.environ.get("LSSVC_ACC_COMP", "1") != "0"
+
+
+def acc_comp(steps):
+    """Per-output-channel weight factor compensating the accumulator truncation; steps: tensor or number of MMA steps."""
+    steps = torch.as_tensor(steps, dtype=torch.float32)
+    if not ACC_COMP:
+        return torch.ones_like(steps)
+    return torch.where(steps > 0, 1.0 + (0.264 * steps + 0.6) * 2.0 ** -24, torch.ones_like(steps))
+
+
 class PackedConv:
     """Weights of one Conv2d repacked for the kernels: [kh*kw][n_pad][cin_total] + bias[n_pad]."""
 
     __slots__ = ("weight", "bias", "kh", "kw", "stride", "pad", "cout", "n_pad", "cin_total", "src_c", "pixel_shuffle",
-                 "_split", "_h2")
+                 "_split", "_h2", "exact_in")
 
-    def __init__(self, w, b, stride=1, pad=None, src_channels=None, pixel_shuffle=False, transposed=False, device=None):
+    def __init__(self, w, b, stride=1, pad=None, src_channels=None, pixel_shuffle=False, transposed=False, device=None,
+                 exact_in=False):
         """w: [Cout, Cin, kh, kw] (Conv2d) or, with transposed=True, a stride-1 ConvTranspose2d weight
         [Cin, Cout, kh, kw] (turned into the equivalent flipped Conv2d).  src_channels: list of
-        (real, view) channel counts per source when sources are padded; default one unpadded source."""
+        (real, view) channel counts per source when sources are padded; default one unpadded source.
+        exact_in: the input holds quantised symbols (z_hat: small integers, x_lo = 0, hi*hi products that add without
+        truncation), so the accumulator-truncation compensation (acc_comp) must stay off for this layer."""
+        self.exact_in = exact_in
         w = w.detach().to(torch.float32).cpu()
         if transposed:
             w = w.permute(1, 0, 2, 3).flip(2, 3)
@@ -178,6 +202,16 @@ class PackedConv:
             shift = 0 if m == 0.0 else 13 - int(math.floor(math.log2(m)))
             ws = w * (2.0 ** shift)
             cin16 = sum(round_up(c, 16) for c in self.src_c)
+            # accumulation steps per output channel: (tap, 16-channel slice) blocks holding a non-zero weight
+            nz = torch.zeros(taps, n_pad, cin16, dtype=torch.bool, device=w.device)
+            ci = co = 0
+            for c in self.src_c:
+                nz[:, :, co:co + c] = w[:, :, ci:ci + c] != 0
+                ci += c
+                co += round_up(c, 16)
+            steps = nz.reshape(taps, n_pad, cin16 // 16, 16).any(-1).sum(dim=(0, 2))
+            if not self.exact_in:
+                ws = ws * acc_comp(steps).to(w.device)[None, :, None]
             packed = torch.zeros(taps, 2, n_pad, cin16, dtype=torch.float16, device=w.device)
             ci = co = 0
             for c in self.src_c:
@@ -362,8 +396,8 @@ class PackedFfn:
             out[..., swap, 1, :] = t[..., swap, 0, :]
             return out.reshape(*out.shape[:-2], 16)
 
-        w1s, self.scale1 = scaled(w1)
-        w2s, self.scale2 = scaled(w2)
+        w1s, self.scale1 = scaled(w1 * float(acc_comp(C // 16)))
+        w2s, self.scale2 = scaled(w2 * float(acc_comp(hidden // 16)))
         n_chunks = hidden // 32
         # W1: rows = hidden channel of the chunk, K = input channel     -> [chunk][ks][hi|lo][32][16]
         h1, l1 = split(w1s)
@@ -417,7 +451,7 @@ class PackedPw:
         assert PackedPw.supported(cin, cout, dw_w is not None), (cin, cout)
         m = float(w.abs().max())
         shift = 0 if m == 0.0 else 13 - int(math.floor(math.log2(m)))
-        ws = w * (2.0 ** shift)
+        ws = w * (2.0 ** shift) * float(acc_comp(cin // 16))
         hi = ws.to(torch.float16)
         lo = (ws - hi.to(torch.float32)).to(torch.float16)
         t = torch.stack([hi, lo], 0).reshape(2, cout, cin // 16, 16).permute(2, 0, 1, 3).reshape(cin // 16, 2 * cout, 2, 8)

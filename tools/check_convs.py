@@ -12,6 +12,8 @@ def main():
     ap.add_argument("--size", type=int, nargs=2, default=[256, 256])
     ap.add_argument("--thr", type=float, default=5e-5)
     ap.add_argument("--engine", default=None)
+    ap.add_argument("--bias", action="store_true", help="print every layer's signed relative error against the fp32 kernel "
+                    "(accumulator-truncation study, ops.acc_comp): < 0 = pulled towards zero")
     args = ap.parse_args()
     import torch
     from lssvc_b200 import IntraSS, LSSVC_extend, _lib, ops, synth
@@ -41,6 +43,14 @@ def main():
         a, b = out.as_tensor(), ref.as_tensor()
         err = (a - b).abs().max().item() / (b.abs().max().item() + 1e-20)
         stats["n"] += 1
+        if args.bias:
+            big = b.abs() > b.abs().mean()
+            sh = (((a - b) * b.sign())[big] / b.abs()[big]).mean().item()
+            rms = ((a - b).pow(2).mean().sqrt() / (b.pow(2).mean().sqrt() + 1e-30)).item()
+            steps = pc.kh * pc.kw * sum((c + 15) // 16 for c in pc.src_c)
+            stats.setdefault("rows", []).append((steps, sh * 2 ** 24, rms))
+            print(f"  {str(ops.TRACE_NAME):45s} k{pc.kh} s{pc.stride} cin{pc.src_c} cout{pc.cout} {out.H}x{out.W}: steps {steps:4d} "
+                  f"signed rel err {sh * 2 ** 24:+7.2f} x 2^-24 ({sh * 2 ** 24 / steps:+.3f}/step)  rms rel {rms:.2e}", flush=True)
         if not (err < args.thr):
             stats["bad"] += 1
             d = (a - b).abs().amax(dim=2)
@@ -66,6 +76,12 @@ def main():
         r = net_p.encode_decode(b.to(dev), e.to(dev), dpb, None, None, W, H, W // 2, H // 2)
         dpb = r["dpb"]
     print(f"checked {stats['n']} convs, {stats['bad']} above {args.thr}")
+    if args.bias and stats.get("rows"):
+        import numpy as np
+        rows = np.array(stats["rows"])
+        k = np.polyfit(rows[:, 0], rows[:, 1], 1)
+        print(f"signed error / 2^-24 over {len(rows)} layers: mean {rows[:, 1].mean():+.2f}, per step {np.mean(rows[:, 1] / rows[:, 0]):+.4f}, "
+              f"least-squares {k[0]:+.4f} * steps {k[1]:+.3f}; mean rms rel {rows[:, 2].mean():.3e}")
 
 
 if __name__ == "__main__":

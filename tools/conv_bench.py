@@ -47,6 +47,8 @@ def run(engine, shape, dev, check_rows=64):
     cin = sum(cins)
     w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
     b = torch.randn(cout, generator=g)
+    if os.environ.get("CONV_BENCH_BIAS"):        # accumulation-bias study: no conv bias, signed error statistics printed
+        b = torch.zeros(cout)
     pad = k // 2 if k > 1 else 0
     pc = ops.PackedConv(w, b, stride=stride, pad=pad, src_channels=[(c, c) for c in cins], pixel_shuffle=ps, device=dev)
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
@@ -77,6 +79,15 @@ def run(engine, shape, dev, check_rows=64):
     rows_out = (min(check_rows, Ho) - k) * f          # rows not touched by the cut at the bottom of the crop
     got = out.as_tensor()[:rows_out].permute(2, 0, 1)[None].double()
     err = ((got - ref[:, :, :rows_out]).abs().max() / ref.abs().max()).item()
+    if os.environ.get("CONV_BENCH_BIAS"):
+        r = ref[:, :, :rows_out]
+        d = got - r
+        big = r.abs() > r.abs().mean()
+        shrink = ((d * r.sign())[big] / r.abs()[big]).mean().item()      # < 0: results pulled towards zero
+        rms = (d.pow(2).mean().sqrt() / r.pow(2).mean().sqrt()).item()
+        steps = k * k * sum((c + 15) // 16 for c in cins)
+        print(f"    [{engine}] {name}: signed relative error (towards zero < 0) {shrink:+.3e} = {shrink * 2 ** 24:+.2f} x 2^-24 "
+              f"({shrink * 2 ** 24 / steps:+.3f} per K=16 accumulation step, {steps} steps), rms rel {rms:.3e}")
     # ---- time
     for i in range(3):
         ops.conv(pc, bufs[i], out, act=0.01, engine=engine, **kw)
