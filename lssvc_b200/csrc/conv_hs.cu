@@ -140,10 +140,12 @@ __device__ __forceinline__ void transform_row(float4 (&v)[NV], int in_transform,
 // the layer has no activation), the output scale is always applied (x 1.0 is exact), so the only compile-time variants
 // are the two residual sources.  ~35 instructions per float4 instead of the ~120 of the general path below, which is
 // what bounds the HBM-bound 1x1 layers (the epilogue warps are instruction-latency bound).
-template <bool R1, bool R2>
+// EPI = LSSVC_EPI_GDN / IGDN: v = x * rsqrt(v) / x * sqrt(v) with x (gdn_x) read from global memory, row pointer gx_row
+// (clamped to a valid pixel for the overhang of border tiles: those rows are clipped by the TMA store).
+template <bool R1, bool R2, int EPI>
 __device__ __forceinline__ void epilogue_lean(uint32_t t_row, int n_tile, int n0, int cout, const float *__restrict__ bias,
                                               float acc_scale, float slope, float out_scale, uint32_t stage, uint32_t stage2,
-                                              uint32_t slab_w, int m) {
+                                              uint32_t slab_w, int m, const float *__restrict__ gx_row) {
   const uint32_t sswz = (slab_w == 32 ? static_cast<uint32_t>(m & 7) : static_cast<uint32_t>((m >> 1) & 3)) << 4;
   const uint32_t row_b = static_cast<uint32_t>(m) * (slab_w * 4u);
   for (int n = 0; n < n_tile; n += 16) {
@@ -155,6 +157,11 @@ __device__ __forceinline__ void epilogue_lean(uint32_t t_row, int n_tile, int n0
     float4 b4v[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) b4v[g] = __ldg(reinterpret_cast<const float4 *>(bias + cg) + g);  // bias is padded to n_pad
+    float4 gxv[4];
+    if (EPI != LSSVC_EPI_PLAIN) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) gxv[g] = __ldg(reinterpret_cast<const float4 *>(gx_row + cg) + g);  // cout % 16 == 0 on this path
+    }
     const uint32_t srow = static_cast<uint32_t>(n / static_cast<int>(slab_w)) * (128u * slab_w * 4u) + row_b;
     const uint32_t spiece = static_cast<uint32_t>(n % static_cast<int>(slab_w)) << 2;
     float4 a1[4], a2[4];
@@ -172,6 +179,13 @@ __device__ __forceinline__ void epilogue_lean(uint32_t t_row, int n_tile, int n0
       v[1] = (__uint_as_float(r1[4 * g + 1]) + __uint_as_float(r2[4 * g + 1])) * acc_scale + b4v[g].y;
       v[2] = (__uint_as_float(r1[4 * g + 2]) + __uint_as_float(r2[4 * g + 2])) * acc_scale + b4v[g].z;
       v[3] = (__uint_as_float(r1[4 * g + 3]) + __uint_as_float(r2[4 * g + 3])) * acc_scale + b4v[g].w;
+      if (EPI == LSSVC_EPI_GDN) {
+        v[0] = gxv[g].x * rsqrtf(v[0]); v[1] = gxv[g].y * rsqrtf(v[1]);
+        v[2] = gxv[g].z * rsqrtf(v[2]); v[3] = gxv[g].w * rsqrtf(v[3]);
+      } else if (EPI == LSSVC_EPI_IGDN) {
+        v[0] = gxv[g].x * sqrtf(v[0]); v[1] = gxv[g].y * sqrtf(v[1]);
+        v[2] = gxv[g].z * sqrtf(v[2]); v[3] = gxv[g].w * sqrtf(v[3]);
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], v[e] * slope) * out_scale;
       if (R1) { v[0] += a1[g].x; v[1] += a1[g].y; v[2] += a1[g].z; v[3] += a1[g].w; }
@@ -538,7 +552,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
     uint32_t res_ph = 0;
     // the common case runs the branch-free epilogue_lean: TMA store, plain epilogue, one output, residuals only via staging,
     // LeakyReLU slope within [0, 1] (max(v, slope v) form)
-    const bool lean = use_tma && epi == LSSVC_EPI_PLAIN && out2 == nullptr && (res1 == nullptr || r1_tma) && (res2 == nullptr || r2_tma) &&
+    const bool lean = use_tma && (epi == LSSVC_EPI_PLAIN || ((cout & 15) == 0 && !r2_tma && (gdn_pitch & 3) == 0)) && out2 == nullptr &&
+                      (res1 == nullptr || r1_tma) && (res2 == nullptr || r2_tma) &&
                       !(r2_tma && !r1_tma) && (!has_act || (slope >= 0.f && slope <= 1.f)) && (cout & 3) == 0;
     int u = 0;  // running unit counter (all units, both sets)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -586,9 +601,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slot * 2 * n_tile);
         if (lean && !(dbgf & 8)) {
           const float sl = has_act ? slope : 1.f;
-          if (r1_tma && r2_tma) epilogue_lean<true, true>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m);
-          else if (r1_tma) epilogue_lean<true, false>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m);
-          else epilogue_lean<false, false>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m);
+          if (epi != LSSVC_EPI_PLAIN) {
+            // gdn_x row of this thread's pixel, clamped into the image for the overhang of border tiles
+            const int cy = oy < p.Ho ? oy : p.Ho - 1, cx = ox < Wo ? ox : Wo - 1;
+            const float *gx_row = gdn_x + (static_cast<long long>(cy) * Wo + cx) * gdn_pitch;
+            if (epi == LSSVC_EPI_GDN) {
+              if (r1_tma) epilogue_lean<true, false, LSSVC_EPI_GDN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, gx_row);
+              else epilogue_lean<false, false, LSSVC_EPI_GDN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, gx_row);
+            } else {
+              if (r1_tma) epilogue_lean<true, false, LSSVC_EPI_IGDN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, gx_row);
+              else epilogue_lean<false, false, LSSVC_EPI_IGDN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, gx_row);
+            }
+          } else if (r1_tma && r2_tma) epilogue_lean<true, true, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr);
+          else if (r1_tma) epilogue_lean<true, false, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr);
+          else epilogue_lean<false, false, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr);
         }
         for (int n = 0; n < n_tile && !(dbgf & 8) && !lean; n += 16) {
           const int cg = n0 + n;

@@ -391,6 +391,61 @@ __global__ void __launch_bounds__(TPB) bilinear_resize_q_kernel(const float *__r
                              (hy * (hx * a[j].w + ax * b[j].w) + ay * (hx * d[j].w + ax * e[j].w)) * mul);
 }
 
+// Exact x2 upsampling (every resampler of the x2 configurations): one lane group per CELL of the input grid, i.e. the 2 x 2
+// input pixels (i, j) .. (i + 1, j + 1), i in [-1, Hi - 1], j in [-1, Wi - 1], clamped at the borders.  The four output pixels
+// (2i + 1 .. 2i + 2, 2j + 1 .. 2j + 2) interpolate exactly these four inputs (weights 0.75 / 0.25), so each input quad is loaded
+// once per four outputs instead of four times.  Every output still evaluates the same expression with the coordinates and
+// weights resize_coord gives it (bit-identical to bilinear_resize_kernel); at the borders the clamped neighbour carries weight 0.
+template <int Q>
+__global__ void __launch_bounds__(TPB) bilinear_up2_q_kernel(const float *__restrict__ in, uint32_t i_pitch, int Hi, int Wi,
+                                                             float *__restrict__ out, uint32_t o_pitch, uint32_t lpp,
+                                                             uint32_t n_threads, float mul) {
+  const uint32_t gid = blockIdx.x * TPB + threadIdx.x;
+  if (gid >= n_threads) return;
+  const uint32_t cell = gid / lpp, l = gid - cell * lpp;
+  const int cw = Wi + 1;
+  const int i = static_cast<int>(cell / static_cast<uint32_t>(cw)) - 1, j = static_cast<int>(cell % static_cast<uint32_t>(cw)) - 1;
+  const int ra = i < 0 ? 0 : i, rb = i + 1 < Hi ? i + 1 : Hi - 1, ca = j < 0 ? 0 : j, cb = j + 1 < Wi ? j + 1 : Wi - 1;
+  const float4 *p00 = reinterpret_cast<const float4 *>(in + (static_cast<size_t>(ra) * Wi + ca) * i_pitch) + l;
+  const float4 *p01 = reinterpret_cast<const float4 *>(in + (static_cast<size_t>(ra) * Wi + cb) * i_pitch) + l;
+  const float4 *p10 = reinterpret_cast<const float4 *>(in + (static_cast<size_t>(rb) * Wi + ca) * i_pitch) + l;
+  const float4 *p11 = reinterpret_cast<const float4 *>(in + (static_cast<size_t>(rb) * Wi + cb) * i_pitch) + l;
+  float4 a[Q], b[Q], d[Q], e[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    a[q] = __ldg(p00 + q * lpp);
+    b[q] = __ldg(p01 + q * lpp);
+    d[q] = __ldg(p10 + q * lpp);
+    e[q] = __ldg(p11 + q * lpp);
+  }
+  const int Ho = 2 * Hi, Wo = 2 * Wi;
+#pragma unroll
+  for (int dy = 1; dy <= 2; ++dy) {
+    const int oy = 2 * i + dy;
+    if (oy < 0 || oy >= Ho) continue;
+    int y0, y1;
+    float ay;
+    resize_coord(oy, 0.5f, Hi, y0, y1, ay);
+    const float hy = 1.f - ay;
+#pragma unroll
+    for (int dx = 1; dx <= 2; ++dx) {
+      const int ox = 2 * j + dx;
+      if (ox < 0 || ox >= Wo) continue;
+      int x0, x1;
+      float ax;
+      resize_coord(ox, 0.5f, Wi, x0, x1, ax);
+      const float hx = 1.f - ax;
+      float4 *o = reinterpret_cast<float4 *>(out + (static_cast<size_t>(oy) * Wo + ox) * o_pitch) + l;
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        o[q * lpp] = make_float4((hy * (hx * a[q].x + ax * b[q].x) + ay * (hx * d[q].x + ax * e[q].x)) * mul,
+                                 (hy * (hx * a[q].y + ax * b[q].y) + ay * (hx * d[q].y + ax * e[q].y)) * mul,
+                                 (hy * (hx * a[q].z + ax * b[q].z) + ay * (hx * d[q].z + ax * e[q].z)) * mul,
+                                 (hy * (hx * a[q].w + ax * b[q].w) + ay * (hx * d[q].w + ax * e[q].w)) * mul);
+    }
+  }
+}
+
 template <bool MAX>
 __global__ void __launch_bounds__(TPB) pool2_4_kernel(const float *__restrict__ in, uint32_t i_pitch, int Wi,
                                                       float *__restrict__ out, uint32_t o_pitch, int Wo, uint32_t cv, uint32_t total) {
@@ -714,7 +769,17 @@ extern "C" int32_t lssvc_bilinear_resize(const lssvc_view *in, float scale, cons
 #define LSSVC_RESIZE_Q(QQ)                                                                                               \
   bilinear_resize_q_kernel<QQ><<<grid, TPB, 0, s>>>(in->ptr, in->pitch, in->H, in->W, out->ptr, out->pitch, out->W, lpp, n_threads, \
                                                     rh, rw, scale)
-    if (legacy_gather()) {
+    if (!legacy_gather() && out->H == 2 * in->H && out->W == 2 * in->W && in->H > 1 && in->W > 1 &&
+        static_cast<long long>(in->H + 1) * (in->W + 1) * lpp < (1LL << 32)) {
+      const uint32_t cells = static_cast<uint32_t>(in->H + 1) * static_cast<uint32_t>(in->W + 1) * lpp, cgrid = (cells + TPB - 1) / TPB;
+#define LSSVC_UP2_Q(QQ) \
+  bilinear_up2_q_kernel<QQ><<<cgrid, TPB, 0, s>>>(in->ptr, in->pitch, in->H, in->W, out->ptr, out->pitch, lpp, cells, scale)
+      if (q == 4) LSSVC_UP2_Q(4);
+      else if (q == 3) LSSVC_UP2_Q(3);
+      else if (q == 2) LSSVC_UP2_Q(2);
+      else LSSVC_UP2_Q(1);
+#undef LSSVC_UP2_Q
+    } else if (legacy_gather()) {
       bilinear_resize4_kernel<<<(total + TPB * 2 - 1) / (TPB * 2), TPB, 0, s>>>(in->ptr, in->pitch, in->H, in->W, out->ptr, out->pitch,
                                                                                out->W, cv, total, rh, rw, scale);
     } else if (q == 4) {
