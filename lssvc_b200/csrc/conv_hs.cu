@@ -853,8 +853,10 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
 
   // output-channel tiling: equal tiles of at most 128 channels
   int n_tile = c->n_pad;
-  if (n_tile > 128) {
-    n_tile = 128;
+  const char *nt_str = getenv("LSSVC_HS_NTILE");  // A/B switch: cap of the channel tile
+  const int nt_cap = nt_str && atoi(nt_str) >= 16 ? atoi(nt_str) : 128;
+  if (n_tile > nt_cap) {
+    n_tile = nt_cap;
     while (n_tile >= 16 && (c->n_pad % n_tile)) n_tile -= 16;
     LSSVC_REQUIRE(n_tile >= 16, "conv_hs: cannot tile n_pad=%d", c->n_pad);
   }

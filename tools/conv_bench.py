@@ -38,6 +38,8 @@ EXTRA = [
     ("study 3x3 64->32 @1/2", [64], 32, 3, 1, 576, 960, False),
     ("study 3x3 64->16 @1/2", [64], 16, 3, 1, 576, 960, False),
     ("study 3x3 64->96 @1/2", [64], 96, 3, 1, 576, 960, False),
+    ("study 1x1 128->512 @1/4", [128], 512, 1, 1, 288, 480, False),
+    ("study 1x1 512->128 @1/4", [512], 128, 1, 1, 288, 480, False),
 ]
 
 
