@@ -260,6 +260,23 @@ int32_t lssvc_eb_quant(const lssvc_view *z, const float *coef, const lssvc_view 
 /* sum of squared error between two views (PSNR statistics gathered over NCCL) */
 int32_t lssvc_sse(const lssvc_view *a, const lssvc_view *b, double *out, void *stream);
 
+/* ---- front end of the frame loop (test.py:185-199, 253-254): planar fp32 [C][H][W], the layout of the tensors
+ * test.py hands to the models ---------------------------------------------------------------------------------------------- */
+/* One 8-bit YUV 4:2:0 frame (YUVReader.read_one_frame, video_reader.py:139-155: y [H][W], uv [2][H/2][W/2], all device
+ * pointers) -> RGB [3][Hp][Wp] in [0, 1], zero padded on the right / bottom (F.pad(rgb, P_HR), test.py:192-197):
+ * planes / 255, chroma x2 like scipy.ndimage.zoom(uv, (1, 2, 2), order=1), BT.709, clip (ycbcr420_to_rgb, functional.py:42-58). */
+int32_t lssvc_yuv420_to_rgb(const uint8_t *y, const uint8_t *uv, int32_t H, int32_t W, float *rgb, int32_t Hp, int32_t Wp,
+                            void *stream);
+/* One separable pass of the MATLAB-compatible resize (resize_1d, utils/core.py:268-337; imresize runs it over rows, then
+ * columns: core.py:417-418): out[c][i][x] = sum_k w[i*K + k] * in[c][taps[i*K + k]][x] for dim = 0 (rows; out is
+ * [C][n_out][Wi]) or the same along x for dim = 1 (out is [C][Hi][n_out]).  w / taps: the normalised kernel weights and the
+ * reflect-resolved source indices of every output sample (they depend on the sizes only; lssvc_b200/frontend.py builds them
+ * as core.py:299-317 does).  clamp01 != 0 applies the .clamp_(0, 1) of test.py:199. */
+int32_t lssvc_resample_1d(const float *in, int32_t C, int32_t Hi, int32_t Wi, int32_t dim, const float *w, const int32_t *taps,
+                          int32_t K, int32_t n_out, float *out, int32_t clamp01, void *stream);
+/* sum of (a - b)^2 over n floats into *out (double; zeroed first): PSNR = 10 log10(n / sum) (test.py:115-118) */
+int32_t lssvc_sse_flat(const float *a, const float *b, int64_t n, double *out, void *stream);
+
 /* ---- rANS entropy coder (host code; src/cpp/rans/rans_interface.cpp, src/cpp/ops/ops.cpp) --- */
 typedef struct lssvc_rans_encoder lssvc_rans_encoder;
 typedef struct lssvc_rans_decoder lssvc_rans_decoder;

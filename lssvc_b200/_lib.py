@@ -100,6 +100,10 @@ _SIGNATURES = {
     "lssvc_bitparm_quant": (c_int32, [_PV, c_void_p, _PV, c_void_p, c_void_p, c_void_p]),
     "lssvc_eb_quant": (c_int32, [_PV, c_void_p, _PV, c_void_p, c_void_p, c_void_p]),
     "lssvc_sse": (c_int32, [_PV, _PV, c_void_p, c_void_p]),
+    "lssvc_yuv420_to_rgb": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
+    "lssvc_resample_1d": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                    c_int32, c_void_p]),
+    "lssvc_sse_flat": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "lssvc_pmf_to_quantized_cdf": (c_int32, [POINTER(c_float), c_int32, c_int32, POINTER(c_uint32)]),
     "lssvc_rans_encoder_new": (c_void_p, []),
     "lssvc_rans_encoder_free": (None, [c_void_p]),
