@@ -11,7 +11,7 @@ dev = torch.device("cuda:0")
 H, W = 1080, 1920
 peak = 6544.7
 try:
-    peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbps_burst"]
+    peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
 rng = np.random.default_rng(0)
