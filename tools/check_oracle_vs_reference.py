@@ -14,7 +14,7 @@ from lssvc_b200 import nets, synth  # noqa: E402
 from oracle import lssvc_oracle as orc  # noqa: E402
 
 
-def main(H=128, W=128, n_frames=4, seed=0):
+def main(H=128, W=128, n_frames=4, seed=0, ratio=2.0):
     torch.manual_seed(0)
     IntraSS, LSSVC_extend = ref_harness.import_reference()
     sd_i = nets.ParamBag(nets.intra_ss_spec(), seed=seed, gains=nets.model_gains("I")).state_dict()
@@ -22,13 +22,13 @@ def main(H=128, W=128, n_frames=4, seed=0):
     ref_i = IntraSS.from_state_dict(dict(sd_i)).eval()
     ref_p = LSSVC_extend().eval()
     ref_p.load_dict(dict(sd_p))
-    frames = synth.make_sequence(H, W, n_frames, seed=seed)
+    frames = synth.make_sequence(H, W, n_frames, seed=seed, ratio=ratio)
     worst = 0.0
     with torch.no_grad():
         dpb_r = dpb_o = None
         for t, (x_bl, x_el) in enumerate(frames):
-            ref_i.set_scale_information(2.0, (H, W), (0, 0, 0, 0))
-            ref_p.set_scale_information(2.0, (H, W), (0, 0, 0, 0))
+            ref_i.set_scale_information(ratio, (H, W), (0, 0, 0, 0))
+            ref_p.set_scale_information(ratio, (H, W), (0, 0, 0, 0))
             t0 = time.time()
             if t == 0:
                 r = ref_i.encode_decode(x_bl, x_el, None, None, x_bl.shape[2], x_bl.shape[3], H, W)
@@ -41,7 +41,7 @@ def main(H=128, W=128, n_frames=4, seed=0):
                          "ref_feature_el": o["feature_el"]}
             else:
                 r = ref_p.encode_decode(x_bl, x_el, dpb_r, None, None, W, H, x_bl.shape[3], x_bl.shape[2])
-                o = orc.lssvc(sd_p, x_bl, x_el, dpb_o, (H, W), 2.0)
+                o = orc.lssvc(sd_p, x_bl, x_el, dpb_o, (H, W), ratio)
                 pairs = [(k, r["dpb"][k], o["dpb"][k]) for k in r["dpb"]] + [("mv_hat", r["mv_hat"], o["mv_hat"]),
                                                                              ("warp_frame", r["warp_frame"], o["warp_frame"])]
                 dpb_r, dpb_o = r["dpb"], o["dpb"]
@@ -72,4 +72,7 @@ def main(H=128, W=128, n_frames=4, seed=0):
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-    main(n_frames=n)
+    if len(sys.argv) > 2:          # e.g. "3 1.5 192": the x1_5 ratio of recommend_test_config.json at EL 192x192 / BL 128x128
+        main(H=int(sys.argv[3]), W=int(sys.argv[3]), n_frames=n, ratio=float(sys.argv[2]))
+    else:
+        main(n_frames=n)
