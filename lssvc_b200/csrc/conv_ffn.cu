@@ -49,6 +49,7 @@ struct alignas(64) FfnParams {
   int in_off, stage_off;  // smem offsets (after the resident weights)
   float scale1, scale2;   // 2^-shift of W1 / W2
   float slope1, slope2;
+  long long *prof;  // DBG variant (LSSVC_FFN_DBG=1): [6 roles][8] wait-cycle counters of CTA 0
 };
 
 __device__ __forceinline__ void split_pair_f(float a, float b, uint32_t &hi, uint32_t &lo) {
@@ -67,7 +68,21 @@ __device__ __forceinline__ uint32_t tile_addr(uint32_t base, int slab_w, int m, 
   return row + ((static_cast<uint32_t>(c % slab_w) << 2) ^ swz);
 }
 
+// DBG = true: instrumented variant (per-role wait-time counters), never on the product path
+template <bool DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_constant__ FfnParams p) {
+  long long prof[6] = {0, 0, 0, 0, 0, 0};
+  const long long t_begin = DBG ? clock64() : 0;
+#define FFN_WAIT(slot, bar, parity)       \
+  do {                                    \
+    if (DBG) {                            \
+      const long long t0__ = clock64();   \
+      ptx::mbar_wait(bar, parity);        \
+      prof[slot] += clock64() - t0__;     \
+    } else {                              \
+      ptx::mbar_wait(bar, parity);        \
+    }                                     \
+  } while (0)
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t in_full[IN_BUFS], in_empty[IN_BUFS];
   __shared__ uint64_t ao_full, ao_empty, w_full;
@@ -133,7 +148,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
       uint32_t iph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-        ptx::mbar_wait(b_in_empty + 8 * ib, iph ^ 1u);
+        FFN_WAIT(0, b_in_empty + 8 * ib, iph ^ 1u);
         ptx::mbar_expect_tx(b_in_full + 8 * ib, in_bytes);
         for (int s = 0; s < p.n_slabs; ++s)
           ptx::tma_load_3d(in_s + static_cast<uint32_t>(ib) * in_bytes + static_cast<uint32_t>(s) * (128u * p.slab_w * 4u),
@@ -178,8 +193,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
       uint32_t dy_ph = 0;
       ptx::mbar_wait(b_w_full, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(b_ao_full, tphase);
-        ptx::mbar_wait(b_dy_empty + 8 * tb, dy_ph ^ 1u);
+        FFN_WAIT(0, b_ao_full, tphase);
+        FFN_WAIT(1, b_dy_empty + 8 * tb, dy_ph ^ 1u);
         ptx::tc_fence_after();
         uint32_t w1p = w1_16, w2p = w2_16;  // running weight descriptors of GEMM-a / GEMM-b
         const uint32_t dy = t_dy + static_cast<uint32_t>(tb * 2 * C);
@@ -187,7 +202,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
         for (int ja = 0; ja <= n_chunks; ++ja) {
           if (ja < n_chunks) {
             const uint32_t b = static_cast<uint32_t>(ja) & 1u;
-            ptx::mbar_wait(b_dh_empty + 8 * b, ((dh_mask >> b) & 1u) ^ 1u);
+            FFN_WAIT(2, b_dh_empty + 8 * b, ((dh_mask >> b) & 1u) ^ 1u);
             ptx::tc_fence_after();
             const uint32_t d = t_dh + 64u * b;
             for (int ks = 0; ks < KS1; ++ks) {
@@ -203,7 +218,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
           if (ja > 0) {
             const int j = ja - 1;
             const uint32_t b = static_cast<uint32_t>(j) & 1u;
-            ptx::mbar_wait(b_ah_full + 8 * b, (ah_mask >> b) & 1u);
+            FFN_WAIT(3, b_ah_full + 8 * b, (ah_mask >> b) & 1u);
             ptx::tc_fence_after();
             const uint32_t a = t_ah + 32u * b;
 #pragma unroll
@@ -233,9 +248,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
     int ib = 0;
     uint32_t iph = 0, tphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      ptx::mbar_wait(b_in_full + 8 * ib, iph);
+      FFN_WAIT(0, b_in_full + 8 * ib, iph);
       const uint32_t tile_s = in_s + static_cast<uint32_t>(ib) * in_bytes;
-      ptx::mbar_wait(b_ao_empty, tphase ^ 1u);  // the previous tile's GEMM-a MMAs have read A_o
+      FFN_WAIT(1, b_ao_empty, tphase ^ 1u);  // the previous tile's GEMM-a MMAs have read A_o
       ptx::tc_fence_after();
       for (int ks = 0; ks < KS1; ++ks) {
         float4 v[4];
@@ -280,7 +295,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
         float4 bv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) bv[i] = __ldg(bq + i);
-        ptx::mbar_wait(b_dh_full + 8 * b, use & 1u);
+        FFN_WAIT(0, b_dh_full + 8 * b, use & 1u);
         ptx::tc_fence_after();
         uint32_t r1[16], r2[16];
         ptx::tmem_ld16(src1, r1);
@@ -303,7 +318,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
           split_pair_f(h0, h1, hi[2 * i], lo[2 * i]);
           split_pair_f(h2, h3, hi[2 * i + 1], lo[2 * i + 1]);
         }
-        ptx::mbar_wait(b_ah_empty + 8 * b, (use & 1u) ^ 1u);  // GEMM-b of this buffer's previous chunk is done
+        FFN_WAIT(1, b_ah_empty + 8 * b, (use & 1u) ^ 1u);  // GEMM-b of this buffer's previous chunk is done
         ptx::tc_fence_after();
         ptx::tmem_st8(dst_hi, hi);
         ptx::tmem_st8(dst_lo, lo);
@@ -327,13 +342,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
       const int oy = ty * TILE_H + h, ox = tx * TILE_W + w;
-      ptx::mbar_wait(b_in_full + 8 * ib, iph);  // acquire the TMA-written o tile for the residual reads below
+      FFN_WAIT(0, b_in_full + 8 * ib, iph);  // acquire the TMA-written o tile for the residual reads below
       const bool valid = oy < p.H && ox < p.W;
       const uint32_t tile_s = in_s + static_cast<uint32_t>(ib) * in_bytes;
       // staging is free once the previous tile's TMA store has read it
       if (store_thread) ptx::bulk_wait_read_all();
       ptx::named_bar_sync(2, 128);
-      ptx::mbar_wait(b_dy_full + 8 * tb, dy_ph);
+      FFN_WAIT(1, b_dy_full + 8 * tb, dy_ph);
       ptx::tc_fence_after();
       const uint32_t src = t_dy + static_cast<uint32_t>(tb * 2 * C) + lane_off;
       for (int n = 0; n < C; n += 16) {
@@ -392,6 +407,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
     if (store_thread) ptx::bulk_wait_all();
   }
 
+  if (DBG && p.prof && blockIdx.x == 0 && lane == 0) {
+    // rows: 0 input TMA, 1 MMA issuer, 2 splitter warp 4, 3 hidden warp 8 (buffer 0), 4 hidden warp 16 (buffer 1), 5 output warp 24
+    const int row = warp == 0 ? 0 : warp == 1 ? 1 : warp == 4 ? 2 : warp == 8 ? 3 : warp == 16 ? 4 : warp == 24 ? 5 : -1;
+    if (row >= 0) {
+      for (int i = 0; i < 6; ++i) p.prof[row * 8 + i] = prof[i];
+      p.prof[row * 8 + 7] = clock64() - t_begin;
+    }
+  }
+#undef FFN_WAIT
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -485,13 +509,35 @@ extern "C" int32_t lssvc_conv_ffn(const lssvc_ffn *f, void *stream) {
     return LSSVC_ERR_CUDA;
   }
   if (!g_attr_set) {
-    LSSVC_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(conv_ffn_kernel),
+    LSSVC_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(conv_ffn_kernel<false>),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LSSVC_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(conv_ffn_kernel<true>),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     g_attr_set = true;
   }
   const int total_tiles = p.tiles_x * p.tiles_y;
   const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
-  conv_ffn_kernel<<<grid, NUM_THREADS, smem, lssvc::as_stream(stream)>>>(p);
+  // instrumented variant (tools/ffn_bench.py): LSSVC_FFN_DBG=1 prints the per-role wait counters of CTA 0 after a device sync
+  const char *dbg_str = getenv("LSSVC_FFN_DBG");
+  if (dbg_str != nullptr && atoi(dbg_str) != 0) {
+    long long *prof_dev = nullptr;
+    LSSVC_CUDA(cudaMalloc(&prof_dev, 48 * sizeof(long long)));
+    LSSVC_CUDA(cudaMemset(prof_dev, 0, 48 * sizeof(long long)));
+    p.prof = prof_dev;
+    conv_ffn_kernel<true><<<grid, NUM_THREADS, smem, lssvc::as_stream(stream)>>>(p);
+    LSSVC_LAUNCHED();
+    long long h[48];
+    LSSVC_CUDA(cudaStreamSynchronize(lssvc::as_stream(stream)));
+    LSSVC_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(prof_dev);
+    static const char *names[6] = {"input_tma [wait in_empty]", "mma       [wait ao_full, dy_empty, dh_empty, ah_full]", "splitter  [wait in_full, ao_empty]",
+                                   "hidden b0 [wait dh_full, ah_empty]", "hidden b1 [wait dh_full, ah_empty]", "output    [wait in_full, dy_full]"};
+    fprintf(stderr, "conv_ffn prof (CTA 0, cycles; C=%d hidden=%d tiles/cta~%d):\n", C, Hd, (total_tiles + grid - 1) / grid);
+    for (int r = 0; r < 6; ++r)
+      fprintf(stderr, "  %-58s total %8lld | %8lld %8lld %8lld %8lld\n", names[r], h[r * 8 + 7], h[r * 8], h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3]);
+    return LSSVC_OK;
+  }
+  conv_ffn_kernel<false><<<grid, NUM_THREADS, smem, lssvc::as_stream(stream)>>>(p);
   LSSVC_LAUNCHED();
   return LSSVC_OK;
 }
