@@ -144,3 +144,37 @@ def test_1080p_bitstream_round_trip(nets, tmp_path):
         ratio = 8 * n / est[f"bit_{layer}"]
         print(f"1080p P-frame {layer}: {n} B written, {ratio:.4f} x the estimated bits")
         assert 0.5 < ratio < 2.0
+
+
+def test_4k_stream_round_trip(cuda_device, tmp_path):
+    """BASELINE config 5 (EL 3840x2160 padded to 2176x3840, BL 1088x1920): one I-frame and one P-frame through the estimate pass
+    and through the bitstream path — the stress case of the warp, conv and entropy kernels (8.9 M EL pixels, 32-bit index
+    limits, 9 M entropy-coded symbols per P-frame).  The decoder must rebuild the forward pass bit for bit."""
+    from lssvc_b200 import IntraSS, LSSVC_extend, frontend, synth
+    pad = frontend.get_interlayer_padding(2160, 3840, 2)
+    Hk, Wk = pad["HR_padded_size"]
+    assert (Hk, Wk) == (2176, 3840)
+    net_i = IntraSS(seed=0).to(cuda_device)
+    net_p = LSSVC_extend(seed=1).to(cuda_device)
+    for n in (net_i, net_p):
+        n.set_scale_information(2.0, (Hk, Wk), (0, 0, 0, 0))
+        n.update(force=True)
+    frames = synth.make_sequence(Hk, Wk, 2, seed=4)
+    x_bl, x_el = (t.to(cuda_device) for t in frames[0])
+    est = net_i.encode_decode(x_bl, x_el, None, None, Hk // 2, Wk // 2, Hk, Wk)
+    for k in ("x_hat_bl", "x_hat_el", "feature_el"):
+        assert torch.isfinite(est[k]).all()
+    r = net_i.encode_decode(x_bl, x_el, str(tmp_path / "i_bl.bin"), str(tmp_path / "i_el.bin"), Hk // 2, Wk // 2, Hk, Wk)
+    assert torch.equal(r["x_hat_el"], est["x_hat_el"]) and torch.equal(r["x_hat_bl"], est["x_hat_bl"])
+    assert r["bit_el"] == 8 * (tmp_path / "i_el.bin").stat().st_size
+    dpb = {"ref_frame_bl": est["x_hat_bl"].clamp(0, 1), "ref_frame_el": est["x_hat_el"].clamp(0, 1), "ref_feature_bl": None,
+           "ref_feature_el": est["feature_el"]}
+    x_bl, x_el = (t.to(cuda_device) for t in frames[1])
+    fresh = lambda: {k: (None if v is None else v.clone()) for k, v in dpb.items()}
+    est = net_p.encode_decode(x_bl, x_el, fresh(), None, None, Wk, Hk, Wk // 2, Hk // 2)
+    r = net_p.encode_decode(x_bl, x_el, fresh(), str(tmp_path / "p_bl.bin"), str(tmp_path / "p_el.bin"), Wk, Hk, Wk // 2, Hk // 2)
+    for k in ("ref_frame_el", "ref_feature_el", "ref_feature_bl"):
+        assert torch.isfinite(est["dpb"][k]).all()
+        assert torch.equal(r["dpb"][k], est["dpb"][k]), f"4K P-frame: decoder differs from the forward pass in {k}"
+    print(f"4K P-frame: BL {(tmp_path / 'p_bl.bin').stat().st_size} B, EL {(tmp_path / 'p_el.bin').stat().st_size} B written; "
+          f"estimated {est['bit_bl'] / 8:.0f} / {est['bit_el'] / 8:.0f} B")
