@@ -231,6 +231,9 @@ class Engine(nets.ParamBag):
         if t.device != self.device:
             t = t.to(self.device)
         C = t.shape[1]
+        shared = View.from_channels_last(t)       # a feature map this package handed out (View.to_nchw_shared): no pass
+        if shared is not None:
+            return shared
         return View.from_nchw(t.float(), C_view=ops.round_up(C, 8))
 
     # ---- blocks -----------------------------------------------------------------------------------------------

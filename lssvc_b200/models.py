@@ -286,7 +286,7 @@ class IntraSS(Engine):
              c1=c1, c2=c2, c3=c3)
         bit_bl, bit_el = bits.read()
         result = {"bit_bl": bit_bl, "bit_el": bit_el, "x_hat_bl": x_hat_bl.to_nchw(), "x_hat_el": x_hat.to_nchw(),
-                  "feature_el": feature.to_nchw()}
+                  "feature_el": feature.to_nchw_shared()}
         if _native:
             result["_native"] = {"x_hat_bl": x_hat_bl, "x_hat_el": x_hat, "feature_el": feature, "y_hat_bl": y_hat_bl,
                                  "y": y, "z_hat": z_hat, "params_el": prm, "y_bl": y_bl, "ctx": (c1, c2, c3)}
@@ -756,8 +756,11 @@ class LSSVC(Engine):
 
     def _frame_result(self, v, bit_bl, bit_el, token=None):
         """Views of one coded frame -> the reference's result dict (fresh NCHW tensors the caller may mutate)."""
-        out = {"ref_frame_bl": v["bl_recon"].to_nchw(), "ref_feature_bl": v["bl_feature"].to_nchw(),
-               "ref_frame_el": v["recon"].to_nchw(), "ref_feature_el": v["feature"].to_nchw()}
+        # the 64-channel feature maps leave as channels_last tensors sharing the NHWC buffers (no conversion pass) unless they
+        # are a graph's static outputs, which the next replay overwrites
+        feat = (lambda x: x.to_nchw()) if token is not None else (lambda x: x.to_nchw_shared())
+        out = {"ref_frame_bl": v["bl_recon"].to_nchw(), "ref_feature_bl": feat(v["bl_feature"]),
+               "ref_frame_el": v["recon"].to_nchw(), "ref_feature_el": feat(v["feature"])}
         # NHWC originals of the features: the next frame reads them directly when the caller passes the tensors back
         # untouched.  token: (graph entry, generation) when the views are a graph's static outputs, valid until its next replay.
         out["_native"] = {"ref_feature_bl": (v["bl_feature"], out["ref_feature_bl"], out["ref_feature_bl"]._version, token),

@@ -83,6 +83,25 @@ class View:
         _lib.check(lib.lssvc_nhwc_to_nchw(byref(v.c()), _ptr(out), _stream()), "nhwc_to_nchw")
         return out
 
+    def to_nchw_shared(self):
+        """[1, real, H, W] tensor in torch's channels_last memory format that SHARES this view's buffer (no copy) when the
+        view is a whole unpadded buffer; a contiguous copy otherwise.  For the wide feature maps of the DPB: the caller gets a
+        regular tensor (in-place edits included), the next frame re-imports it without a pass (View.from_channels_last)."""
+        if self.coff == 0 and self.pitch == self.C and self.real == self.C and self.buf.numel() == self.H * self.W * self.C:
+            return self.buf.view(1, self.H, self.W, self.C).permute(0, 3, 1, 2)
+        return self.to_nchw()
+
+    @staticmethod
+    def from_channels_last(t):
+        """Zero-copy NHWC view of a [1, C, H, W] fp32 tensor stored channels_last (what to_nchw_shared hands out); None if
+        the tensor is not of that kind."""
+        if (t.dim() == 4 and t.shape[0] == 1 and t.dtype == torch.float32 and t.shape[1] % 8 == 0 and t.shape[1] > 1
+                and t.stride() == (t.shape[1] * t.shape[2] * t.shape[3], 1, t.shape[3] * t.shape[1], t.shape[1])
+                and t.data_ptr() % 16 == 0):
+            _, C, H, W = t.shape
+            return View(t.permute(0, 2, 3, 1).reshape(-1), H, W, C, C)
+        return None
+
     @staticmethod
     def from_nchw(t, C_view=None, out=None):
         """[1, C, H, W] (or [C, H, W]) contiguous fp32 -> NHWC view with C_view >= C channels (rest zero)."""
