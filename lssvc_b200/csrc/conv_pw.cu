@@ -188,6 +188,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_co
     const int in_w = p.in_w;
     const int rc = dw ? (h + 1) * in_w + (w + 1) : m;  // row of this pixel in the input tile
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const bool s32 = p.in_slab_w == 32;
+    const uint32_t row_bytes = s32 ? 128u : 64u;
     int ib = 0, b = 0;
     uint32_t iph = 0, ph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -198,16 +200,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_co
       const uint32_t dst = t_a + static_cast<uint32_t>(b * Cin) + lane_off;
       for (int ks = sg; ks < KS; ks += 4) {
         float4 v[4];
+        // a 16-channel slice lies inside one slab: slab base and chunk offset once per slice, row base and swizzle once per
+        // tap (slab_addr's divisions in the tap loop were 20 % of the kernel's instructions)
+        const uint32_t c0 = static_cast<uint32_t>(ks) * 16u;
+        const uint32_t slab_base = tile_s + (s32 ? (c0 >> 5) : (c0 >> 4)) * in_slab_stride;
+        const uint32_t coff0 = s32 ? ((c0 & 31u) << 2) : 0u;
         if (dw) {
+          const uint32_t wb = dw_s + c0 * 4u;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = ptx::lds_f4(dw_s + static_cast<uint32_t>(9 * Cin + ks * 16 + 4 * i) * 4u);  // bias
+          for (int i = 0; i < 4; ++i) v[i] = ptx::lds_f4(wb + static_cast<uint32_t>(9 * Cin + 4 * i) * 4u);  // bias
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            const int r = rc + (t / 3 - 1) * in_w + (t % 3 - 1);
+            const uint32_t r = static_cast<uint32_t>(rc + (t / 3 - 1) * in_w + (t % 3 - 1));
+            const uint32_t rb = slab_base + r * row_bytes;
+            const uint32_t sw = (s32 ? (r & 7u) : ((r >> 1) & 3u)) << 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 x4 = ptx::lds_f4(slab_addr(tile_s, p.in_slab_w, in_slab_stride, r, ks * 16 + 4 * i));
-              const float4 w4 = ptx::lds_f4(dw_s + static_cast<uint32_t>(t * Cin + ks * 16 + 4 * i) * 4u);
+              const float4 x4 = ptx::lds_f4(rb + ((coff0 + 16u * i) ^ sw));
+              const float4 w4 = ptx::lds_f4(wb + static_cast<uint32_t>(t * Cin + 4 * i) * 4u);
               v[i].x = fmaf(x4.x, w4.x, v[i].x);
               v[i].y = fmaf(x4.y, w4.y, v[i].y);
               v[i].z = fmaf(x4.z, w4.z, v[i].z);
@@ -215,8 +225,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_co
             }
           }
         } else {
+          const uint32_t r = static_cast<uint32_t>(rc);
+          const uint32_t rb = slab_base + r * row_bytes;
+          const uint32_t sw = (s32 ? (r & 7u) : ((r >> 1) & 3u)) << 4;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = ptx::lds_f4(slab_addr(tile_s, p.in_slab_w, in_slab_stride, rc, ks * 16 + 4 * i));
+          for (int i = 0; i < 4; ++i) v[i] = ptx::lds_f4(rb + ((coff0 + 16u * i) ^ sw));
         }
         uint32_t hi[8], lo[8];
 #pragma unroll
