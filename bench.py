@@ -7,7 +7,9 @@ semantics: estimated bitrate).  GOPs are independent, so with N > 1 every rank c
 
   value : frames/s with the frames already resident in HBM (device tensors in, device tensors out, bits read back)
   e2e   : frames/s through the same API from PINNED HOST buffers: H2D of (x_bl, x_el) and D2H of both reconstructions
-          + bits inside the timed region — what test.py's frame loop does (test.py:185-191, 260-263)
+          + bits inside the timed region — what test.py's frame loop does (test.py:185-191, 260-263); the copies run on
+          two copy streams, overlapped with the coding of the neighbouring frames (software pipelining, all inside the
+          timed region)
   --impl reference : the reference's algorithm on the host CPU (oracle port, all host threads), bounded sample.
 """
 import argparse
@@ -111,14 +113,18 @@ class Coder:
         return r["bit_bl"], r["bit_el"], self.dpb["ref_frame_bl"], self.dpb["ref_frame_el"]
 
 
-def timed_loop(torch, dist, world, fn, first, count):
-    """barrier + synchronize, CUDA events around exactly `count` steps on the launching stream, max over ranks."""
+def timed_loop(torch, dist, world, fn, first, count, finish=None):
+    """barrier + synchronize, CUDA events around exactly `count` steps on the launching stream, max over ranks.
+    finish: called before the closing event (the e2e loop makes the launching stream wait for its copy streams there, so
+    that every copy of the timed steps lies between the two events)."""
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     rows = [fn(first + i) for i in range(count)]
+    if finish is not None:
+        finish()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -273,13 +279,48 @@ def main():
     out_bl = torch.empty(1, 3, H // 2, W // 2).pin_memory()
     out_el = torch.empty(1, 3, H, W).pin_memory()
 
+    # The e2e loop is software-pipelined the way a real encoder front end is: the pinned-host -> device copy of frame t + 1
+    # runs on a copy stream while frame t is coded, the device -> pinned-host copy of frame t's reconstructions runs on a
+    # second copy stream while frame t + 1 is coded; the bit counts of frame t are read (a device -> host sync) before
+    # step t returns.  Every copy of a timed step is issued inside the timed region and completes before its closing event.
+    in_stream, out_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    in_bufs = [(torch.empty_like(devf[0][0]), torch.empty_like(devf[0][1])) for _ in range(2)]
+    in_free = [torch.cuda.Event(), torch.cuda.Event()]
+    in_ready = {}
+    out_done = torch.cuda.Event()
+    out_keep = []
+
+    def prefetch(idx):
+        if idx in in_ready or idx >= len(host):
+            return
+        slot = idx % 2
+        in_stream.wait_event(in_free[slot])          # the frame that last used the slot has been coded
+        with torch.cuda.stream(in_stream):
+            in_bufs[slot][0].copy_(host[idx][0], non_blocking=True)
+            in_bufs[slot][1].copy_(host[idx][1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(in_stream)
+        in_ready[idx] = ev
+
     def step_host(idx):
-        x_bl, x_el = host[idx]
-        bb, be, rb, re = coder.step(idx, args.gop, x_bl.to(dev, non_blocking=True), x_el.to(dev, non_blocking=True))
-        out_bl.copy_(rb, non_blocking=True)
-        out_el.copy_(re, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        cur = torch.cuda.current_stream()
+        prefetch(idx)
+        cur.wait_event(in_ready.pop(idx))
+        prefetch(idx + 1)
+        x_bl, x_el = in_bufs[idx % 2]
+        bb, be, rb, re = coder.step(idx, args.gop, x_bl, x_el)      # reads the bit counters: syncs the coding stream
+        in_free[idx % 2].record(cur)
+        out_stream.wait_stream(cur)
+        with torch.cuda.stream(out_stream):
+            out_bl.copy_(rb, non_blocking=True)
+            out_el.copy_(re, non_blocking=True)
+            out_done.record(out_stream)
+        out_keep[:] = [rb, re]                       # keep the sources alive until the copies have run
         return (idx, bb, be)
+
+    def e2e_finish():
+        torch.cuda.current_stream().wait_event(out_done)
+        in_ready.clear()
 
     # ---- device-resident throughput ("value") ---------------------------------------------------------------
     for i in range(W_):
@@ -292,7 +333,9 @@ def main():
     coder.dpb = None
     for i in range(W_):
         step_host(i)
-    ms_e2e, rows_e2e = timed_loop(torch, dist, world, step_host, W_, args.steps)
+    torch.cuda.synchronize()
+    in_ready.clear()                                 # the first timed step copies its own input inside the timed region
+    ms_e2e, rows_e2e = timed_loop(torch, dist, world, step_host, W_, args.steps, finish=e2e_finish)
 
     # ---- rate statistics gathered over NCCL (the only collective of the path) ---------------------------------
     t = torch.tensor(rows, dtype=torch.float64, device=dev)
