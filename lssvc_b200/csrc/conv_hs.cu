@@ -1061,10 +1061,12 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
                 p.halo_bytes, p.b_bytes, use_tma ? 2 * per_set : 0);
   p.halo_bufs = 2;
   p.slots = 2;
+  const char *hb_str = getenv("LSSVC_HS_HALOS");  // A/B switch: cap of the halo ring
+  const int halo_cap = hb_str && atoi(hb_str) >= 2 && atoi(hb_str) <= MAX_HALO ? atoi(hb_str) : MAX_HALO;
   for (bool grown = true; grown;) {
     grown = false;
     if (p.slots < MAX_SLOTS && p.slots <= p.halo_bufs + 1 && fits(p.halo_bufs, p.slots + 1, use_tma)) { ++p.slots; grown = true; }
-    if (p.halo_bufs < MAX_HALO && fits(p.halo_bufs + 1, p.slots, use_tma)) { ++p.halo_bufs; grown = true; }
+    if (p.halo_bufs < halo_cap && fits(p.halo_bufs + 1, p.slots, use_tma)) { ++p.halo_bufs; grown = true; }
   }
   p.use_tma = use_tma ? 1 : 0;
   p.stage_off = p.halo_bufs * p.halo_bytes + p.slots * p.b_bytes;
