@@ -9,6 +9,7 @@ and state_dict layout; tensors in and out are NCHW fp32 torch tensors, batch 1. 
 conversion and the output conversion runs in the kernels of liblssvc_b200.so; there is no PyTorch compute path.
 """
 import math
+import os
 
 import torch
 
@@ -17,6 +18,14 @@ from .engine import Engine
 from .nets import intra_ss_spec, lssvc_spec
 from .ops import View
 from .stream import decode_i, decode_p, encode_i, encode_p, filesize, get_downsampled_shape
+
+
+# Engine of the I-frame hyper-decoders (h_s of both layers: eight convolutions at 1/64 .. 1/16 resolution, < 0.1 % of the
+# frame's FLOPs).  Their output is the mean every latent is quantised against, so their rounding error turns directly into
+# symbol flips: on the fp32 CUDA cores the 1080p I-frame differs from the oracle in 67-69 of 1.30 M symbols (what the
+# all-fp32 engine gets: 64-68), on the tensor-core engine in 83-97 (tools/fullsize_parity.py, gpurun_out/fullsize4.log).
+# LSSVC_PRIOR_ENGINE= (empty) selects the default engine for A/B.
+PRIOR_ENGINE = os.environ.get("LSSVC_PRIOR_ENGINE", "simt") or None
 
 
 def _strip_module_prefix(sd):
@@ -163,11 +172,12 @@ class IntraSS(Engine):
 
     def _bl_params(self, z_hat):
         p = "base_layer_model."
-        g = self.conv(p + "h_s.0", z_hat, act=0.01, exact_in=True)
-        g = self.conv(p + "h_s.2.0", g, ps=True, act=0.01)
-        g = self.conv(p + "h_s.4", g, act=0.01)
-        g = self.conv(p + "h_s.6.0", g, ps=True, act=0.01)
-        return self.conv(p + "h_s.8", g)
+        e = PRIOR_ENGINE
+        g = self.conv(p + "h_s.0", z_hat, act=0.01, exact_in=True, engine=e)
+        g = self.conv(p + "h_s.2.0", g, ps=True, act=0.01, engine=e)
+        g = self.conv(p + "h_s.4", g, act=0.01, engine=e)
+        g = self.conv(p + "h_s.6.0", g, ps=True, act=0.01, engine=e)
+        return self.conv(p + "h_s.8", g, engine=e)
 
     def _bl_synthesis(self, y_hat):
         p = "base_layer_model."
@@ -232,9 +242,10 @@ class IntraSS(Engine):
 
     def _el_params(self, z_hat, y_hat_bl, c3):
         H, W = self.shape_hr
-        hyper = self.conv("h_s.0.0", z_hat, ps=True, act=0.01, exact_in=True)
-        hyper = self.conv("h_s.2.0", hyper, ps=True, act=0.01)
-        hyper = self.conv("h_s.4", hyper)
+        e = PRIOR_ENGINE
+        hyper = self.conv("h_s.0.0", z_hat, ps=True, act=0.01, exact_in=True, engine=e)
+        hyper = self.conv("h_s.2.0", hyper, ps=True, act=0.01, engine=e)
+        hyper = self.conv("h_s.4", hyper, engine=e)
         lp = self.seq2("layer_prior_resampler.conv_adaptor", y_hat_bl)
         lp = self.resize(lp, H // 16, W // 16)
         cp = self.conv("prior_fusion_net.context_parameters.0", c3, stride=2, act=0.1)
