@@ -1,0 +1,72 @@
+"""BASELINE config 1: IntraSS I-frame + LSSVC two-layer P-frames, one 12-frame GOP at 512x320 (BL 256x160), i.e. the padded
+sizes 384x512 / 192x256 the reference runs (common.py:48-86), estimate mode.  Every frame is coded from the ORACLE's DPB and
+teacher-forced on the oracle's symbols, so the twelve frames are twelve independent checks of the north-star tolerances
+(symbols >= 99.99 % equal over the GOP, reconstructions within 1e-3, per-layer bits within 0.1 %), including the P-after-P
+feature path (48-channel EL reference feature) over a full GOP of drift in the reference data."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOP = 12
+
+
+def test_cfg1_gop_against_oracle(cuda_device):
+    from lssvc_b200 import IntraSS, LSSVC_extend, frontend, synth
+    from oracle import lssvc_oracle as orc
+    pad = frontend.get_interlayer_padding(320, 512, 2)
+    H, W = pad["HR_padded_size"]
+    assert (H, W) == (384, 512) and pad["LR_padded_size"] == (192, 256)
+    dev = cuda_device
+    torch.set_num_threads(8)
+    net_i, net_p = IntraSS(seed=0), LSSVC_extend(seed=1)
+    sd_i = {k: v.clone() for k, v in net_i.state_dict().items()}
+    sd_p = {k: v.clone() for k, v in net_p.state_dict().items()}
+    net_i.to(dev)
+    net_p.to(dev)
+    for n in (net_i, net_p):
+        n.set_scale_information(2.0, (H, W), (0, 0, 0, 0))
+    frames = synth.make_sequence(H, W, GOP, seed=5)
+    bad = total = 0
+    worst = {"recon": 0.0, "bits": 0.0}
+    dpb = None
+    for t, (x_bl, x_el) in enumerate(frames):
+        with torch.no_grad():
+            if t == 0:
+                o = orc.intra_ss(sd_i, x_bl, x_el, (H, W))
+                q_ref = {"bl_z_hat": o["bl"]["z_hat"], "bl_y_q": torch.round(o["bl"]["y"] - o["bl"]["means"]), "z_hat": o["z_hat"],
+                         "y_q": torch.round(o["y"] - o["means"])}
+                net, call = net_i, (lambda: net_i.encode_decode(x_bl.to(dev), x_el.to(dev), None, None, H // 2, W // 2, H, W))
+            else:
+                o = orc.lssvc(sd_p, x_bl, x_el, dpb, (H, W), 2.0)
+                q_ref = {"bl_mv_z_hat": o["bl"]["mv_z_hat"], "bl_mv_y_q": o["bl"]["mv_y_q"], "bl_z_hat": o["bl"]["z_hat"],
+                         "bl_y_q": o["bl"]["y_q"], "mv_z_hat": o["mv_z_hat"], "mv_y_q": o["mv_y_q"], "z_hat": o["z_hat"],
+                         "y_q": o["four_part"]["y_q"]}
+                dpb_dev = {k: (None if v is None else v.to(dev)) for k, v in dpb.items()}
+                net, call = net_p, (lambda: net_p.encode_decode(x_bl.to(dev), x_el.to(dev), dpb_dev, None, None, W, H, W // 2, H // 2))
+        try:
+            net._debug, net._force, net._force_flips = {}, q_ref, {}
+            r = call()
+            flips = dict(net._force_flips)
+        finally:
+            net._debug = net._force = None
+        if t == 0:
+            recs = [(r["x_hat_bl"], o["x_hat_bl"]), (r["x_hat_el"], o["x_hat_el"])]
+            dpb = {"ref_frame_bl": o["x_hat_bl"].clamp(0, 1), "ref_frame_el": o["x_hat_el"].clamp(0, 1), "ref_feature_bl": None,
+                   "ref_feature_el": o["feature_el"]}
+        else:
+            recs = [(r["dpb"]["ref_frame_bl"], o["dpb"]["ref_frame_bl"]), (r["dpb"]["ref_frame_el"], o["dpb"]["ref_frame_el"])]
+            dpb = dict(o["dpb"])
+            dpb["ref_frame_bl"] = dpb["ref_frame_bl"].clamp(0, 1)          # test.py:249-250
+            dpb["ref_frame_el"] = dpb["ref_frame_el"].clamp(0, 1)
+        d = max((a.cpu() - b).abs().max().item() for a, b in recs)
+        rb = max(abs(r[k] - o[k]) / o[k] for k in ("bit_bl", "bit_el"))
+        n_bad, n = sum(flips.values()), sum(v.numel() for v in q_ref.values())
+        print(f"frame {t:2d} ({'I' if t == 0 else 'P'}): bits {r['bit_bl']:.0f}/{r['bit_el']:.0f} (rel {rb:.1e}), recon max|d| {d:.2e}, "
+              f"{n_bad} of {n} symbols differ")
+        assert d < 1e-3 and rb < 1e-3
+        bad += n_bad
+        total += n
+        worst["recon"], worst["bits"] = max(worst["recon"], d), max(worst["bits"], rb)
+    print(f"GOP of {GOP}: {bad} of {total} symbols differ ({100 * bad / total:.4f} %), worst recon {worst['recon']:.2e}, worst bits {worst['bits']:.1e}")
+    assert bad <= 1e-4 * total
