@@ -124,3 +124,23 @@ def test_cuda_front_end_1080p(cuda_device):
     print(f"1080p: BL max|d| vs oracle {d:.3e}, equal {100 * (x_bl.cpu() == ref_bl).float().mean().item():.3f} %")
     assert d <= 1.2e-7
     assert abs(fe.psnr(x_bl, ref_bl.to(cuda_device).roll(1, 3)) - fo.psnr(x_bl.cpu(), ref_bl.roll(1, 3))) < 1e-3
+
+
+@pytest.mark.parametrize("shape, sizes", [((96, 64), (64, 48)), ((64, 64), (96, 80)), ((60, 90), (20, 31)), ((128, 128), (64, 64))])
+def test_resize_plans_reproduce_the_oracle(shape, sizes):
+    """Down-sampling with antialiasing (x2/3, x1/3, x1/2) and up-sampling (x1.5, x1.25): evaluating the host-built weights and
+    reflect-resolved taps the way the kernel does (taps in order, multiply then add) gives the oracle's imresize."""
+    from lssvc_b200 import frontend as fe
+    from oracle import frontend_oracle as fo
+    (h, w), (ho, wo) = shape, sizes
+    x = torch.rand(1, 2, h, w, generator=torch.Generator().manual_seed(1))
+    ref = fo.imresize_cubic(x, (ho, wo))
+    wv, tv, _ = fe.resize_plan(h, ho)
+    wh, th, _ = fe.resize_plan(w, wo)
+    rows = torch.zeros(1, 2, ho, w)
+    for k in range(wv.shape[1]):
+        rows = rows + x[:, :, tv[:, k].long(), :] * wv[:, k].view(1, 1, -1, 1)
+    out = torch.zeros(1, 2, ho, wo)
+    for k in range(wh.shape[1]):
+        out = out + rows[:, :, :, th[:, k].long()] * wh[:, k].view(1, 1, 1, -1)
+    assert (out - ref).abs().max().item() <= 1.2e-7
