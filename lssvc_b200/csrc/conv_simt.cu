@@ -3,6 +3,8 @@
 // These cover the layers the tensor-core kernel does not take (odd channel counts, GDN's
 // squared-input norm pool which wants full fp32, tiny heads) and serve as the on-device
 // cross-check of the tcgen05 path.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -221,6 +223,59 @@ __global__ void __launch_bounds__(256) dwconv3x3_x2_kernel(const float *__restri
   if (x0 + 1 < W) *reinterpret_cast<float4 *>(o + out_pitch) = a1;
 }
 
+// same arithmetic, a strip of R output rows x 2 columns per thread: the 3 x 4 input window slides down the strip (4 new float4
+// loads per row instead of 12), the nine weight quads stay in registers.  2 (R + 2) / R loads per output instead of 6; taps
+// are accumulated in the order of the kernels above (bias, then r = 0..2, s = 0..2), so results are identical.
+template <int R>
+__global__ void __launch_bounds__(256) dwconv3x3_strip_kernel(const float *__restrict__ in, uint32_t in_pitch,
+                                                              const float *__restrict__ w, const float *__restrict__ bias,
+                                                              float *__restrict__ out, uint32_t out_pitch, int H, int W, int C,
+                                                              uint32_t total) {
+  const uint32_t c4 = static_cast<uint32_t>(C) >> 2, W2 = static_cast<uint32_t>(W + 1) >> 1;
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const uint32_t pp = idx / c4, c = (idx - pp * c4) * 4;
+  const int ys = static_cast<int>(pp / W2) * R, x0 = static_cast<int>(pp - (pp / W2) * W2) * 2;
+  float4 k[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4 *>(w + t * C + c));
+  const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + c));
+  auto load_row = [&](int iy, float4 (&row)[4]) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int ix = x0 + s - 1;
+      row[s] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                   ? __ldg(reinterpret_cast<const float4 *>(in + (static_cast<size_t>(iy) * W + ix) * in_pitch + c))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  float4 v[3][4];
+  load_row(ys - 1, v[0]);
+  load_row(ys, v[1]);
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int y = ys + j;
+    if (y >= H) break;
+    load_row(y + 1, v[(j + 2) % 3]);
+    float4 a0 = b, a1 = b;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float4(&row)[4] = v[(j + r) % 3];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const float4 kk = k[r * 3 + s];
+        a0.x = fmaf(row[s].x, kk.x, a0.x); a0.y = fmaf(row[s].y, kk.y, a0.y);
+        a0.z = fmaf(row[s].z, kk.z, a0.z); a0.w = fmaf(row[s].w, kk.w, a0.w);
+        a1.x = fmaf(row[s + 1].x, kk.x, a1.x); a1.y = fmaf(row[s + 1].y, kk.y, a1.y);
+        a1.z = fmaf(row[s + 1].z, kk.z, a1.z); a1.w = fmaf(row[s + 1].w, kk.w, a1.w);
+      }
+    }
+    float *o = out + (static_cast<size_t>(y) * W + x0) * out_pitch + c;
+    *reinterpret_cast<float4 *>(o) = a0;
+    if (x0 + 1 < W) *reinterpret_cast<float4 *>(o + out_pitch) = a1;
+  }
+}
+
 // ConvTranspose2d(k=3, s=2, p=1, output_padding=1): out[oy, ox] gathers in[(oy + 1 - ky) / 2, ...] where
 // (oy + 1 - ky) is even.  weight [9][cin][cout].  One block = 32 output pixels x 32 output channels.
 __global__ void __launch_bounds__(256) deconv3x3_s2_kernel(const float *__restrict__ in, int in_pitch, int Hi, int Wi,
@@ -328,6 +383,20 @@ extern "C" int32_t lssvc_dwconv3x3(const lssvc_view *in, const float *weight, co
       (reinterpret_cast<uintptr_t>(out->ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(bias) & 15) == 0) {
     const uint32_t tot2 = static_cast<uint32_t>(in->H) * static_cast<uint32_t>((in->W + 1) / 2) * static_cast<uint32_t>(in->C / 4);
+    // 4-row strips per thread (sliding window): 0.043 -> 0.036 ms at C = 128, 288x480 (50 -> 60 % of the copy bandwidth),
+    // bit-identical results; LSSVC_DW_STRIPS=0 selects the two-pixel kernel (A/B)
+    static const bool strips = [] {
+      const char *e = getenv("LSSVC_DW_STRIPS");
+      return e == nullptr || atoi(e) != 0;
+    }();
+    if (strips && in->H >= 16) {
+      constexpr int R = 4;
+      const uint32_t tot = static_cast<uint32_t>((in->H + R - 1) / R) * static_cast<uint32_t>((in->W + 1) / 2) * static_cast<uint32_t>(in->C / 4);
+      dwconv3x3_strip_kernel<R><<<(tot + 255) / 256, 256, 0, lssvc::as_stream(stream)>>>(in->ptr, in->pitch, weight, bias, out->ptr,
+                                                                                        out->pitch, in->H, in->W, in->C, tot);
+      LSSVC_LAUNCHED();
+      return LSSVC_OK;
+    }
     dwconv3x3_x2_kernel<<<(tot2 + 255) / 256, 256, 0, lssvc::as_stream(stream)>>>(in->ptr, in->pitch, weight, bias, out->ptr,
                                                                                  out->pitch, in->H, in->W, in->C, tot2);
     LSSVC_LAUNCHED();

@@ -299,14 +299,14 @@ def test_dwconv_and_deconv(cuda_device):
     ops = _ops()
     dev = cuda_device
     g = torch.Generator().manual_seed(4)
-    C, H, W = 48, 18, 30
-    x = torch.randn(1, C, H, W, generator=g).to(dev)
-    w = torch.randn(C, 1, 3, 3, generator=g).to(dev)
-    b = torch.randn(C, generator=g).to(dev)
-    out = ops.View.alloc(H, W, C, dev)
-    ops.dwconv3x3(make_view(x, ops), w.view(C, 9).t().contiguous(), b, out)
-    ref = F.conv2d(x, w, b, padding=1, groups=C)
-    assert rel_err(out.to_nchw(), ref) < 1e-5
+    for C, H, W in ((48, 18, 30), (32, 21, 25), (64, 40, 16)):      # odd sizes: ragged last strip / last column pair
+        x = torch.randn(1, C, H, W, generator=g).to(dev)
+        w = torch.randn(C, 1, 3, 3, generator=g).to(dev)
+        b = torch.randn(C, generator=g).to(dev)
+        out = ops.View.alloc(H, W, C, dev)
+        ops.dwconv3x3(make_view(x, ops), w.view(C, 9).t().contiguous(), b, out)
+        ref = F.conv2d(x, w, b, padding=1, groups=C)
+        assert rel_err(out.to_nchw(), ref) < 1e-5
 
     cin, cout = 64, 96
     x = torch.randn(1, cin, 9, 15, generator=g).to(dev)
