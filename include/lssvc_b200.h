@@ -285,25 +285,27 @@ typedef struct lssvc_rans_decoder lssvc_rans_decoder;
 int32_t lssvc_pmf_to_quantized_cdf(const float *pmf, int32_t n, int32_t precision, uint32_t *cdf_out);
 
 /* BufferedRansEncoder (rans_interface.cpp:85-172). All pointers are host pointers;
- * cdfs is row-major [n_rows][cdf_stride]. */
+ * cdfs is row-major [n_rows][cdf_stride], cdf_sizes / offsets have n_rows entries.  Every index is checked against n_rows and
+ * every row's size against cdf_stride (LSSVC_ERR_ARG; the reference only asserts, rans_interface.cpp:101-108). */
 lssvc_rans_encoder *lssvc_rans_encoder_new(void);
 void lssvc_rans_encoder_free(lssvc_rans_encoder *e);
 void lssvc_rans_encoder_reset(lssvc_rans_encoder *e);
 int32_t lssvc_rans_encode_with_indexes(lssvc_rans_encoder *e, const int32_t *symbols,
                                        const int32_t *indexes, int64_t n, const int32_t *cdfs,
-                                       int32_t cdf_stride, const int32_t *cdf_sizes,
+                                       int32_t n_rows, int32_t cdf_stride, const int32_t *cdf_sizes,
                                        const int32_t *offsets);
 /* Finishes the stream; returns its size in bytes and a pointer valid until the next
  * reset/flush/free.  Clears the symbol buffer like the reference's flush(). */
 int64_t lssvc_rans_encoder_flush(lssvc_rans_encoder *e, const uint8_t **data);
 
-/* RansDecoder (rans_interface.cpp:176-244) */
+/* RansDecoder (rans_interface.cpp:176-244).  A stream that runs out, or whose bypass digit count is impossible for a 32-bit
+ * symbol (> 8 nibbles), returns LSSVC_ERR_STREAM instead of silently desynchronising. */
 lssvc_rans_decoder *lssvc_rans_decoder_new(void);
 void lssvc_rans_decoder_free(lssvc_rans_decoder *d);
 int32_t lssvc_rans_decoder_set_stream(lssvc_rans_decoder *d, const uint8_t *data, int64_t nbytes);
 int32_t lssvc_rans_decode_stream(lssvc_rans_decoder *d, const int32_t *indexes, int64_t n,
-                                 const int32_t *cdfs, int32_t cdf_stride, const int32_t *cdf_sizes,
-                                 const int32_t *offsets, int32_t *out);
+                                 const int32_t *cdfs, int32_t n_rows, int32_t cdf_stride,
+                                 const int32_t *cdf_sizes, const int32_t *offsets, int32_t *out);
 
 #ifdef __cplusplus
 }

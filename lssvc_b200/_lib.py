@@ -108,12 +108,12 @@ _SIGNATURES = {
     "lssvc_rans_encoder_new": (c_void_p, []),
     "lssvc_rans_encoder_free": (None, [c_void_p]),
     "lssvc_rans_encoder_reset": (None, [c_void_p]),
-    "lssvc_rans_encode_with_indexes": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
+    "lssvc_rans_encode_with_indexes": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lssvc_rans_encoder_flush": (c_int64, [c_void_p, POINTER(POINTER(c_uint8))]),
     "lssvc_rans_decoder_new": (c_void_p, []),
     "lssvc_rans_decoder_free": (None, [c_void_p]),
     "lssvc_rans_decoder_set_stream": (c_int32, [c_void_p, c_char_p, c_int64]),
-    "lssvc_rans_decode_stream": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "lssvc_rans_decode_stream": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -41,6 +41,23 @@ inline void enc_renorm(uint64_t &x, uint32_t *&out, uint64_t x_max) {
   }
 }
 
+// Every CDF row an index names must exist and fit its stride (a bad row would read outside cdfs / cdf_sizes / offsets).
+bool rows_ok(const char *who, const int32_t *indexes, int64_t n, int32_t n_rows, int32_t cdf_stride, const int32_t *cdf_sizes) {
+  for (int32_t r = 0; r < n_rows; ++r) {
+    if (cdf_sizes[r] < 2 || cdf_sizes[r] > cdf_stride) {
+      lssvc::set_error("%s: cdf_sizes[%d] = %d outside [2, cdf_stride = %d]", who, r, cdf_sizes[r], cdf_stride);
+      return false;
+    }
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    if (indexes[i] < 0 || indexes[i] >= n_rows) {
+      lssvc::set_error("%s: indexes[%lld] = %d outside [0, n_rows = %d)", who, static_cast<long long>(i), indexes[i], n_rows);
+      return false;
+    }
+  }
+  return true;
+}
+
 }  // namespace
 
 struct lssvc_rans_encoder {
@@ -129,12 +146,13 @@ void lssvc_rans_encoder_reset(lssvc_rans_encoder *e) {
 }
 
 int32_t lssvc_rans_encode_with_indexes(lssvc_rans_encoder *e, const int32_t *symbols, const int32_t *indexes, int64_t n,
-                                       const int32_t *cdfs, int32_t cdf_stride, const int32_t *cdf_sizes,
-                                       const int32_t *offsets) {
-  if (!e || (n > 0 && (!symbols || !indexes)) || !cdfs || !cdf_sizes || !offsets || cdf_stride <= 0) {
+                                       const int32_t *cdfs, int32_t n_rows, int32_t cdf_stride,
+                                       const int32_t *cdf_sizes, const int32_t *offsets) {
+  if (!e || (n > 0 && (!symbols || !indexes)) || !cdfs || !cdf_sizes || !offsets || cdf_stride <= 0 || n_rows <= 0) {
     lssvc::set_error("rans_encode_with_indexes: bad arguments");
     return LSSVC_ERR_ARG;
   }
+  if (!rows_ok("rans_encode_with_indexes", indexes, n, n_rows, cdf_stride, cdf_sizes)) return LSSVC_ERR_ARG;
   e->toks.reserve(e->toks.size() + static_cast<size_t>(n));
   for (int64_t i = 0; i < n; ++i) {
     const int32_t row = indexes[i];
@@ -215,11 +233,13 @@ int32_t lssvc_rans_decoder_set_stream(lssvc_rans_decoder *d, const uint8_t *data
 }
 
 int32_t lssvc_rans_decode_stream(lssvc_rans_decoder *d, const int32_t *indexes, int64_t n, const int32_t *cdfs,
-                                 int32_t cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets, int32_t *out) {
-  if (!d || (n > 0 && (!indexes || !out)) || !cdfs || !cdf_sizes || !offsets || cdf_stride <= 0) {
+                                 int32_t n_rows, int32_t cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets,
+                                 int32_t *out) {
+  if (!d || (n > 0 && (!indexes || !out)) || !cdfs || !cdf_sizes || !offsets || cdf_stride <= 0 || n_rows <= 0) {
     lssvc::set_error("rans_decode_stream: bad arguments");
     return LSSVC_ERR_ARG;
   }
+  if (!rows_ok("rans_decode_stream", indexes, n, n_rows, cdf_stride, cdf_sizes)) return LSSVC_ERR_ARG;
   const uint64_t mask = (1ull << kProbBits) - 1;
   for (int64_t i = 0; i < n; ++i) {
     const int32_t row = indexes[i];
@@ -245,6 +265,11 @@ int32_t lssvc_rans_decode_stream(lssvc_rans_decoder *d, const int32_t *indexes, 
         val = static_cast<int32_t>(d->get_bits(kBypassBits));
         digits += val;
         if (d->underflow) break;
+      }
+      if (digits > 8 && !d->underflow) {   // a 32-bit symbol has at most 8 nibbles: the stream is corrupt or out of step
+        lssvc::set_error("rans_decode_stream: %d bypass digits at symbol %lld of %lld (corrupt stream or wrong CDF indexes)",
+                         digits, static_cast<long long>(i), static_cast<long long>(n));
+        return LSSVC_ERR_STREAM;
       }
       int32_t raw = 0;
       for (int32_t j = 0; j < digits && j < 8; ++j) {

@@ -249,7 +249,7 @@ class RansEncoder:
         if s.size != i.size:
             raise ValueError("symbols and indexes must have the same length")
         _lib.check(self._lib.lssvc_rans_encode_with_indexes(
-            self._h, s.ctypes.data, i.ctypes.data, s.size, table.cdf.ctypes.data, table.cdf.shape[1],
+            self._h, s.ctypes.data, i.ctypes.data, s.size, table.cdf.ctypes.data, table.cdf.shape[0], table.cdf.shape[1],
             table.sizes.ctypes.data, table.offsets.ctypes.data), "rans_encode_with_indexes")
 
     def flush(self):
@@ -279,6 +279,6 @@ class RansDecoder:
         i = _i32(indexes)
         out = np.empty(i.size, dtype=np.int32)
         _lib.check(self._lib.lssvc_rans_decode_stream(
-            self._h, i.ctypes.data, i.size, table.cdf.ctypes.data, table.cdf.shape[1], table.sizes.ctypes.data,
+            self._h, i.ctypes.data, i.size, table.cdf.ctypes.data, table.cdf.shape[0], table.cdf.shape[1], table.sizes.ctypes.data,
             table.offsets.ctypes.data, out.ctypes.data), "rans_decode_stream")
         return out
