@@ -65,6 +65,19 @@ def _to_view(model, t, image=False):
     return model.image_view(t) if image else model.feature_view(t)
 
 
+def _rows(model, name, idx):
+    """CDF rows (host int32) about to drive a decode_stream call.  Test hook (tests/test_streams.py): when
+    model._force_rows holds reference rows under `name`, the rows that differ are counted in model._row_flips and replaced —
+    a scale within float noise of a row threshold otherwise desynchronises the decoder of a FOREIGN stream for good (the
+    reference has the same property between its CPU and GPU runs).  Never active outside tests."""
+    f = getattr(model, "_force_rows", None)
+    if f and name in f:
+        ref = np.ascontiguousarray(f[name], dtype=np.int32).reshape(-1)
+        model._row_flips[name] = int((ref != idx).sum())
+        return ref
+    return idx
+
+
 class _Reader:
     """Decoder-side glue: rANS decoder + device<->host hops of the symbol / index tensors."""
 
@@ -84,13 +97,13 @@ class _Reader:
         C = int(table.cdf.shape[0])
         return self._view(self.dec.decode_stream(_channel_index(C, H, W), table), C, H, W)
 
-    def laplace(self, params, table):
+    def laplace(self, params, table, name):
         """GaussianEncoder.decode_stream(scales) + means (LSSVC_net_extend.py:120-123): params = (scales | means)."""
         C = params.real // 2
         scale, mean = params.slice(0, C), params.slice(C, 2 * C)
         idx = torch.empty(C * params.H * params.W, dtype=torch.int32, device=self.m.device)
         ops.scale_index(scale, idx, self.m._thr())
-        sym = self.dec.decode_stream(idx.cpu().numpy(), table)
+        sym = self.dec.decode_stream(_rows(self.m, name, idx.cpu().numpy()), table)
         return self._view(sym, C, params.H, params.W, add=mean)
 
     def four_part(self, common, table):
@@ -103,7 +116,8 @@ class _Reader:
         for step in range(4):
             idx = torch.empty(n, dtype=torch.int32, device=m.device)
             ops.four_part_index(prm, step, idx, m._thr())
-            sym = torch.from_numpy(self.dec.decode_stream(idx.cpu().numpy(), table)).to(m.device)
+            rows = _rows(m, f"el_y{step}", idx.cpu().numpy())
+            sym = torch.from_numpy(self.dec.decode_stream(rows, table)).to(m.device)
             ops.four_part_dec_step(sym, prm, step, y_hat)
             if step < 3:
                 prm = m._spatial_prior(step + 1, y_hat, common)
@@ -134,11 +148,11 @@ def bl_decompress(model, string, height, width, dpb):
     ref_feature = _to_view(model, dpb.get("ref_feature_bl"))
     zh, zw = stream.get_downsampled_shape(height, width, 64)
     mv_z_hat = rd.factorized(t["bl_mv_z"], zh, zw)
-    mv_y_hat = rd.laplace(model._bl_mv_params(p, mv_z_hat), t["laplace"])
+    mv_y_hat = rd.laplace(model._bl_mv_params(p, mv_z_hat), t["laplace"], "bl_mv_y")
     mv_hat = model._bl_mv_decode(p, mv_y_hat)
     c1, c2, c3 = model._bl_contexts(p, ref, ref_feature, mv_hat)
     z_hat = rd.factorized(t["bl_z"], zh, zw)
-    y_hat = rd.laplace(model._bl_res_params(p, z_hat, c1, c2, c3), t["laplace"])
+    y_hat = rd.laplace(model._bl_res_params(p, z_hat, c1, c2, c3), t["laplace"], "bl_y")
     rec_feat = model._res_decoder_gdn(p + "res_decoder", y_hat, c2, c3, intra=False)
     feature, recon = model._recon_generation(p + "recon_generation_net", rec_feat, c1)
     return {"dpb": _bl_dpb({"recon": recon, "feature": feature, "y_hat": y_hat, "mv_hat": mv_hat}, clamp=True)}
@@ -196,7 +210,7 @@ def el_decompress(model, string, height, width, dpb):
     mv_ctx_prior, mv_ctx = model._mv_contexts(_to_view(model, dpb["mv_hat_bl"]))
     zh, zw = stream.get_downsampled_shape(height, width, 64)
     mv_z_hat = rd.factorized(t["el_mv_z"], zh, zw)
-    mv_y_hat = rd.laplace(model._mv_params(mv_z_hat, mv_ctx_prior), t["laplace"])
+    mv_y_hat = rd.laplace(model._mv_params(mv_z_hat, mv_ctx_prior), t["laplace"], "el_mv_y")
     mv_hat = model._mv_decode(mv_y_hat, mv_ctx)
     c1, c2, c3, _ = model._hybrid_contexts(_to_view(model, dpb["texture"]), mv_hat, ref, ref_feature)
     z_hat = rd.factorized(t["el_z"], zh, zw)
@@ -268,13 +282,13 @@ def _gaussian_encode(model, y, prm, table):
     return _encode([(dump.host("y"), dump.host("y_idx"), table)]), y_hat
 
 
-def _gaussian_decode(model, string, prm, table):
+def _gaussian_decode(model, string, prm, table, name):
     C = prm.real // 2
     idx = torch.empty(C * prm.H * prm.W, dtype=torch.int32, device=model.device)
     ops.scale_index(prm.slice(0, C), idx, _thr_img(model))
     dec = entropy.RansDecoder()
     dec.set_stream(string)
-    sym = torch.from_numpy(dec.decode_stream(idx.cpu().numpy(), table)).to(model.device)
+    sym = torch.from_numpy(dec.decode_stream(_rows(model, name, idx.cpu().numpy()), table)).to(model.device)
     y_hat = model.new(prm.H, prm.W, C)
     ops.symbols_to_view(sym, prm.slice(C, 2 * C), y_hat.exact())
     return y_hat
@@ -312,7 +326,7 @@ def intra_bl_decompress(model, strings, shape):
     model.update()
     t = model._tables
     z_hat = _eb_decode(model, strings[1][0], _BL_EB, t["bl_z"], int(shape[0]), int(shape[1]))
-    y_hat = _gaussian_decode(model, strings[0][0], model._bl_params(z_hat), t["gaussian"])
+    y_hat = _gaussian_decode(model, strings[0][0], model._bl_params(z_hat), t["gaussian"], "bl_y")
     return {"x_hat": model._bl_synthesis(y_hat).to_nchw(), "y_hat": y_hat.to_nchw()}
 
 
@@ -340,7 +354,7 @@ def intra_decompress(model, strings, DPB_layer, shape):
     c1, c2, c3 = model._context_mining(model.image_view(DPB_layer["x_hat_bl"]))
     z_hat = _eb_decode(model, strings[1][0], "entropy_bottleneck.", t["el_z"], int(shape[0]), int(shape[1]))
     prm = model._el_params(z_hat, _to_view(model, DPB_layer["y_hat_bl"]), c3)
-    y_hat = _gaussian_decode(model, strings[0][0], prm, t["gaussian"])
+    y_hat = _gaussian_decode(model, strings[0][0], prm, t["gaussian"], "el_y")
     res_hat = model._res_decoder_gdn("g_s", y_hat, c2, c3, intra=True)
     feature, x_hat = model._recon_generation("recon_net", res_hat, c1)
     return {"x_hat": x_hat.to_nchw(), "feature": feature.to_nchw()}

@@ -15,6 +15,7 @@ class Engine(nets.ParamBag):
         super().__init__(spec, seed=seed, gains=nets.model_gains(model_tag))
         self._packs = {}
         self._graphs = {}
+        self._tables = None
         # whole-frame CUDA graphs (models.py), opt in with LSSVC_CUDA_GRAPH=1: measured equal to eager launches on one
         # B200 (the GPU never waits for the host: tools/graph_ab.py), useful when the host is the bottleneck
         self.use_graphs = os.environ.get("LSSVC_CUDA_GRAPH", "0") == "1"
@@ -40,6 +41,7 @@ class Engine(nets.ParamBag):
     def _invalidate(self):
         self._packs = {}
         self._graphs = {}
+        self._tables = None     # CDF tables follow the bit-estimator / bottleneck parameters: update() rebuilds them
 
     def _apply(self, fn, *a, **k):
         self._invalidate()
