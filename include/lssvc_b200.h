@@ -142,6 +142,10 @@ int32_t lssvc_abi_version(void);
 /* 0 when device `dev` is sm_100-class and the driver entry points needed for TMA resolve. */
 int32_t lssvc_device_check(int32_t dev);
 const char *lssvc_last_error(void);
+/* Range guard of the split-fp16 kernels (csrc/range.cu): writes 1.0 to *dst (device double) if, since the last fetch, an
+ * operand of conv_hs / conv_pw / conv_ffn reached the fp16 limit (|x| >= 65520, or x^2 under LSSVC_IN_SQUARE) — the
+ * outputs of that launch are then NaN — else 0.0; clears the flag.  Stream-ordered, no host synchronisation. */
+int32_t lssvc_range_flag_fetch(double *dst, void *stream);
 /* number of kernels this library launched since load (bench.py's gpu_launches) */
 int64_t lssvc_launch_count(void);
 /* kernels launched by replaying a captured CUDA graph are added by the host layer (n per replay) */

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "lssvc_abi_version": (c_int32, []),
     "lssvc_device_check": (c_int32, [c_int32]),
     "lssvc_last_error": (c_char_p, []),
+    "lssvc_range_flag_fetch": (c_int32, [c_void_p, c_void_p]),
     "lssvc_launch_count": (c_int64, []),
     "lssvc_launch_count_add": (None, [c_int64]),
     "lssvc_conv_tc": (c_int32, [POINTER(CConv), c_void_p]),

@@ -58,6 +58,26 @@ def _bits_scratch(model):
     return _Bits(model.device)
 
 
+def _range_guarded(fn):
+    """Stream-mode entry points: after the call the range flag of the split-fp16 kernels (csrc/range.cu) is fetched; if an
+    operand left the fp16 range the whole call is repeated on the fp32 engine (models._recode_fp32)."""
+    import functools
+
+    @functools.wraps(fn)
+    def inner(model, *a, **k):
+        from .models import _recode_fp32
+        out = fn(model, *a, **k)
+        if ops.default_engine() != "h2":
+            return out
+        bits = _bits_scratch(model)
+        bits.fetch_range()
+        bits.read()
+        if bits.out_of_range:
+            return _recode_fp32(model, fn.__name__, lambda: fn(model, *a, **k))
+        return out
+    return inner
+
+
 def _to_view(model, t, image=False):
     """NCHW tensor (or an NHWC View handed over natively) -> NHWC view."""
     if isinstance(t, View) or t is None:
@@ -125,6 +145,7 @@ class _Reader:
 
 
 # ---- base layer -------------------------------------------------------------------------------------------------
+@_range_guarded
 def bl_compress(model, x, dpb):
     """DMCExtend.compress(x, dpb) -> {"string", "dpb": {ref_frame_bl, ref_feature_bl, y_hat_bl, mv_hat_bl}}."""
     model.update()
@@ -138,6 +159,7 @@ def bl_compress(model, x, dpb):
     return {"string": string, "dpb": _bl_dpb(bl, clamp=False)}
 
 
+@_range_guarded
 def bl_decompress(model, string, height, width, dpb):
     """DMCExtend.decompress(string, height, width, dpb): the reconstruction is clamped to [0, 1] (dmc_net_extend.py:138)."""
     model.update()
@@ -183,6 +205,7 @@ def bl_encode_decode_extend(model, x, dpb, output_path=None, pic_width=None, pic
 
 
 # ---- enhancement layer ------------------------------------------------------------------------------------------
+@_range_guarded
 def el_compress(model, x, dpb):
     """LSSVC_extend.compress(x, dpb): dpb carries the decoded base layer as 'texture', 'y_hat_bl', 'mv_hat_bl'."""
     model.update()
@@ -200,6 +223,7 @@ def el_compress(model, x, dpb):
                     "warp_frame": el["warp_frame"].to_nchw(), "mv_hat": el["mv_hat"].to_nchw()}}
 
 
+@_range_guarded
 def el_decompress(model, string, height, width, dpb):
     """LSSVC_extend.decompress(string, height, width, dpb) -> {"dpb": {ref_frame_el, ref_feature_el}}."""
     model.update()
@@ -297,12 +321,14 @@ def _gaussian_decode(model, string, prm, table, name):
 _BL_EB = "base_layer_model.entropy_bottleneck."
 
 
+@_range_guarded
 def intra_bl_get_y_z(model, x):
     """IntraNoAR.get_y_z(x)."""
     y, z = model._bl_analysis(model.image_view(x))
     return y.to_nchw(), z.to_nchw()
 
 
+@_range_guarded
 def intra_bl_compress(model, x, y, z):
     """IntraNoAR.compress(x, y, z) (priors.py:420-435) -> {"strings": [[y], [z]], "shape"}."""
     model.update()
@@ -312,6 +338,7 @@ def intra_bl_compress(model, x, y, z):
     return {"strings": [[y_string], [z_string]], "shape": tuple(z.shape[-2:])}
 
 
+@_range_guarded
 def intra_bl_get_y_hat_recon(model, y, z):
     """IntraNoAR.get_y_hat_recon(y, z): the encoder-side reconstruction {x_hat, y_hat, z_hat}."""
     model.update()
@@ -321,6 +348,7 @@ def intra_bl_get_y_hat_recon(model, y, z):
     return {"x_hat": model._bl_synthesis(y_hat).to_nchw(), "y_hat": y_hat.to_nchw(), "z_hat": z_hat.to_nchw()}
 
 
+@_range_guarded
 def intra_bl_decompress(model, strings, shape):
     """IntraNoAR.decompress(strings, shape) (priors.py:437-452) -> {"x_hat", "y_hat"}."""
     model.update()
@@ -330,6 +358,7 @@ def intra_bl_decompress(model, strings, shape):
     return {"x_hat": model._bl_synthesis(y_hat).to_nchw(), "y_hat": y_hat.to_nchw()}
 
 
+@_range_guarded
 def intra_get_y_z_ctx(model, x_hat_bl, x_el):
     """IntraSS.get_y_z_ctx (IntraSS.py:239-243)."""
     c1, c2, c3 = model._context_mining(model.image_view(x_hat_bl))
@@ -337,6 +366,7 @@ def intra_get_y_z_ctx(model, x_hat_bl, x_el):
     return y.to_nchw(), z.to_nchw(), (c1.to_nchw(), c2.to_nchw(), c3.to_nchw())
 
 
+@_range_guarded
 def intra_compress(model, y=None, z=None, ctx3=None, y_hat_bl=None):
     """IntraSS.compress(y, z, ctx3, y_hat_bl) (IntraSS.py:304-314)."""
     model.update()
@@ -347,6 +377,7 @@ def intra_compress(model, y=None, z=None, ctx3=None, y_hat_bl=None):
     return {"strings": [[y_string], [z_string]], "shape": tuple(z.shape[-2:])}
 
 
+@_range_guarded
 def intra_decompress(model, strings, DPB_layer, shape):
     """IntraSS.decompress(strings, DPB_layer, shape) (IntraSS.py:316-336) -> {"x_hat", "feature"}."""
     model.update()

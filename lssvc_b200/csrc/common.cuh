@@ -11,6 +11,10 @@ namespace lssvc {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+// device word raised by the split-fp16 kernels when an operand leaves the fp16 range (range.cu); nullptr if unavailable
+unsigned int *range_flag();
+// operands at or beyond this magnitude round to inf in fp16
+constexpr float kSplitRangeLimit = 65520.f;
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 

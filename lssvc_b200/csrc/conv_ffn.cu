@@ -49,6 +49,7 @@ struct alignas(64) FfnParams {
   int in_off, stage_off;  // smem offsets (after the resident weights)
   float scale1, scale2;   // 2^-shift of W1 / W2
   float slope1, slope2;
+  unsigned int *range_flag;  // raised when a split operand leaves the fp16 range (range.cu)
   long long *prof;  // DBG variant (LSSVC_FFN_DBG=1): [6 roles][8] wait-cycle counters of CTA 0
 };
 
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
     const uint32_t lane_addr = t_ao + (static_cast<uint32_t>(q * 32) << 16);
     int ib = 0;
     uint32_t iph = 0, tphase = 0;
+    float amax = 0.f;  // running max |operand| of this thread (range guard)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       FFN_WAIT(0, b_in_full + 8 * ib, iph);
       const uint32_t tile_s = in_s + static_cast<uint32_t>(ib) * in_bytes;
@@ -259,6 +261,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v[i].x), fabsf(v[i].y))), fmaxf(fabsf(v[i].z), fabsf(v[i].w)));
           split_pair_f(v[i].x, v[i].y, hi[2 * i], lo[2 * i]);
           split_pair_f(v[i].z, v[i].w, hi[2 * i + 1], lo[2 * i + 1]);
         }
@@ -278,6 +281,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
         iph ^= 1u;
       }
     }
+    if (amax >= lssvc::kSplitRangeLimit && p.range_flag) atomicOr(p.range_flag, 1u);
   } else if (warp >= 8 && warp < 24) {
     // ------------------------------- hidden epilogue: D_h -> lrelu -> split -> A_h ---------
     const int hw = warp - 8;
@@ -289,6 +293,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
     const uint32_t dst_hi = t_ah + 32u * b + 8u * half + lane_off, dst_lo = dst_hi + 16u;
     const float scale1 = p.scale1, slope1 = p.slope1;
     uint32_t use = 0;
+    float amax = 0.f;  // running max |hidden activation| of this thread (range guard)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int j = b; j < n_chunks; j += 2) {
         const float4 *bq = reinterpret_cast<const float4 *>(p.b1 + j * HC + 16 * half);
@@ -315,6 +320,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
           h1 = h1 > 0.f ? h1 : h1 * slope1;
           h2 = h2 > 0.f ? h2 : h2 * slope1;
           h3 = h3 > 0.f ? h3 : h3 * slope1;
+          amax = fmaxf(fmaxf(amax, fmaxf(fabsf(h0), fabsf(h1))), fmaxf(fabsf(h2), fabsf(h3)));
           split_pair_f(h0, h1, hi[2 * i], lo[2 * i]);
           split_pair_f(h2, h3, hi[2 * i + 1], lo[2 * i + 1]);
         }
@@ -329,6 +335,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
         ++use;
       }
     }
+    if (amax >= lssvc::kSplitRangeLimit && p.range_flag) atomicOr(p.range_flag, 1u);
   } else if (warp >= 24) {
     // ------------------------------- output epilogue ---------------------------------------
     const int q = warp & 3;
@@ -485,6 +492,7 @@ extern "C" int32_t lssvc_conv_ffn(const lssvc_ffn *f, void *stream) {
   p.w1 = f->w1; p.w2 = f->w2; p.b1 = f->b1; p.b2 = f->b2;
   p.res2 = f->res2.ptr; p.res2_pitch = f->res2.pitch;
   p.scale1 = f->scale1; p.scale2 = f->scale2; p.slope1 = f->slope1; p.slope2 = f->slope2;
+  p.range_flag = lssvc::range_flag();
   const int tile_bytes = 128 * C * 4;
   p.in_off = (p.w1_bytes + p.w2_bytes + 1023) & ~1023;
   p.stage_off = p.in_off + IN_BUFS * tile_bytes;

@@ -95,6 +95,7 @@ struct alignas(64) HsParams {
   float *out2;
   int out2_pitch;
   float slope2;
+  unsigned int *range_flag;  // raised when a split operand leaves the fp16 range (range.cu)
   long long *prof;  // DBG variant: [5 roles][8] cycle counters of CTA 0
   int dbg;  // LSSVC_HS_DBG: bottleneck-isolation switches (results are wrong when non-zero); see lssvc_conv_hs
 };
@@ -482,6 +483,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
     const uint32_t halo_bytes = static_cast<uint32_t>(p.halo_bytes);
     int hb = 0;
     uint32_t hph = 0;
+    float amax = 0.f;  // running max |operand| of this thread (range guard)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int j = 0; j < p.n_src; ++j) {
         for (int c = 0; c < p.chunks[j]; ++c) {
@@ -499,6 +501,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
               uint32_t hi[2 * NV], lo[2 * NV];
 #pragma unroll
               for (int i = 0; i < NV; ++i) {
+                amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v[i].x), fabsf(v[i].y))), fmaxf(fabsf(v[i].z), fabsf(v[i].w)));
                 split_pair(v[i].x, v[i].y, hi[2 * i], lo[2 * i]);
                 split_pair(v[i].z, v[i].w, hi[2 * i + 1], lo[2 * i + 1]);
               }
@@ -520,6 +523,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
         }
       }
     }
+    if (amax >= lssvc::kSplitRangeLimit && p.range_flag) atomicOr(p.range_flag, 1u);
   } else if (warp >= 12) {
     // ------------------------------- epilogue ---------------------------------------------
     // two independent sets of 4 warps; set e owns the accumulator units u = tile_counter * mt + j with (u & 1) == e
@@ -1002,6 +1006,7 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
   p.b_bytes = tps * (2 * n_tile * kc * 2);  // n_tile % 16 == 0 keeps every tile 1024-byte aligned
   p.in_transform = c->in_transform;
   p.in_slope = c->in_slope;
+  p.range_flag = lssvc::range_flag();
   p.acc_scale = c->acc_scale;
   p.bias = c->bias;
   p.epi = c->epi;

@@ -45,6 +45,7 @@ struct alignas(64) PwParams {
   int w_bytes, dw_off, in_off, stage_off, in_bufs;
   int act;
   float slope, out_scale, acc_scale;
+  unsigned int *range_flag;  // raised when a split operand leaves the fp16 range (range.cu)
 };
 
 __device__ __forceinline__ void split_pair_p(float a, float b, uint32_t &hi, uint32_t &lo) {
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_co
     const uint32_t row_bytes = s32 ? 128u : 64u;
     int ib = 0, b = 0;
     uint32_t iph = 0, ph = 0;
+    float amax = 0.f;  // running max |operand| of this thread (range guard)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       ptx::mbar_wait(b_in_full + 8 * ib, iph);
       const uint32_t tile_s = in_s + static_cast<uint32_t>(ib) * in_bytes;
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_co
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v[i].x), fabsf(v[i].y))), fmaxf(fabsf(v[i].z), fabsf(v[i].w)));
           split_pair_p(v[i].x, v[i].y, hi[2 * i], lo[2 * i]);
           split_pair_p(v[i].z, v[i].w, hi[2 * i + 1], lo[2 * i + 1]);
         }
@@ -256,6 +259,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_co
         ph ^= 1u;
       }
     }
+    if (amax >= lssvc::kSplitRangeLimit && p.range_flag) atomicOr(p.range_flag, 1u);
   } else if (warp >= 20) {
     // ------------------------------- epilogue ----------------------------------------------
     const int ew = warp - 20;
@@ -434,6 +438,7 @@ extern "C" int32_t lssvc_conv_pw(const lssvc_pw *f, void *stream) {
   p.res1 = f->res1.ptr; p.res1_pitch = f->res1.pitch;
   p.res2 = f->res2.ptr; p.res2_pitch = f->res2.pitch;
   p.act = f->act; p.slope = f->slope; p.out_scale = f->out_scale; p.acc_scale = f->acc_scale;
+  p.range_flag = lssvc::range_flag();
   p.dw_off = (p.w_bytes + 1023) & ~1023;
   p.in_off = (p.dw_off + (dw ? 10 * Cin * 4 : 0) + 1023) & ~1023;
   size_t smem = 0;

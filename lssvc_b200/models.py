@@ -66,15 +66,41 @@ def _force(model, key, out, mean=None, mask=None, q_view=None):
 class _Bits:
     """Device-side double accumulators for the per-layer bit counts of one frame."""
 
-    def __init__(self, device):
-        self.t = torch.zeros(2, dtype=torch.float64, device=device)
+    def __init__(self, device, t=None):
+        # [bits_bl, bits_el, range flag of the split-fp16 kernels (csrc/range.cu)]
+        self.t = torch.zeros(3, dtype=torch.float64, device=device) if t is None else t
+        self.out_of_range = False
 
     def ptr(self, layer):
         return self.t[layer:layer + 1]
 
+    def fetch_range(self):
+        """Stream-ordered: moves (and clears) the library's range flag into slot 2; call after the frame's last kernel."""
+        ops.range_flag_fetch(self.t[2:3])
+
     def read(self):
-        bl, el = self.t.tolist()   # the one device->host sync of a frame
+        bl, el, flag = self.t.tolist()   # the one device->host sync of a frame
+        self.out_of_range = flag != 0.0
         return bl, el
+
+
+def _recode_fp32(model, what, call):
+    """An operand of the split-fp16 tensor-core kernels left the fp16 range while `what` was coded (its outputs are NaN):
+    code it again on the fp32 CUDA-core engine.  Counted in ops.RANGE_FALLBACKS; warned about once per model."""
+    if ops.default_engine() != "h2":
+        raise _lib.LssvcError(f"{what}: range flag raised although the split-fp16 engine is not in use")
+    ops.RANGE_FALLBACKS += 1
+    if not getattr(model, "_range_warned", False):
+        import warnings
+        warnings.warn(f"lssvc_b200: {what}: an activation reached the fp16 limit of the split-fp16 tensor-core engine "
+                      "(|x| >= 65520, or a GDN input beyond 255.9); the frame is re-coded on the fp32 CUDA-core engine "
+                      "(about 10x slower). Set LSSVC_CONV_ENGINE=tc3 to avoid the split-fp16 engine for this checkpoint.")
+        model._range_warned = True
+    prev = ops.set_engine("simt")
+    try:
+        return call()
+    finally:
+        ops.set_engine(prev)
 
 
 # =============================================================================================================
@@ -256,8 +282,9 @@ class IntraSS(Engine):
 
     # ---- forward ------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, x_bl, x_el, train_with_recon=False, _native=False, _write=None):
-        """IntraSS.forward (IntraSS.py:137-172)."""
+    def forward(self, x_bl, x_el, train_with_recon=False, _native=False, _write=None, _async=False):
+        """IntraSS.forward (IntraSS.py:137-172).  _async (runner.py): no host synchronisation — the bit counts stay on the
+        device (result["_bits"]) and "bit_bl" / "bit_el" are None until the caller reads them."""
         self._require_cuda()
         bits = _Bits(self.device)
         xb, xe = self.image_view(x_bl), self.image_view(x_el)
@@ -295,9 +322,14 @@ class IntraSS(Engine):
         feature, x_hat = self._recon_generation("recon_net", res_hat, c1)
         _dbg(self, y_bl=y_bl, y_hat_bl=y_hat_bl, z_hat_bl=z_hat_bl, y=y, y_hat=y_hat, z_hat=z_hat, params_el=prm,
              c1=c1, c2=c2, c3=c3)
-        bit_bl, bit_el = bits.read()
+        bits.fetch_range()
+        bit_bl, bit_el = (None, None) if _async else bits.read()
+        if bits.out_of_range:
+            return _recode_fp32(self, "IntraSS.forward", lambda: self.forward(x_bl, x_el, train_with_recon, _native, _write))
         result = {"bit_bl": bit_bl, "bit_el": bit_el, "x_hat_bl": x_hat_bl.to_nchw(), "x_hat_el": x_hat.to_nchw(),
                   "feature_el": feature.to_nchw_shared()}
+        if _async:
+            result["_bits"] = bits
         if _native:
             result["_native"] = {"x_hat_bl": x_hat_bl, "x_hat_el": x_hat, "feature_el": feature, "y_hat_bl": y_hat_bl,
                                  "y": y, "z_hat": z_hat, "params_el": prm, "y_bl": y_bl, "ctx": (c1, c2, c3)}
@@ -730,6 +762,7 @@ class LSSVC(Engine):
         weight caches): what a CUDA graph of the frame captures."""
         bl = self._base_layer(xb, rb, fb, bits, w)
         el = self._el_layer(xe, re, fe, bl["feature"], bl["y_hat"], bl["mv_hat"], bits, w)
+        bits.fetch_range()
         return {"bl_recon": bl["recon"], "bl_feature": bl["feature"], "recon": el["recon"], "feature": el["feature"],
                 "mv_hat": el["mv_hat"], "warp_frame": el["warp_frame"]}
 
@@ -782,29 +815,51 @@ class LSSVC(Engine):
 
     @torch.no_grad()
     def forward_one_frame(self, x_bl, x_el, ref_frame_bl, ref_frame_el, ref_feature_bl, ref_feature_el, _dpb=None,
-                          _write=None):
-        """LSSVC.forward_one_frame (LSSVC_net.py:445-528)."""
+                          _write=None, _async=False):
+        """LSSVC.forward_one_frame (LSSVC_net.py:445-528).  _async (runner.py): no host synchronisation — the bit counts
+        stay on the device (result["_bits"]) and "bit_bl" / "bit_el" are None until the caller reads them."""
         self._require_cuda()
         dpb = _dpb if _dpb is not None else {"ref_frame_bl": ref_frame_bl, "ref_frame_el": ref_frame_el,
                                              "ref_feature_bl": ref_feature_bl, "ref_feature_el": ref_feature_el}
         if (self.use_graphs and _write is None and getattr(self, "_debug", None) is None and not getattr(self, "_force", None)
                 and ops.TRACE is None and not _lib.DRY_RUN):
-            return self._forward_graphed(x_bl, x_el, dpb)
+            return self._forward_graphed(x_bl, x_el, dpb, _async)
         bits = _Bits(self.device)
         xb, xe = self.image_view(x_bl), self.image_view(x_el)
         rb, re = self._dpb_view(dpb, "ref_frame_bl", True), self._dpb_view(dpb, "ref_frame_el", True)
         fb, fe = self._dpb_view(dpb, "ref_feature_bl", False), self._dpb_view(dpb, "ref_feature_el", False)
         v = self._frame_core(xb, xe, rb, re, fb, fe, bits, _write)
+        return self._frame_done(v, bits, _async, redo=(x_bl, x_el, dpb, _write))
+
+    def _frame_done(self, v, bits, _async, token=None, redo=None):
+        if _async:
+            r = self._frame_result(v, None, None, token=token)
+            r["_bits"] = bits
+            return r
         bit_bl, bit_el = bits.read()
-        return self._frame_result(v, bit_bl, bit_el)
+        if bits.out_of_range:
+            x_bl, x_el, dpb, w = redo
+
+            def again():
+                graphs, self.use_graphs = self.use_graphs, False
+                try:
+                    return self.forward_one_frame(x_bl, x_el, None, None, None, None, _dpb=dpb, _write=w)
+                finally:
+                    self.use_graphs = graphs
+            return _recode_fp32(self, "LSSVC.forward_one_frame", again)
+        return self._frame_result(v, bit_bl, bit_el, token=token)
 
     # ---- whole-frame CUDA graph ---------------------------------------------------------------------------------
     # A P-frame is ~530 kernel launches with static shapes: after one eager frame per input signature (which packs the
     # weights and warms the allocator) the launches are captured once and replayed; inputs are staged into static
     # buffers, results leave as fresh tensors, the only host<->device sync stays the read of the two bit counters.
-    def _forward_graphed(self, x_bl, x_el, dpb):
+    # `lane` (runner.py): coding lanes of one GPU share the model (weights, packed weights) but replay their own graphs —
+    # a graph owns its static inputs / outputs, and lanes run concurrently on their own streams.
+    lane = 0
+
+    def _forward_graphed(self, x_bl, x_el, dpb, _async=False):
         fbt, fet = dpb.get("ref_feature_bl"), dpb.get("ref_feature_el")
-        key = (tuple(x_bl.shape), tuple(x_el.shape), None if fbt is None else tuple(fbt.shape),
+        key = (self.lane, tuple(x_bl.shape), tuple(x_el.shape), None if fbt is None else tuple(fbt.shape),
                None if fet is None else tuple(fet.shape))
         g = self._graphs.get(key)
         if g is None or g == "warm":
@@ -814,8 +869,7 @@ class LSSVC(Engine):
                 v = self._frame_core(self.image_view(x_bl), self.image_view(x_el), self._dpb_view(dpb, "ref_frame_bl", True),
                                      self._dpb_view(dpb, "ref_frame_el", True), self._dpb_view(dpb, "ref_feature_bl", False),
                                      self._dpb_view(dpb, "ref_feature_el", False), bits, None)
-                bit_bl, bit_el = bits.read()
-                return self._frame_result(v, bit_bl, bit_el)
+                return self._frame_done(v, bits, _async, redo=(x_bl, x_el, dpb, None))
             g = self._graphs[key] = self._capture_frame(x_bl, x_el, dpb)
         # ---- stage the inputs
         for name, t in (("x_bl", x_bl), ("x_el", x_el), ("ref_frame_bl", dpb["ref_frame_bl"]), ("ref_frame_el", dpb["ref_frame_el"])):
@@ -830,8 +884,9 @@ class LSSVC(Engine):
         g["gen"] += 1
         g["graph"].replay()
         _lib.load().lssvc_launch_count_add(g["launches"])
-        bit_bl, bit_el = g["bits"].read()
-        return self._frame_result(g["out"], bit_bl, bit_el, token=(g, g["gen"]))
+        # the graph zeroes its static counters at the start of every replay: an asynchronous caller gets a snapshot
+        bits = _Bits(self.device, g["bits"].t.clone()) if _async else g["bits"]
+        return self._frame_done(g["out"], bits, _async, token=(g, g["gen"]), redo=(x_bl, x_el, dpb, None))
 
     def _capture_frame(self, x_bl, x_el, dpb):
         dev = self.device
@@ -851,7 +906,9 @@ class LSSVC(Engine):
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         l0 = _lib.launch_count()
-        with torch.cuda.graph(graph):
+        # the frame graphs of one lane never run concurrently (the P-chain is serial): they share one memory pool
+        pool = self._graph_pools.setdefault(self.lane, torch.cuda.graph_pool_handle())
+        with torch.cuda.graph(graph, pool=pool):
             bits.t.zero_()
             v = self._frame_core(self.image_view(static["x_bl"]), self.image_view(static["x_el"]),
                                  self.image_view(static["ref_frame_bl"]), self.image_view(static["ref_frame_el"]),

@@ -312,6 +312,13 @@ _SAVED = _ENGINE
 # Optional launch trace (tools/join_launches.py): when TRACE is a list every conv appends its shape and engine.
 TRACE = None
 TRACE_NAME = None
+# Convolutions the tensor-core engine could not take (a view that fails the TMA alignment rules, an unsupported stride /
+# kernel size) and that ran on the fp32 CUDA-core kernel instead: a 10x slower launch nobody would otherwise notice.
+# bench.py reports the count of its timed region (`roofline.simt_downgrades`).
+SIMT_DOWNGRADES = 0
+# Frames (or stream-mode layer calls) re-coded on the fp32 engine because an operand of the split-fp16 kernels left the fp16
+# range (csrc/range.cu, models._recode_fp32).
+RANGE_FALLBACKS = 0
 
 
 def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, out_scale=1.0,
@@ -346,6 +353,8 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
         ok = (all(s.C % 4 == 0 and s.pitch % 4 == 0 and (s.coff % 4 == 0) for s in srcs) and pc.kh * pc.kw <= 49
               and pc.stride in (1, 2) and srcs[0].H % pc.stride == 0 and srcs[0].W % pc.stride == 0)
         if not ok:
+            global SIMT_DOWNGRADES
+            SIMT_DOWNGRADES += 1
             engine = "simt"
     elif engine != "simt":
         tc_ok = (in_transform == _lib.IN_NONE and epi == _lib.EPI_PLAIN
@@ -640,6 +649,12 @@ def bitparm_quant(z, coef, z_hat=None, bits=None, sym=None):
 def eb_quant(z, coef, z_hat=None, bits=None, sym=None):
     lib = _lib.load()
     _lib.check(lib.lssvc_eb_quant(byref(z.c()), _ptr(coef), _opt(z_hat), _ptr(bits), _ptr(sym), _stream()), "eb_quant")
+
+
+def range_flag_fetch(dst):
+    """dst: 1-element float64 device tensor <- 1.0 if a split-fp16 operand left the fp16 range since the last fetch."""
+    lib = _lib.load()
+    _lib.check(lib.lssvc_range_flag_fetch(_ptr(dst), _stream()), "range_flag_fetch")
 
 
 def sse(a, b, out):

@@ -53,43 +53,62 @@ def _fraction(flips, q_ref):
     return 1.0 - bad / total
 
 
-def test_1080p_against_oracle(nets):
+def _rows_given_oracle_scales(dev, what, scales, image):
+    """CDF rows of the index kernel on the ORACLE's scales against oracle.build_indexes_* (north star: bit-exact given
+    identical scales) — every scale tensor of the frame at full size."""
+    from lssvc_b200 import entropy, ops
+    from lssvc_b200.ops import View
+    from oracle import lssvc_oracle as orc
+    want = (orc.build_indexes_image if image else orc.build_indexes_video)(scales).reshape(-1)
+    thr = (entropy.image_scale_thresholds() if image else entropy.video_scale_thresholds()).to(dev)
+    v = View.from_nchw(scales.to(dev))
+    idx = torch.empty(scales.numel(), dtype=torch.int32, device=dev)
+    ops.scale_index(v.exact(), idx, thr)
+    bad = int((idx.cpu() != want).sum())
+    print(f"  rows {what:12s} {scales.numel()} scales, {int(want.unique().numel())} distinct rows, {bad} differ")
+    assert bad == 0, f"{what}: {bad} CDF rows differ from the oracle's on identical scales"
+
+
+def _against_oracle(net_i, net_p, frames, Hf, Wf, dev, tag):
+    """I-frame + P-frame at (Hf, Wf) teacher-forced on the oracle's symbols: the north-star tolerances at full size."""
     import os
     from lssvc_b200 import ops
     from oracle import lssvc_oracle as orc
-    s, dev = nets, nets["dev"]
-    net_i, net_p = s["net_i"], s["net_p"]
     default = ops.default_engine()
     torch.set_num_threads(os.cpu_count() or 8)
     sd_i = {k: v.detach().cpu().clone() for k, v in net_i.state_dict().items()}
     sd_p = {k: v.detach().cpu().clone() for k, v in net_p.state_dict().items()}
-    x_bl, x_el = s["frames"][0]
+    x_bl, x_el = frames[0]
     with torch.no_grad():
-        o = orc.intra_ss(sd_i, x_bl, x_el, (H, W))
+        o = orc.intra_ss(sd_i, x_bl, x_el, (Hf, Wf))
     q_ref = {"bl_z_hat": o["bl"]["z_hat"], "bl_y_q": torch.round(o["bl"]["y"] - o["bl"]["means"]), "z_hat": o["z_hat"],
              "y_q": torch.round(o["y"] - o["means"])}
     xb, xe = x_bl.to(dev), x_el.to(dev)
-    got, dbg = _run(net_i, default, lambda: net_i.encode_decode(xb, xe, None, None, H // 2, W // 2, H, W), force=q_ref)
-    print(f"1080p I-frame ({default}): bits {got['bit_bl']:.0f}/{got['bit_el']:.0f} oracle {o['bit_bl']:.0f}/{o['bit_el']:.0f}")
+    got, dbg = _run(net_i, default, lambda: net_i.encode_decode(xb, xe, None, None, Hf // 2, Wf // 2, Hf, Wf), force=q_ref)
+    print(f"{tag} I-frame ({default}): bits {got['bit_bl']:.0f}/{got['bit_el']:.0f} oracle {o['bit_bl']:.0f}/{o['bit_el']:.0f}")
     assert _fraction(dbg["flips"], q_ref) >= 0.9999
     for k in ("x_hat_bl", "x_hat_el"):
         _check(k, got[k].cpu(), o[k], 1e-3)
     _check("feature_el", got["feature_el"].cpu(), o["feature_el"], 5e-3)
     for k in ("bit_bl", "bit_el"):
         assert abs(got[k] - o[k]) / o[k] < 1e-3, (k, got[k], o[k])
+    _rows_given_oracle_scales(dev, "I bl y", o["bl"]["scales"], image=True)
+    _rows_given_oracle_scales(dev, "I el y", o["scales"], image=True)
+    del got, dbg
 
     dpb = {"ref_frame_bl": o["x_hat_bl"].clamp(0, 1), "ref_frame_el": o["x_hat_el"].clamp(0, 1), "ref_feature_bl": None,
            "ref_feature_el": o["feature_el"]}
-    x_bl, x_el = s["frames"][1]
+    del o
+    x_bl, x_el = frames[1]
     with torch.no_grad():
-        o = orc.lssvc(sd_p, x_bl, x_el, dpb, (H, W), 2.0)
+        o = orc.lssvc(sd_p, x_bl, x_el, dpb, (Hf, Wf), 2.0)
     q_ref = {"bl_mv_z_hat": o["bl"]["mv_z_hat"], "bl_mv_y_q": o["bl"]["mv_y_q"], "bl_z_hat": o["bl"]["z_hat"],
              "bl_y_q": o["bl"]["y_q"], "mv_z_hat": o["mv_z_hat"], "mv_y_q": o["mv_y_q"], "z_hat": o["z_hat"],
              "y_q": o["four_part"]["y_q"]}
     xb, xe = x_bl.to(dev), x_el.to(dev)
     dpb_dev = {k: (None if v is None else v.to(dev)) for k, v in dpb.items()}
-    got, dbg = _run(net_p, default, lambda: net_p.encode_decode(xb, xe, dpb_dev, None, None, W, H, W // 2, H // 2), force=q_ref)
-    print(f"1080p P-frame ({default}): bits {got['bit_bl']:.0f}/{got['bit_el']:.0f} oracle {o['bit_bl']:.0f}/{o['bit_el']:.0f}")
+    got, dbg = _run(net_p, default, lambda: net_p.encode_decode(xb, xe, dpb_dev, None, None, Wf, Hf, Wf // 2, Hf // 2), force=q_ref)
+    print(f"{tag} P-frame ({default}): bits {got['bit_bl']:.0f}/{got['bit_el']:.0f} oracle {o['bit_bl']:.0f}/{o['bit_el']:.0f}")
     assert _fraction(dbg["flips"], q_ref) >= 0.9999
     for k in ("mv_hat", "warp_frame"):
         _check(k, got[k].cpu(), o[k], 1e-3)
@@ -99,6 +118,14 @@ def test_1080p_against_oracle(nets):
         _check(k, got["dpb"][k].cpu(), o["dpb"][k], 5e-3)
     for k in ("bit_bl", "bit_el"):
         assert abs(got[k] - o[k]) / o[k] < 1e-3, (k, got[k], o[k])
+    _rows_given_oracle_scales(dev, "P bl mv_y", o["bl"]["mv_scales"], image=False)
+    _rows_given_oracle_scales(dev, "P bl y", o["bl"]["scales"], image=False)
+    _rows_given_oracle_scales(dev, "P el mv_y", o["mv_scales"], image=False)
+    _rows_given_oracle_scales(dev, "P el y", o["four_part"]["scales_hat"], image=False)
+
+
+def test_1080p_against_oracle(nets):
+    _against_oracle(nets["net_i"], nets["net_p"], nets["frames"], H, W, nets["dev"], "1080p")
 
 
 def test_1080p_bitstream_round_trip(nets, tmp_path):
@@ -178,3 +205,19 @@ def test_4k_stream_round_trip(cuda_device, tmp_path):
         assert torch.equal(r["dpb"][k], est["dpb"][k]), f"4K P-frame: decoder differs from the forward pass in {k}"
     print(f"4K P-frame: BL {(tmp_path / 'p_bl.bin').stat().st_size} B, EL {(tmp_path / 'p_el.bin').stat().st_size} B written; "
           f"estimated {est['bit_bl'] / 8:.0f} / {est['bit_el'] / 8:.0f} B")
+
+
+def test_4k_against_oracle(cuda_device):
+    """BASELINE config 5 against the oracle itself (same contract as at 1080p): the CPU restatement needs ~50 GB of host
+    memory and a couple of minutes for a 4K I-frame + P-frame, so the test requires 96 GB of free host RAM."""
+    import psutil
+    from lssvc_b200 import IntraSS, LSSVC_extend, synth
+    free = psutil.virtual_memory().available / 2 ** 30
+    if free < 96:
+        pytest.skip(f"4K oracle needs ~50 GB of host memory; {free:.0f} GB available")
+    Hk, Wk = 2176, 3840
+    net_i = IntraSS(seed=0).to(cuda_device)
+    net_p = LSSVC_extend(seed=1).to(cuda_device)
+    for n in (net_i, net_p):
+        n.set_scale_information(2.0, (Hk, Wk), (0, 0, 0, 0))
+    _against_oracle(net_i, net_p, synth.make_sequence(Hk, Wk, 2, seed=4), Hk, Wk, cuda_device, "4K")
