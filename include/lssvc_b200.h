@@ -47,8 +47,8 @@ typedef struct {
 #define LSSVC_IN_SQUARE 1 /* x*x, used by GDN's norm pool */
 #define LSSVC_IN_LRELU 2
 
-#define LSSVC_PREC_TF32 0   /* tensor core reads the fp32 operands as TF32 (10 mantissa bits)            */
-#define LSSVC_PREC_3XTF32 1 /* error-compensated: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32-reference parity */
+#define LSSVC_PREC_TF32 0   /* reserved (study engines under tools/engines/, not in this library)          */
+#define LSSVC_PREC_3XTF32 1 /* reserved                                                                    */
 #define LSSVC_PREC_H2 2     /* split-fp16: a = a_hi + a_lo, w = w_hi + w_lo in fp16 (22 significant bits each),
                                3 kind::f16 MMAs per product, hi*hi and the cross terms in separate fp32 accumulators */
 
@@ -92,11 +92,10 @@ typedef struct {
   lssvc_view out2;
   float slope2;
   lssvc_view gdn_x;
-  /* tensor-core path only: LSSVC_PREC_*; weight_split is [2*kh*kw][n_pad][cin_total] = (w_hi taps | w_lo taps)
-   * with w_hi = rn_tf32(w) and w_lo = rn_tf32(w - w_hi), required for LSSVC_PREC_3XTF32 */
+  /* lssvc_conv_hs: LSSVC_PREC_H2; weight_split is reserved (NULL) */
   int32_t precision;
   const float *weight_split;
-  /* lssvc_conv_h2 only: fp16 weights [kh*kw][2 (hi, lo)][n_pad][cin_pad16] of w * 2^w_shift (a power of two that
+  /* lssvc_conv_hs only: fp16 weights [kh*kw][2 (hi, lo)][n_pad][cin_pad16] of w * 2^w_shift (a power of two that
    * moves max|w| to [2^13, 2^14) so that w_lo stays a normal fp16), cin_pad16 = sum of src[i].C rounded up to 16
    * (each source's channels start at a multiple of 16), acc_scale = 2^-w_shift applied to the accumulator. */
   const void *weight_h2;
@@ -152,14 +151,11 @@ int64_t lssvc_launch_count(void);
 void lssvc_launch_count_add(int64_t n);
 
 /* ---- convolutions ------------------------------------------------------------------------ */
-/* tcgen05 / TMEM / TMA implicit-GEMM (TF32 operands, fp32 accumulate). */
-int32_t lssvc_conv_tc(const lssvc_conv *c, void *stream);
-/* tcgen05 kind::f16 implicit GEMM on split-fp16 operands (LSSVC_PREC_H2): activations are split in flight
- * (fp32 halo tile by TMA -> hi/lo fp16 -> tensor memory), weights are pre-split (weight_h2).  Any kernel size,
- * stride 1 or 2, up to 3 concatenated sources, input transform (GDN's x^2), GDN / IGDN epilogue. */
-int32_t lssvc_conv_h2(const lssvc_conv *c, void *stream);
-/* same arithmetic and arguments as lssvc_conv_h2; the activation operand is read by the tensor core straight from the
- * converted halo tile in shared memory (tap = shifted descriptor), 16x8 / 16x16 pixel tiles (csrc/conv_hs.cu) */
+/* tcgen05 kind::f16 implicit GEMM on split-fp16 operands (LSSVC_PREC_H2), the convolution of the path: activations are
+ * split in flight (fp32 halo tile by TMA -> [fp16 hi | fp16 lo] in place in shared memory, read by the tensor core straight
+ * from there: a filter tap = a shifted descriptor), weights are pre-split (weight_h2); 16x8 / 16x16 pixel tiles, any kernel
+ * size up to 7x7, stride 1 or 2, up to 3 concatenated sources, input transform (LeakyReLU, GDN's x^2), GDN / IGDN epilogue,
+ * residuals, PixelShuffle (csrc/conv_hs.cu).  Needs every source's C, pitch and pointer 16-byte aligned. */
 int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream);
 /* fused 1x1 -> LeakyReLU -> 1x1 -> LeakyReLU -> + identity block (see lssvc_ffn) */
 int32_t lssvc_conv_ffn(const lssvc_ffn *f, void *stream);
@@ -206,10 +202,13 @@ int32_t lssvc_spynet_prep(const lssvc_view *im1, const lssvc_view *im2, const ls
  * resolution (3*G*O channels = o1 | o2 | mask); it is bilinearly x2-upsampled on the fly,
  * offset = mag * tanh(o) + flow, the feature is warped per (group, offset) and multiplied by
  * sigmoid(mask); result is the (C * O)-channel tensor fed to the grouped 1x1 fusion conv,
- * which is applied here too: out[g*cg + k] = sum_{j<2cg} w[g*cg+k][j] * warped[g*2cg + j] + b. */
+ * which is applied here too: out[g*cg + k] = sum_{j<2cg} w[g*cg+k][j] * warped[g*2cg + j] + b.
+ * scratch: device buffer of G * H * W * 4 floats (16-byte aligned) for the group-planar copy of x the coalesced gather
+ * reads ([G][H][W] float4); NULL selects the direct NHWC gather (same results, ~4x slower at 1080p). */
 int32_t lssvc_offset_diversity(const lssvc_view *x, const lssvc_view *off, const lssvc_view *flow,
                                const float *fusion_w, const float *fusion_b, int32_t groups,
-                               int32_t offset_num, float magnitude, const lssvc_view *out, void *stream);
+                               int32_t offset_num, float magnitude, const lssvc_view *out, float *scratch,
+                               void *stream);
 
 /* ---- entropy models ---------------------------------------------------------------------- */
 /* Laplace branch (LSSVC_net.py:154-161, 466-473; dmc_net.py:370-377, 429-449):

@@ -73,8 +73,6 @@ _SIGNATURES = {
     "lssvc_range_flag_fetch": (c_int32, [c_void_p, c_void_p]),
     "lssvc_launch_count": (c_int64, []),
     "lssvc_launch_count_add": (None, [c_int64]),
-    "lssvc_conv_tc": (c_int32, [POINTER(CConv), c_void_p]),
-    "lssvc_conv_h2": (c_int32, [POINTER(CConv), c_void_p]),
     "lssvc_conv_hs": (c_int32, [POINTER(CConv), c_void_p]),
     "lssvc_conv_ffn": (c_int32, [POINTER(CFfn), c_void_p]),
     "lssvc_conv_pw": (c_int32, [POINTER(CPw), c_void_p]),
@@ -90,7 +88,7 @@ _SIGNATURES = {
     "lssvc_avgpool2": (c_int32, [_PV, _PV, c_void_p]),
     "lssvc_maxpool2": (c_int32, [_PV, _PV, c_void_p]),
     "lssvc_spynet_prep": (c_int32, [_PV, _PV, _PV, _PV, _PV, c_void_p]),
-    "lssvc_offset_diversity": (c_int32, [_PV, _PV, _PV, c_void_p, c_void_p, c_int32, c_int32, c_float, _PV, c_void_p]),
+    "lssvc_offset_diversity": (c_int32, [_PV, _PV, _PV, c_void_p, c_void_p, c_int32, c_int32, c_float, _PV, c_void_p, c_void_p]),
     "lssvc_laplace_quant": (c_int32, [_PV, _PV, _PV, _PV, _PV, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "lssvc_four_part_step": (c_int32, [_PV, _PV, c_int32, _PV, _PV, _PV, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "lssvc_four_part_index": (c_int32, [_PV, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),

@@ -606,6 +606,113 @@ __global__ void __launch_bounds__(TPB) offset_diversity_kernel(const float *__re
   for (int k = 0; k < CG; ++k) out[pix * outp + g * CG + k] = acc[k];
 }
 
+// ---- OffsetDiversity, group-planar variant --------------------------------------------------------------------------
+// The kernel above gives the 16 groups of a pixel to 16 neighbouring lanes; every (group, offset) has its OWN sampling
+// position, so a warp-level load touches 32 scattered 12-byte pieces of the NHWC feature (one 32-byte sector each: 8.6 % of
+// the copy bandwidth).  Offsets vary smoothly in SPACE, not across groups: with the feature regrouped as [G][H][W] float4
+// (3 channels + pad) and lanes running along x for a fixed group, the four corner loads of a warp hit two runs of
+// ~33 contiguous float4 — fully coalesced.  Same arithmetic in the same order as offset_diversity_kernel (bit-identical).
+constexpr int OD_PX = 64;  // pixels per block of the regroup kernel
+
+// x [H*W][xp] (C = 3 * G channels) -> planar [G][H*W] float4 = (c0, c1, c2, 0): coalesced on both sides through shared memory
+__global__ void __launch_bounds__(TPB) od_regroup_kernel(const float *__restrict__ xin, int xp, float4 *__restrict__ planar, int G,
+                                                         long long pixels) {
+  __shared__ float tile[OD_PX][49];
+  const int C = 3 * G;
+  const long long pix0 = static_cast<long long>(blockIdx.x) * OD_PX;
+  for (int i = threadIdx.x; i < OD_PX * C; i += TPB) {
+    const int p = i / C, c = i - p * C;
+    tile[p][c] = pix0 + p < pixels ? xin[(pix0 + p) * xp + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < OD_PX * G; j += TPB) {
+    const int g = j / OD_PX, p = j - g * OD_PX;
+    if (pix0 + p < pixels)
+      planar[static_cast<long long>(g) * pixels + pix0 + p] = make_float4(tile[p][3 * g], tile[p][3 * g + 1], tile[p][3 * g + 2], 0.f);
+  }
+}
+
+// block = G warps x 32 lanes: warp g codes group g of 32 consecutive pixels of one row; outputs staged in shared memory and
+// written as 32 x C contiguous floats.  O == 2, 3 channels per group (the configuration of the reference).
+template <bool VEC_OFF>
+__global__ void __launch_bounds__(512) od_planar_kernel(const float4 *__restrict__ planar, const float *__restrict__ off, int op,
+                                                        const float *__restrict__ flow, int fp, const float *__restrict__ fw,
+                                                        const float *__restrict__ fb, int G, float mag, float *__restrict__ out,
+                                                        int outp, int H, int W) {
+  constexpr int O = 2, CG = 3;
+  __shared__ float stage[32][49];
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = (W + 31) / 32;
+  const int y = blockIdx.x / tiles_x;
+  const int x = (blockIdx.x - y * tiles_x) * 32 + lane;
+  const long long pixels = static_cast<long long>(H) * W;
+  if (x < W && g < G) {
+    const long long pix = static_cast<long long>(y) * W + x;
+    const int Hc = H / 2, Wc = W / 2;
+    const int n_off = G * O;
+    int bx0, bx1, by0, by1;
+    float bwx, bwy;
+    resize_coord(x, 0.5f, Wc, bx0, bx1, bwx);
+    resize_coord(y, 0.5f, Hc, by0, by1, bwy);
+    const float hx = 1.f - bwx, hy = 1.f - bwy;
+    const float *q00 = off + (static_cast<long long>(by0) * Wc + bx0) * op, *q01 = off + (static_cast<long long>(by0) * Wc + bx1) * op;
+    const float *q10 = off + (static_cast<long long>(by1) * Wc + bx0) * op, *q11 = off + (static_cast<long long>(by1) * Wc + bx1) * op;
+    float upv[3 * O];
+    if (VEC_OFF) {
+      const float4 a4 = __ldg(reinterpret_cast<const float4 *>(q00 + 4 * g)), b4 = __ldg(reinterpret_cast<const float4 *>(q01 + 4 * g));
+      const float4 d4 = __ldg(reinterpret_cast<const float4 *>(q10 + 4 * g)), e4 = __ldg(reinterpret_cast<const float4 *>(q11 + 4 * g));
+      const float2 a2 = __ldg(reinterpret_cast<const float2 *>(q00 + 2 * n_off + 2 * g)), b2 = __ldg(reinterpret_cast<const float2 *>(q01 + 2 * n_off + 2 * g));
+      const float2 d2 = __ldg(reinterpret_cast<const float2 *>(q10 + 2 * n_off + 2 * g)), e2 = __ldg(reinterpret_cast<const float2 *>(q11 + 2 * n_off + 2 * g));
+      auto up4 = [&](float v00, float v01, float v10, float v11) { return hy * (hx * v00 + bwx * v01) + bwy * (hx * v10 + bwx * v11); };
+      upv[0] = up4(a4.x, b4.x, d4.x, e4.x); upv[1] = up4(a4.y, b4.y, d4.y, e4.y);
+      upv[2] = up4(a4.z, b4.z, d4.z, e4.z); upv[3] = up4(a4.w, b4.w, d4.w, e4.w);
+      upv[4] = up4(a2.x, b2.x, d2.x, e2.x); upv[5] = up4(a2.y, b2.y, d2.y, e2.y);
+    } else {
+      auto up1 = [&](int ch) { return hy * (hx * q00[ch] + bwx * q01[ch]) + bwy * (hx * q10[ch] + bwx * q11[ch]); };
+#pragma unroll
+      for (int t = 0; t < O; ++t) {
+        upv[2 * t] = up1(2 * (g * O + t));
+        upv[2 * t + 1] = up1(2 * (g * O + t) + 1);
+        upv[2 * O + t] = up1(2 * n_off + g * O + t);
+      }
+    }
+    const float flx = flow[pix * fp], fly = flow[pix * fp + 1];
+    float acc[CG];
+#pragma unroll
+    for (int k = 0; k < CG; ++k) acc[k] = fb[g * CG + k];
+#pragma unroll
+    for (int t = 0; t < O; ++t) {
+      const int n = g * O + t;
+      const int xg = n % G;
+      const float ox = mag * tanhf(upv[2 * t]) + flx;
+      const float oy = mag * tanhf(upv[2 * t + 1]) + fly;
+      const float mk = 1.f / (1.f + expf(-upv[2 * O + t]));
+      int x0, x1, y0, y1;
+      float wx, wy;
+      warp_coords(x, y, ox, oy, W, H, x0, x1, y0, y1, wx, wy);
+      const float4 *base = planar + static_cast<long long>(xg) * pixels;
+      const float4 a = __ldg(base + static_cast<long long>(y0) * W + x0), b = __ldg(base + static_cast<long long>(y0) * W + x1);
+      const float4 d = __ldg(base + static_cast<long long>(y1) * W + x0), e = __ldg(base + static_cast<long long>(y1) * W + x1);
+      const float v[CG] = {bilerp(a.x, b.x, d.x, e.x, wx, wy) * mk, bilerp(a.y, b.y, d.y, e.y, wx, wy) * mk,
+                           bilerp(a.z, b.z, d.z, e.z, wx, wy) * mk};
+#pragma unroll
+      for (int j = 0; j < CG; ++j) {
+#pragma unroll
+        for (int k = 0; k < CG; ++k) acc[k] = fmaf(fw[(g * CG + k) * (O * CG) + t * CG + j], v[j], acc[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CG; ++k) stage[lane][g * CG + k] = acc[k];
+  }
+  __syncthreads();
+  const int C = G * CG;
+  const int x_base = (blockIdx.x - y * tiles_x) * 32;
+  for (int i = threadIdx.x; i < 32 * C; i += blockDim.x) {
+    const int p = i / C, c = i - p * C;
+    if (x_base + p < W) out[(static_cast<long long>(y) * W + x_base + p) * outp + c] = stage[p][c];
+  }
+}
+
 __global__ void sse_kernel(const float *__restrict__ a, int ap, const float *__restrict__ b, int bp, int C,
                            long long pixels, double *__restrict__ out) {
   double local = 0.0;
@@ -848,7 +955,8 @@ extern "C" int32_t lssvc_spynet_prep(const lssvc_view *im1, const lssvc_view *im
 
 extern "C" int32_t lssvc_offset_diversity(const lssvc_view *x, const lssvc_view *off, const lssvc_view *flow,
                                           const float *fusion_w, const float *fusion_b, int32_t groups,
-                                          int32_t offset_num, float magnitude, const lssvc_view *out, void *stream) {
+                                          int32_t offset_num, float magnitude, const lssvc_view *out, float *scratch,
+                                          void *stream) {
   LSSVC_REQUIRE(lssvc::view_ok(x) && lssvc::view_ok(off) && lssvc::view_ok(flow) && lssvc::view_ok(out),
                 "offset_diversity: bad view");
   LSSVC_REQUIRE(groups > 0 && x->C % groups == 0 && x->C / groups == 3 && offset_num == 2,
@@ -860,6 +968,27 @@ extern "C" int32_t lssvc_offset_diversity(const lssvc_view *x, const lssvc_view 
                 "offset_diversity: size mismatch");
   const long long total = static_cast<long long>(x->H) * x->W * groups;
   const bool vec_off = off->pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(off->ptr) & 15) == 0;
+  static const bool legacy = getenv("LSSVC_GATHER_LEGACY") != nullptr;
+  if (scratch != nullptr && !legacy && groups <= 16) {
+    // group-planar path: regroup the feature once ([G][H][W] float4 in `scratch`), then gather with lanes along x
+    LSSVC_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "offset_diversity: scratch must be 16-byte aligned");
+    const long long pixels = static_cast<long long>(x->H) * x->W;
+    float4 *planar = reinterpret_cast<float4 *>(scratch);
+    od_regroup_kernel<<<static_cast<int>((pixels + OD_PX - 1) / OD_PX), TPB, 0, lssvc::as_stream(stream)>>>(x->ptr, x->pitch, planar,
+                                                                                                         groups, pixels);
+    LSSVC_LAUNCHED();
+    const int blocks = x->H * ((x->W + 31) / 32);
+    if (vec_off)
+      od_planar_kernel<true><<<blocks, 32 * groups, 0, lssvc::as_stream(stream)>>>(planar, off->ptr, off->pitch, flow->ptr, flow->pitch,
+                                                                                  fusion_w, fusion_b, groups, magnitude, out->ptr,
+                                                                                  out->pitch, x->H, x->W);
+    else
+      od_planar_kernel<false><<<blocks, 32 * groups, 0, lssvc::as_stream(stream)>>>(planar, off->ptr, off->pitch, flow->ptr, flow->pitch,
+                                                                                   fusion_w, fusion_b, groups, magnitude, out->ptr,
+                                                                                   out->pitch, x->H, x->W);
+    LSSVC_LAUNCHED();
+    return LSSVC_OK;
+  }
   if (vec_off)
     offset_diversity_kernel<3, 2, true><<<blocks_for(total), TPB, 0, lssvc::as_stream(stream)>>>(
         x->ptr, x->pitch, off->ptr, off->pitch, flow->ptr, flow->pitch, fusion_w, fusion_b, groups, magnitude, out->ptr,

@@ -94,7 +94,7 @@ def _recode_fp32(model, what, call):
         import warnings
         warnings.warn(f"lssvc_b200: {what}: an activation reached the fp16 limit of the split-fp16 tensor-core engine "
                       "(|x| >= 65520, or a GDN input beyond 255.9); the frame is re-coded on the fp32 CUDA-core engine "
-                      "(about 10x slower). Set LSSVC_CONV_ENGINE=tc3 to avoid the split-fp16 engine for this checkpoint.")
+                      "(about 10x slower). Set LSSVC_CONV_ENGINE=simt to keep this checkpoint off the split-fp16 engine altogether.")
         model._range_warned = True
     prev = ops.set_engine("simt")
     try:

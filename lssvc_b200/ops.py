@@ -164,7 +164,7 @@ class PackedConv:
     """Weights of one Conv2d repacked for the kernels: [kh*kw][n_pad][cin_total] + bias[n_pad]."""
 
     __slots__ = ("weight", "bias", "kh", "kw", "stride", "pad", "cout", "n_pad", "cin_total", "src_c", "pixel_shuffle",
-                 "_split", "_h2", "exact_in")
+                 "_h2", "exact_in")
 
     def __init__(self, w, b, stride=1, pad=None, src_channels=None, pixel_shuffle=False, transposed=False, device=None,
                  exact_in=False):
@@ -206,11 +206,10 @@ class PackedConv:
         self.cout, self.n_pad, self.cin_total = cout, n_pad, cin_total
         self.src_c = [v for _, v in src_channels]
         self.pixel_shuffle = pixel_shuffle
-        self._split = None
         self._h2 = None
 
     def weight_h2(self):
-        """Split-fp16 weights for lssvc_conv_h2: (fp16 [taps][2 (hi, lo)][n_pad][cin_pad16], cin_pad16, acc_scale).
+        """Split-fp16 weights for lssvc_conv_hs: (fp16 [taps][2 (hi, lo)][n_pad][cin_pad16], cin_pad16, acc_scale).
         The weights are first scaled by the power of two that puts max|w| in [2^13, 2^14), so that w_lo is a normal
         fp16 for every weight that matters; acc_scale = 2^-shift undoes it on the fp32 accumulator (exact).
         Each source's channels start at a multiple of 16 (the MMA's K step); pad columns are zero."""
@@ -243,26 +242,16 @@ class PackedConv:
             self._h2 = (packed.contiguous(), cin16, 2.0 ** -shift)
         return self._h2
 
-    def weight_split(self):
-        """(w_hi | w_lo) along the tap axis for the 3xTF32 kernel: w_hi = rn_tf32(w), w_lo = rn_tf32(w - w_hi)."""
-        if self._split is None:
-            rn = lambda t: ((t.view(torch.int32) + 4096) & -8192).view(torch.float32)
-            hi = rn(self.weight)
-            self._split = torch.cat([hi, rn(self.weight - hi)], dim=0).contiguous()
-        return self._split
-
 
 # Convolution engines:
-#   "simt" fp32 CUDA cores (exact fp32 arithmetic)
-#   "tc"   tcgen05 kind::tf32, operands truncated to TF32 by the tensor core (fast, ~5e-4 relative error per conv)
-#   "tc3"  tcgen05 kind::tf32, error-compensated 3xTF32 (fp32-level accuracy: the parity configuration)
+#   "h2"   split-fp16 on tcgen05 (csrc/conv_hs.cu): fp32-level accuracy, the engine of the path
+#   "simt" fp32 CUDA cores (csrc/conv_simt.cu): exact fp32 arithmetic — the on-device cross-check, the home of views the TMA
+#          path cannot address, and what a frame is re-coded on when its activations leave the fp16 range (csrc/range.cu)
+# (the earlier TF32 / 3xTF32 / TMEM-operand kernels live under tools/engines/ as study material; they are not built into
+# the library)
 ENGINES = {
     "simt": {"kernel": "conv_simt_kernel", "dtype": "f32", "peak_vs_bf16": 0.5,
              "note": "fp32 FMA on CUDA cores (no tensor cores); shown against the TF32 tensor peak for comparison"},
-    "tc": {"kernel": "conv_tc_kernel", "dtype": "tf32", "peak_vs_bf16": 0.5,
-           "note": "tcgen05.mma kind::tf32, fp32 accumulate in TMEM"},
-    "tc3": {"kernel": "conv_tc_kernel(3xTF32)", "dtype": "tf32x3", "peak_vs_bf16": 0.5,
-            "note": "tcgen05.mma kind::tf32 error-compensated 3xTF32 (3 MMAs per algorithmic MAC); FLOPs counted are algorithmic"},
     "h2": {"kernel": "conv_hs_kernel", "dtype": "f16x2-split", "peak_vs_bf16": 1.0,
            "note": "tcgen05.mma kind::f16 on split-fp16 operands (x = x_hi + x_lo; 3 MMAs per algorithmic MAC, both operands "
                    "read from shared memory, taps = shifted descriptors on one converted halo tile, hi*hi and cross terms in "
@@ -270,11 +259,6 @@ ENGINES = {
 }
 _ENGINE = os.environ.get("LSSVC_CONV_ENGINE", "h2")
 assert _ENGINE in ENGINES, _ENGINE
-# Kernel behind the "h2" (split-fp16) engine: "hs" = activation operand read from shared memory by shifted descriptors
-# (csrc/conv_hs.cu, default), "h2t" = activation operand staged in tensor memory per tap (csrc/conv_h2.cu).
-# conv(..., engine="hs" | "h2t") forces one of them for A/B tests.
-_H2_IMPL = os.environ.get("LSSVC_H2_IMPL", "hs")
-assert _H2_IMPL in ("hs", "h2t"), _H2_IMPL
 
 
 def default_engine():
@@ -289,12 +273,7 @@ def set_engine(name):
 
 
 def engine_info(name):
-    info = dict(ENGINES[name])
-    if name == "h2" and _H2_IMPL == "h2t":
-        info["kernel"] = "conv_h2_kernel"
-        info["note"] = info["note"].replace("both operands read from shared memory, taps = shifted descriptors on one converted halo tile",
-                                            "A operand staged in TMEM per tap")
-    return info
+    return dict(ENGINES[name])
 
 
 def force_simt(flag):
@@ -324,7 +303,7 @@ RANGE_FALLBACKS = 0
 def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, out_scale=1.0,
          in_transform=_lib.IN_NONE, in_slope=0.0, epi=_lib.EPI_PLAIN, gdn_x=None, engine=None):
     """Run one packed convolution.  act: None or the LeakyReLU slope (0.0 = ReLU).
-    engine: None (the default engine), 'tc3', 'tc' or 'simt'."""
+    engine: None (the default engine), 'h2' / 'hs' or 'simt'."""
     if isinstance(srcs, View):
         srcs = [srcs]
     assert len(srcs) == len(pc.src_c), (len(srcs), pc.src_c)
@@ -346,9 +325,9 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
     d.slope2 = float(slope2)
     lib = _lib.load()
     engine = engine or _ENGINE
-    impl = _H2_IMPL
-    if engine in ("hs", "h2t"):
-        engine, impl = "h2", engine
+    if engine == "hs":
+        engine = "h2"
+    assert engine in ENGINES, engine
     if engine == "h2":
         ok = (all(s.C % 4 == 0 and s.pitch % 4 == 0 and (s.coff % 4 == 0) for s in srcs) and pc.kh * pc.kw <= 49
               and pc.stride in (1, 2) and srcs[0].H % pc.stride == 0 and srcs[0].W % pc.stride == 0)
@@ -356,36 +335,20 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
             global SIMT_DOWNGRADES
             SIMT_DOWNGRADES += 1
             engine = "simt"
-    elif engine != "simt":
-        tc_ok = (in_transform == _lib.IN_NONE and epi == _lib.EPI_PLAIN
-                 and all(s.C % 8 == 0 and s.pitch % 4 == 0 and (s.coff % 4 == 0) for s in srcs)
-                 and pc.stride in (1, 2) and srcs[0].H % pc.stride == 0 and srcs[0].W % pc.stride == 0)
-        if not tc_ok:
-            engine = "simt"
     if TRACE is not None:
         Ho, Wo = (out.H // 2, out.W // 2) if pc.pixel_shuffle else (out.H, out.W)
-        TRACE.append({"name": TRACE_NAME, "engine": engine if engine != "h2" else impl, "k": pc.kh, "stride": pc.stride, "cin": pc.cin_total,
+        TRACE.append({"name": TRACE_NAME, "engine": "hs" if engine == "h2" else engine, "k": pc.kh, "stride": pc.stride, "cin": pc.cin_total,
                       "src_c": list(pc.src_c), "cout": pc.cout, "Ho": Ho, "Wo": Wo, "ps": bool(pc.pixel_shuffle),
                       "extras": ("r" if res1 is not None else "") + ("s" if res2 is not None else "") + ("o" if out2 is not None else "")
                                 + ("l" if in_transform == _lib.IN_LRELU else "") + ("g" if epi != _lib.EPI_PLAIN else ""),
                       "flops": 2.0 * Ho * Wo * pc.kh * pc.kw * sum(s.real for s in srcs) * pc.cout})
     if engine == "simt":
         _lib.check(lib.lssvc_conv_simt(byref(d), _stream()), "conv_simt")
-    elif engine == "h2":
+    else:
         wh, cin16, acc_scale = pc.weight_h2()
         d.precision = _lib.PREC_H2
         d.weight_h2, d.cin_pad16, d.acc_scale = wh.data_ptr(), cin16, acc_scale
-        if impl == "hs":
-            _lib.check(lib.lssvc_conv_hs(byref(d), _stream()), "conv_hs")
-        else:
-            _lib.check(lib.lssvc_conv_h2(byref(d), _stream()), "conv_h2")
-    else:
-        if engine == "tc3":
-            d.precision = _lib.PREC_3XTF32
-            d.weight_split = pc.weight_split().data_ptr()
-        else:
-            d.precision = _lib.PREC_TF32
-        _lib.check(lib.lssvc_conv_tc(byref(d), _stream()), "conv_tc")
+        _lib.check(lib.lssvc_conv_hs(byref(d), _stream()), "conv_hs")
     return out
 
 
@@ -582,10 +545,12 @@ def spynet_prep(im1, im2, flow_coarse, out8, flow_up):
                "spynet_prep")
 
 
-def offset_diversity(x, off, flow, fusion_w, fusion_b, groups, offset_num, magnitude, out):
+def offset_diversity(x, off, flow, fusion_w, fusion_b, groups, offset_num, magnitude, out, planar=True):
+    """planar: regroup x into a [G][H][W] float4 scratch first so that the per-(group, offset) gathers coalesce."""
     lib = _lib.load()
+    scratch = torch.empty(groups * x.H * x.W * 4, dtype=torch.float32, device=x.device) if planar else None
     _lib.check(lib.lssvc_offset_diversity(byref(x.c()), byref(off.c()), byref(flow.c()), _ptr(fusion_w), _ptr(fusion_b),
-                                          groups, offset_num, float(magnitude), byref(out.c()), _stream()),
+                                          groups, offset_num, float(magnitude), byref(out.c()), _ptr(scratch), _stream()),
                "offset_diversity")
     return out
 

@@ -108,7 +108,7 @@ class GopRunner:
                 # the lanes run ahead of the host: the frames behind this one already used its DPB, so there is nothing to
                 # re-code in place (the synchronous API does that, models._recode_fp32)
                 raise _lib.LssvcError(f"sequence {meta[0]} frame {meta[1]}: an activation reached the fp16 limit of the split-fp16 "
-                                      "tensor-core engine; run this job with LSSVC_CONV_ENGINE=tc3 (or through the synchronous API, "
+                                      "tensor-core engine; run this job with LSSVC_CONV_ENGINE=simt (or through the synchronous API, "
                                       "which re-codes such frames on the fp32 engine)")
             rows.append(meta + tuple(stats[:4]))
 

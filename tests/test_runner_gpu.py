@@ -59,6 +59,7 @@ def test_runner_lanes_reproduce_the_frame_loop(cuda_device):
             assert abs(frontend.psnr(x_el, re) - 10 * torch.log10(torch.tensor(x_el.numel() / sse[1])).item()) < 1e-6
     want = torch.tensor(want, dtype=torch.float64)
 
+    first = None
     for lanes, graphs in ((1, False), (2, True), (3, False), (2, None)):
         runner = GopRunner(net_i, net_p, lanes=lanes, graphs=graphs)
         rows = runner.code_units(units, source)
@@ -68,8 +69,12 @@ def test_runner_lanes_reproduce_the_frame_loop(cuda_device):
         assert torch.equal(got[:, :3], want[:, :3])
         rel = ((got[:, 3:5] - want[:, 3:5]).abs() / want[:, 3:5]).max().item()
         d_sse = ((got[:, 5:] - want[:, 5:]).abs() / want[:, 5:]).max().item()
-        print(f"lanes={lanes} graphs={graphs}: bits rel {rel:.1e}, sse rel {d_sse:.1e}")
-        assert rel < 1e-9 and d_sse < 1e-12
+        # against the plain loop: the bits are the same kernels (atomics order only); the reference SSE above is torch's
+        # double-precision sum of fp32 squares, the kernel squares in double: 1e-8.  Between runner configurations: identical.
+        first = got if first is None else first
+        same = ((got[:, 3:] - first[:, 3:]).abs() / first[:, 3:]).max().item()
+        print(f"lanes={lanes} graphs={graphs}: bits rel {rel:.1e}, sse rel {d_sse:.1e}; against the one-lane runner {same:.1e}")
+        assert rel < 1e-9 and d_sse < 1e-8 and same < 1e-12
         if graphs:
             assert any(isinstance(g, dict) for g in net_p._graphs.values()), "no frame graph was captured"
     s = gop.summarize(want, H * W, H * W // 4)

@@ -110,7 +110,7 @@ def main():
     only = os.environ.get("CONV_BENCH_ONLY")
     if only:
         SHAPES[:] = [s for s in SHAPES + EXTRA if only in s[0]]
-    engines = sys.argv[1:] or ["h2", "tc3"]
+    engines = sys.argv[1:] or ["h2", "simt"]
     dev = torch.device("cuda:0")
     _lib.check(_lib.load().lssvc_device_check(0), "device_check")
     print(f"{'shape':26s} " + " ".join(f"{e + ' err':>11s} {e + ' ms':>9s} {e + ' TF/s':>9s}" for e in engines))
