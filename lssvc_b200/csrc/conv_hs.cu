@@ -818,6 +818,20 @@ int floor_div_h(int a, int b) {
 
 }  // namespace
 
+extern "C" int32_t lssvc_device_check(int32_t dev) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    lssvc::set_error("cudaGetDeviceProperties(%d): %s", dev, cudaGetErrorString(e));
+    return LSSVC_ERR_NO_DEVICE;
+  }
+  if (prop.major != 10) {
+    lssvc::set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    return LSSVC_ERR_NO_DEVICE;
+  }
+  return resolve_driver();
+}
+
 extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
   LSSVC_REQUIRE(c != nullptr, "conv_hs: null descriptor");
   LSSVC_REQUIRE(c->n_src >= 1 && c->n_src <= LSSVC_MAX_SRC, "conv_hs: n_src=%d", c->n_src);

@@ -52,6 +52,24 @@ __global__ void nhwc_to_nchw_kernel(const float *__restrict__ src, int C, int pi
   }
 }
 
+// C <= 8 (reconstructed frames, flows): the 32 x 32 transpose tile would run 3 of its 32 channel lanes; one thread per pixel
+// instead: C strided reads of one sector, C coalesced plane writes.
+__global__ void __launch_bounds__(TPB) nhwc_to_nchw_small_kernel(const float *__restrict__ src, int C, int pitch, float *__restrict__ dst,
+                                                                 long long HW) {
+  const long long pp = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pp >= HW) return;
+  const float *s = src + pp * pitch;
+  for (int c = 0; c < C; ++c) dst[static_cast<long long>(c) * HW + pp] = s[c];
+}
+
+__global__ void __launch_bounds__(TPB) nchw_to_nhwc_small_kernel(const float *__restrict__ src, int C, float *__restrict__ dst, int Cv,
+                                                                 int pitch, long long HW) {
+  const long long pp = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pp >= HW) return;
+  float *d = dst + pp * pitch;
+  for (int c = 0; c < Cv; ++c) d[c] = c < C ? src[static_cast<long long>(c) * HW + pp] : 0.f;
+}
+
 __global__ void lrelu_copy_kernel(const float *__restrict__ in, int in_pitch, float slope, float *__restrict__ out,
                                   int out_pitch, int C, long long pixels) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -766,6 +784,11 @@ bool legacy_gather() {
 extern "C" int32_t lssvc_nchw_to_nhwc(const float *src, int32_t C, const lssvc_view *out, void *stream) {
   LSSVC_REQUIRE(src && lssvc::view_ok(out) && C >= 1 && C <= out->C, "nchw_to_nhwc: bad arguments");
   const long long HW = static_cast<long long>(out->H) * out->W;
+  if (out->C <= 8) {
+    nchw_to_nhwc_small_kernel<<<blocks_for(HW), TPB, 0, lssvc::as_stream(stream)>>>(src, C, out->ptr, out->C, out->pitch, HW);
+    LSSVC_LAUNCHED();
+    return LSSVC_OK;
+  }
   dim3 grid(static_cast<unsigned>((HW + 31) / 32), lssvc::ceil_div(out->C, 32));
   nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, lssvc::as_stream(stream)>>>(src, C, out->ptr, out->C, out->pitch, HW);
   LSSVC_LAUNCHED();
@@ -775,6 +798,11 @@ extern "C" int32_t lssvc_nchw_to_nhwc(const float *src, int32_t C, const lssvc_v
 extern "C" int32_t lssvc_nhwc_to_nchw(const lssvc_view *in, float *dst, void *stream) {
   LSSVC_REQUIRE(dst && lssvc::view_ok(in), "nhwc_to_nchw: bad arguments");
   const long long HW = static_cast<long long>(in->H) * in->W;
+  if (in->C <= 8) {
+    nhwc_to_nchw_small_kernel<<<blocks_for(HW), TPB, 0, lssvc::as_stream(stream)>>>(in->ptr, in->C, in->pitch, dst, HW);
+    LSSVC_LAUNCHED();
+    return LSSVC_OK;
+  }
   dim3 grid(static_cast<unsigned>((HW + 31) / 32), lssvc::ceil_div(in->C, 32));
   nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, lssvc::as_stream(stream)>>>(in->ptr, in->C, in->pitch, dst, HW);
   LSSVC_LAUNCHED();

@@ -530,6 +530,13 @@ def test_layout_roundtrip(cuda_device):
     v = ops.View.from_nchw(x, C_view=40)
     assert torch.equal(v.slice(0, 37).to_nchw(), x)
     assert v.slice(37, 40).to_nchw().abs().max().item() == 0.0
+    # the <= 8-channel path (frames, flows): 3 data channels in an 8-channel view, ragged pixel count
+    for C, Cv in ((3, 8), (2, 8), (3, 4), (8, 8)):
+        y = torch.randn(1, C, 19, 35, device=dev)
+        w = ops.View.from_nchw(y, C_view=Cv)
+        assert torch.equal(w.exact().to_nchw(), y)
+        if Cv > C:
+            assert w.slice(C, Cv).to_nchw().abs().max().item() == 0.0
 
 
 # ---------------------------------------------------------------------------------------------------------------------
