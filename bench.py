@@ -273,6 +273,11 @@ def in_frame_roofline(torch, coder, frames_dev, peaks, gop):
     for k in ("ffn", "pw", "simt"):
         if k in fam and fam[k]["ms"] > 0:
             out[k] = {"launches": fam[k]["launches"], "ms": round(fam[k]["ms"], 2), "tflops": round(fam[k]["flops"] / fam[k]["ms"] / 1e9, 1)}
+    other = {}
+    for name, info, ms in rows:
+        if name not in ("conv", "ffn", "pw"):
+            other[name] = round(other.get(name, 0.0) + ms, 3)
+    out["other_ms"] = dict(sorted(other.items(), key=lambda kv: -kv[1]))
     return out
 
 

@@ -19,12 +19,25 @@ from .ops import View
 
 
 class _Dump:
-    """model._write hook: int32 device buffers for symbols / CDF indices (NCHW order) next to the NHWC outputs."""
+    """model._write hook: int32 device buffers for symbols / CDF indices (NCHW order) next to the NHWC outputs.
 
-    def __init__(self, device):
+    With `owner` (a model) the buffers of a layer travel to PINNED host memory as soon as the layer's last entropy kernel has
+    been issued (layer_done, called by the models): the copy runs on a side stream behind an event, so the host coder can
+    start while the GPU is still running the layer's synthesis networks.  Pinned buffers are cached on the
+    owner, two sets used alternately so that a background job of the previous frame never sees them overwritten."""
+
+    def __init__(self, device, owner=None, on_layer=None):
         self.device = device
         self.bufs = {}
         self.shapes = {}
+        self.owner = owner
+        self.on_layer = on_layer
+        self.pinned = {}
+        self.done = {}
+        if owner is not None:
+            st = owner.__dict__.setdefault("_dump_state", {"stream": torch.cuda.Stream(device=device), "sets": ({}, {}), "turn": 0})
+            st["turn"] ^= 1
+            self._copy_stream, self._cache = st["stream"], st["sets"][st["turn"]]
 
     def buf(self, name, view, C=None):
         C = view.real if C is None else C
@@ -33,7 +46,34 @@ class _Dump:
         self.shapes[name] = (C, view.H, view.W)
         return t
 
+    def layer_done(self, tag):
+        """Every dump of layer `tag` ('bl' / 'el') has been issued on the current stream."""
+        if self.owner is None:
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ev)
+            for name, t in self.bufs.items():
+                if name.startswith(tag + "_"):
+                    p = self._cache.get(name)
+                    if p is None or p.numel() != t.numel():
+                        p = self._cache[name] = torch.empty(t.numel(), dtype=torch.int32).pin_memory()
+                    p.copy_(t, non_blocking=True)
+                    self.pinned[name] = p
+            done = torch.cuda.Event()
+            done.record()
+        for name in self.pinned:
+            if name.startswith(tag + "_"):
+                self.done[name] = done
+        if self.on_layer is not None:
+            self.on_layer(tag)
+
     def host(self, name):
+        p = self.pinned.get(name)
+        if p is not None:
+            self.done[name].synchronize()
+            return p.numpy()
         return self.bufs[name].cpu().numpy()
 
     def channel_index(self, name):
@@ -150,7 +190,7 @@ def bl_compress(model, x, dpb):
     """DMCExtend.compress(x, dpb) -> {"string", "dpb": {ref_frame_bl, ref_feature_bl, y_hat_bl, mv_hat_bl}}."""
     model.update()
     t = model._tables
-    dump = _Dump(model.device)
+    dump = _Dump(model.device, owner=model)
     bl = model._base_layer(model.image_view(x), _to_view(model, dpb["ref_frame_bl"], image=True),
                            _to_view(model, dpb.get("ref_feature_bl")), _bits_scratch(model), dump)
     h = dump.host
@@ -210,7 +250,7 @@ def el_compress(model, x, dpb):
     """LSSVC_extend.compress(x, dpb): dpb carries the decoded base layer as 'texture', 'y_hat_bl', 'mv_hat_bl'."""
     model.update()
     t = model._tables
-    dump = _Dump(model.device)
+    dump = _Dump(model.device, owner=model)
     el = model._el_layer(model.image_view(x), _to_view(model, dpb["ref_frame_el"], image=True),
                          _to_view(model, dpb.get("ref_feature_el")), _to_view(model, dpb["texture"]),
                          _to_view(model, dpb["y_hat_bl"]), _to_view(model, dpb["mv_hat_bl"]), _bits_scratch(model), dump)

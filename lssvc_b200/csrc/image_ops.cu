@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(TPB) offset_diversity_kernel(const float *__re
 // position, so a warp-level load touches 32 scattered 12-byte pieces of the NHWC feature (one 32-byte sector each: 8.6 % of
 // the copy bandwidth).  Offsets vary smoothly in SPACE, not across groups: with the feature regrouped as [G][H][W] float4
 // (3 channels + pad) and lanes running along x for a fixed group, the four corner loads of a warp hit two runs of
-// ~33 contiguous float4 — fully coalesced.  Same arithmetic in the same order as offset_diversity_kernel (bit-identical).
+// ~33 contiguous float4 — fully coalesced when the offsets are smooth.  Same formulae as offset_diversity_kernel.
 constexpr int OD_PX = 64;  // pixels per block of the regroup kernel
 
 // x [H*W][xp] (C = 3 * G channels) -> planar [G][H*W] float4 = (c0, c1, c2, 0): coalesced on both sides through shared memory

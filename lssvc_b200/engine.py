@@ -138,7 +138,8 @@ class Engine(nets.ParamBag):
                 beta = torch.max(beta, torch.ones_like(beta) * ((1e-6 + ped) ** 0.5)) ** 2 - ped
                 gamma = torch.max(gamma, torch.ones_like(gamma) * (2.0 ** -18)) ** 2 - ped
             C = beta.numel()
-            return ops.PackedConv(gamma.view(C, C, 1, 1), beta, pad=0, src_channels=[(C, x.C)], device=self.device)
+            return ops.PackedConv(gamma.view(C, C, 1, 1), beta, pad=0, src_channels=[(C, x.C)], device=self.device,
+                                  coherent=os.environ.get("LSSVC_GDN_COHERENT", "1") != "0")
         pc = self.cached(("gdn", name, x.C), build)
         out = out if out is not None else self.new(x.H, x.W, x.real)
         # split-fp16 tensor-core engine: x^2 is formed and split in the kernel's operand path; the other engines keep

@@ -533,6 +533,8 @@ class LSSVC(Engine):
         ops.laplace_quant(y, prm.slice(C, 2 * C), prm.slice(0, C), None, y_hat, bits.ptr(0),
                           sym=w.buf("bl_y", y) if w else None, index=w.buf("bl_y_idx", y) if w else None, thresholds=thr)
         _force(self, "bl_y_q", y_hat, mean=prm.slice(C, 2 * C))
+        if w:
+            w.layer_done("bl")      # every symbol of the BL string is on its way to the host while the synthesis runs
         rec_feat = self._res_decoder_gdn(p + "res_decoder", y_hat, c2, c3, intra=False)
         feature, recon = self._recon_generation(p + "recon_generation_net", rec_feat, c1)
         _dbg(self, bl_mv_y=mv_y, bl_mv_y_hat=mv_y_hat, bl_mv_prm=mv_prm, bl_mv_z_hat=mv_z_hat, bl_y=y, bl_y_hat=y_hat,
@@ -793,6 +795,8 @@ class LSSVC(Engine):
         _force(self, "z_hat", z_hat)
         params = self._res_params(z_hat, c3, y_hat_bl)
         y_hat = self._four_part(y, params, bits, w)
+        if w:
+            w.layer_done("el")
         feature, recon = self._res_decode(y_hat, c1, c2, c3)
         _dbg(self, mv=mv, mv_y=mv_y, mv_y_hat=mv_y_hat, mv_prm=mv_prm, mv_z_hat=mv_z_hat, z_hat=z_hat, y=y, y_hat=y_hat,
              params=params, c1=c1, c2=c2, c3=c3)

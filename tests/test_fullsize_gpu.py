@@ -164,6 +164,10 @@ def test_1080p_bitstream_round_trip(nets, tmp_path):
         assert torch.equal(r["dpb"]["ref_frame_bl"].clamp(0, 1), est["dpb"]["ref_frame_bl"].clamp(0, 1))
         assert r["bit_bl"] == 8 * len(outs[single][0]) and r["bit_el"] == 8 * len(outs[single][1])
     net_p.single_pass_streams = False
+    from lssvc_b200 import streams
+    secs = streams.drain(net_p)                      # the background decode-and-compare of both strings passed
+    assert len(secs) == 2
+    print(f"1080p P-frame single pass: background verification BL {secs[0] * 1e3:.0f} ms, EL {secs[1] * 1e3:.0f} ms")
     assert outs[False] == outs[True]
     # the rANS strings against the estimated (entropy) bits: printed; only gross disagreement fails (random-init weights put part of the
     # symbols outside the CDF tables, where the coder escapes to bypass bits)

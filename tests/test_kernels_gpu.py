@@ -351,11 +351,11 @@ def test_offset_diversity(cuda_device):
     xx = torch_warp_ref(xx, offset) * mask
     ref = F.conv2d(xx.view(1, C * O, H, W), fw, fb, groups=G)
     assert rel_err(out.to_nchw(), ref) < 2e-5
-    # the group-planar gather (default) and the direct NHWC gather are the same arithmetic in the same order
+    # the group-planar gather (default) and the direct NHWC gather: same formulae (FMA contraction may differ in the last bit)
     direct = ops.View.alloc(H, W, C, dev)
     ops.offset_diversity(make_view(x, ops), make_view(off, ops), make_view(flow, ops), fw.reshape(C, -1).contiguous(), fb,
                          G, O, 40.0, direct, planar=False)
-    assert torch.equal(direct.to_nchw(), out.to_nchw())
+    assert rel_err(direct.to_nchw(), out.to_nchw()) < 1e-6
 
 
 def test_offset_diversity_planar_ragged(cuda_device):
@@ -372,7 +372,7 @@ def test_offset_diversity_planar_ragged(cuda_device):
     a, b = ops.View.alloc(H, W, C, dev), ops.View.alloc(H, W, C, dev)
     ops.offset_diversity(x, off, flow, fw, fb, G, O, 40.0, a)
     ops.offset_diversity(x, off, flow, fw, fb, G, O, 40.0, b, planar=False)
-    assert torch.equal(a.to_nchw(), b.to_nchw())
+    assert rel_err(a.to_nchw(), b.to_nchw()) < 1e-6
 
 
 def test_softmax_blend_and_lrelu(cuda_device):

@@ -342,6 +342,8 @@ def test_bitstream_round_trip(setup, tmp_path):
                                     W, H, W // 2, H // 2)
             outs.append(r)
         net_p.single_pass_streams = False
+        from lssvc_b200 import streams
+        assert len(streams.drain(net_p)) == 2       # the background decode-and-compare of both strings passed
         for layer in ("bl", "el"):
             a = (tmp_path / f"{layer}{frame}d.bin").read_bytes()
             b = (tmp_path / f"{layer}{frame}s.bin").read_bytes()

@@ -61,9 +61,22 @@ def run(torch, dev, H=1152, W=1920, peak_gbs=6544.7):
     G, O, C = 16, 2, 48
     fw, fb = torch.randn(C, 2 * C // G, device=dev) * 0.1, torch.randn(C, device=dev)
     sets = [(rnd(H, W, C), rnd(H // 2, W // 2, 3 * G * O, 0.5), rnd(H, W, 2, 3.0), new(H, W, C)) for _ in range(2)]
-    add("offset_diversity C=48 G=16 O=2 1152x1920",
-        _time(torch, lambda s: ops.offset_diversity(s[0], s[1], s[2], fw, fb, G, O, 40.0, s[3]), sets, n=6),
-        px * (C * 4 * 2 + 8) + (px // 4) * 96 * 4, "replaces a (32,3,H,W) grid_sample + 566 MB of grids + the grouped 1x1 conv")
+    od_bytes = px * (C * 4 * 2 + 8) + (px // 4) * 96 * 4
+    add("offset_diversity C=48 G=16 O=2 1152x1920 (i.i.d. offsets +-20 px, planar)",
+        _time(torch, lambda s: ops.offset_diversity(s[0], s[1], s[2], fw, fb, G, O, 40.0, s[3]), sets, n=6), od_bytes,
+        "worst case: every (pixel, group, offset) samples an unrelated position")
+    add("offset_diversity (i.i.d. offsets, direct NHWC gather)",
+        _time(torch, lambda s: ops.offset_diversity(s[0], s[1], s[2], fw, fb, G, O, 40.0, s[3], planar=False), sets, n=6), od_bytes)
+    import torch.nn.functional as F
+    smooth = []
+    for s in sets:      # offsets as the conv stack produces them in a frame: smooth fields (low-pass noise), a few pixels of residue
+        low = F.interpolate(torch.randn(1, 3 * G * O, H // 32, W // 32, device=dev), size=(H // 2, W // 2), mode="bicubic") * 0.1
+        smooth.append((s[0], V(low[0].permute(1, 2, 0).contiguous().reshape(-1), H // 2, W // 2, 3 * G * O, 3 * G * O), s[2], s[3]))
+    add("offset_diversity (smooth offsets, planar)",
+        _time(torch, lambda s: ops.offset_diversity(s[0], s[1], s[2], fw, fb, G, O, 40.0, s[3]), smooth, n=6), od_bytes,
+        "replaces a (32,3,H,W) grid_sample + 566 MB of grids + the grouped 1x1 conv")
+    add("offset_diversity (smooth offsets, direct NHWC gather)",
+        _time(torch, lambda s: ops.offset_diversity(s[0], s[1], s[2], fw, fb, G, O, 40.0, s[3], planar=False), smooth, n=6), od_bytes)
     # entropy: laplace quant + bits (y, mean, scale read; y_hat written) and the four-part step
     h, w = H // 16, W // 16
     bits = torch.zeros(2, dtype=torch.float64, device=dev)
