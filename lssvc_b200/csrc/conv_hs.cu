@@ -1017,7 +1017,12 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
   p.halo_tx = halo_w * halo_h * row_bytes;
   p.halo_rows = halo_w * halo_h;
   p.halo_bytes = (p.halo_tx + 1023) & ~1023;
-  p.b_bytes = tps * (2 * n_tile * kc * 2);  // n_tile % 16 == 0 keeps every tile 1024-byte aligned
+  // a weight stage holds the taps of ONE pipeline step: a 1x1 conv (one tap per step) needs half / a quarter of the room of a
+  // 3x3 one, and the shared memory it gives back goes to the halo ring below — 1x1 layers are latency-bound on that ring
+  // (one 32-channel chunk feeds only two MMA pairs per TMA round trip)
+  int max_step = 1;
+  for (int g = 0; g < p.n_groups; ++g) max_step = p.g_step[g] > max_step ? p.g_step[g] : max_step;
+  p.b_bytes = max_step * (2 * n_tile * kc * 2);  // n_tile % 16 == 0 keeps every tile 1024-byte aligned
   p.in_transform = c->in_transform;
   p.in_slope = c->in_slope;
   p.range_flag = lssvc::range_flag();

@@ -339,7 +339,7 @@ def test_offset_diversity(cuda_device):
     fb = torch.randn(C, generator=g).to(dev)
     out = ops.View.alloc(H, W, C, dev)
     ops.offset_diversity(make_view(x, ops), make_view(off, ops), make_view(flow, ops), fw.reshape(C, -1).contiguous(), fb,
-                         G, O, 40.0, out)
+                         G, O, 40.0, out, planar=True)
     # reference data flow (lssvc_modules.py:92-112)
     o = F.interpolate(off, size=(H, W), mode="bilinear", align_corners=False)
     o1, o2, mask = torch.chunk(o, 3, dim=1)
@@ -351,11 +351,13 @@ def test_offset_diversity(cuda_device):
     xx = torch_warp_ref(xx, offset) * mask
     ref = F.conv2d(xx.view(1, C * O, H, W), fw, fb, groups=G)
     assert rel_err(out.to_nchw(), ref) < 2e-5
-    # the group-planar gather (default) and the direct NHWC gather: same formulae (FMA contraction may differ in the last bit)
+    # the direct NHWC gather (default) and the group-planar variant: same formulae; the sampling position mag * tanh(o) + flow
+    # is contracted into an FMA in one and not in the other, i.e. positions differ by 1 ulp of ~40 px = 4e-6 px
     direct = ops.View.alloc(H, W, C, dev)
     ops.offset_diversity(make_view(x, ops), make_view(off, ops), make_view(flow, ops), fw.reshape(C, -1).contiguous(), fb,
-                         G, O, 40.0, direct, planar=False)
-    assert rel_err(direct.to_nchw(), out.to_nchw()) < 1e-6
+                         G, O, 40.0, direct)
+    assert rel_err(direct.to_nchw(), ref) < 2e-5
+    assert rel_err(direct.to_nchw(), out.to_nchw()) < 2e-5
 
 
 def test_offset_diversity_planar_ragged(cuda_device):
@@ -370,9 +372,9 @@ def test_offset_diversity_planar_ragged(cuda_device):
     fw = torch.randn(C, C * O // G, generator=g).to(dev)
     fb = torch.randn(C, generator=g).to(dev)
     a, b = ops.View.alloc(H, W, C, dev), ops.View.alloc(H, W, C, dev)
-    ops.offset_diversity(x, off, flow, fw, fb, G, O, 40.0, a)
-    ops.offset_diversity(x, off, flow, fw, fb, G, O, 40.0, b, planar=False)
-    assert rel_err(a.to_nchw(), b.to_nchw()) < 1e-6
+    ops.offset_diversity(x, off, flow, fw, fb, G, O, 40.0, a, planar=True)
+    ops.offset_diversity(x, off, flow, fw, fb, G, O, 40.0, b)
+    assert rel_err(a.to_nchw(), b.to_nchw()) < 2e-5
 
 
 def test_softmax_blend_and_lrelu(cuda_device):

@@ -29,41 +29,20 @@ def main():
     _lib.check(_lib.load().lssvc_device_check(0), "device_check")
     frames, shape_hr = bench.make_frames(bench.SIZES[args.size], 4, seed=0)
     coder = bench.Coder(dev, shape_hr)
-    records = []
-    state = {"on": False}
-    names = ["conv", "ffn", "pw", "dwconv3x3", "deconv3x3_s2", "lrelu_copy", "softmax2_blend", "flow_warp", "bilinear_resize", "avgpool2",
-             "maxpool2", "spynet_prep", "offset_diversity", "laplace_quant", "four_part_step", "gaussian_quant",
-             "bitparm_quant", "eb_quant", "sse"]
-
-    def wrap(name, fn):
-        def inner(*a, **k):
-            if not state["on"]:
-                return fn(*a, **k)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n_before = len(ops.TRACE)
-            e0.record()
-            r = fn(*a, **k)
-            e1.record()
-            info = ops.TRACE[-1] if (name in ("conv", "pw", "ffn") and len(ops.TRACE) > n_before) else None
-            records.append((name, info, e0, e1))
-            return r
-        return inner
-
-    for n in names:
-        setattr(ops, n, wrap(n, getattr(ops, n)))
-    # View.to_nchw / from_nchw use the lib directly; time them as a group through the frame total
+    from lssvc_b200 import profile
+    timer = None
     for idx, (b, e) in enumerate(frames):
         if idx == 3:
-            ops.TRACE = []
-            state["on"] = True
+            timer = profile.LaunchTimer()
+            timer.__enter__()
             torch.cuda.synchronize()
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record()
         coder.step(idx, 100, b.to(dev), e.to(dev))
     t1.record()
-    torch.cuda.synchronize()
+    rows = timer.rows()
+    timer.__exit__(None, None, None)
     total = t0.elapsed_time(t1)
-    rows = [(n, i, a.elapsed_time(b)) for n, i, a, b in records]
     tsum = sum(r[2] for r in rows)
     print(f"P-frame wall {total:.2f} ms; sum of {len(rows)} bracketed launches {tsum:.2f} ms")
     fam = defaultdict(lambda: [0, 0.0])

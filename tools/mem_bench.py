@@ -63,7 +63,7 @@ def run(torch, dev, H=1152, W=1920, peak_gbs=6544.7):
     sets = [(rnd(H, W, C), rnd(H // 2, W // 2, 3 * G * O, 0.5), rnd(H, W, 2, 3.0), new(H, W, C)) for _ in range(2)]
     od_bytes = px * (C * 4 * 2 + 8) + (px // 4) * 96 * 4
     add("offset_diversity C=48 G=16 O=2 1152x1920 (i.i.d. offsets +-20 px, planar)",
-        _time(torch, lambda s: ops.offset_diversity(s[0], s[1], s[2], fw, fb, G, O, 40.0, s[3]), sets, n=6), od_bytes,
+        _time(torch, lambda s: ops.offset_diversity(s[0], s[1], s[2], fw, fb, G, O, 40.0, s[3], planar=True), sets, n=6), od_bytes,
         "worst case: every (pixel, group, offset) samples an unrelated position")
     add("offset_diversity (i.i.d. offsets, direct NHWC gather)",
         _time(torch, lambda s: ops.offset_diversity(s[0], s[1], s[2], fw, fb, G, O, 40.0, s[3], planar=False), sets, n=6), od_bytes)
@@ -73,7 +73,7 @@ def run(torch, dev, H=1152, W=1920, peak_gbs=6544.7):
         low = F.interpolate(torch.randn(1, 3 * G * O, H // 32, W // 32, device=dev), size=(H // 2, W // 2), mode="bicubic") * 0.1
         smooth.append((s[0], V(low[0].permute(1, 2, 0).contiguous().reshape(-1), H // 2, W // 2, 3 * G * O, 3 * G * O), s[2], s[3]))
     add("offset_diversity (smooth offsets, planar)",
-        _time(torch, lambda s: ops.offset_diversity(s[0], s[1], s[2], fw, fb, G, O, 40.0, s[3]), smooth, n=6), od_bytes,
+        _time(torch, lambda s: ops.offset_diversity(s[0], s[1], s[2], fw, fb, G, O, 40.0, s[3], planar=True), smooth, n=6), od_bytes,
         "replaces a (32,3,H,W) grid_sample + 566 MB of grids + the grouped 1x1 conv")
     add("offset_diversity (smooth offsets, direct NHWC gather)",
         _time(torch, lambda s: ops.offset_diversity(s[0], s[1], s[2], fw, fb, G, O, 40.0, s[3], planar=False), smooth, n=6), od_bytes)
