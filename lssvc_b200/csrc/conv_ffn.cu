@@ -6,17 +6,24 @@
 // Two chained GEMMs per 128-pixel tile in the split-fp16 arithmetic of conv_h2.cu (x = x_hi + x_lo, three
 // kind::f16 MMAs per product, hi*hi and cross terms in separate fp32 TMEM accumulators):
 //
-//   o tile (TMA, fp32, stays in smem for the residual) --splitters--> A_o in TMEM
-//   for each chunk j of 32 hidden channels:
-//       D_h[j&1]  = A_o . W1[j]                         (K = C,  N = 32, accumulators 64 TMEM columns)
-//       A_h[j&1]  = split(lrelu(D_h * 2^-s + b1))       (16 "hidden" warps: TMEM -> regs -> TMEM)
-//       D_y[tile&1] += A_h[j&1] . W2[j]                 (K = 32, N = C)
+//   o tile (TMA, fp32, stays in smem for the residual) --splitters--> A_o[tile & 1] in TMEM
+//   for each chunk j of 32 hidden channels (global chunk counter g over the CTA's tiles, buffer g % 4):
+//       D_h[g%4]  = A_o . W1[j]                         (K = C,  N = 32, accumulators 64 TMEM columns)
+//       A_h[g%4]  = split(lrelu(D_h * 2^-s + b1))       (16 "hidden" warps: TMEM -> regs -> TMEM, IN PLACE over D_h)
+//       D_y      += A_h[g%4] . W2[j]                    (K = 32, N = C)
 //   y = o + lrelu(D_y * 2^-s + b2) -> swizzled smem staging -> TMA store
+//
+// Pipeline (round 2): the chain GEMM-a -> hidden warps -> GEMM-b of one chunk has ~1.2 k cycles of latency (tcgen05.ld, the
+// activation, tcgen05.st, fences, two barrier round trips) against ~0.5 k cycles of tensor time; with the two chunks in
+// flight of the first version a 128-pixel tile took 10 k cycles for 4 k of MMA time.  Now FOUR chunks are in flight: A_h is
+// written in place over the D_h columns already read (so a buffer costs 64 TMEM columns instead of 96), D_y is single-buffered
+// (its epilogue hides behind the GEMM-a chunks of the next tile, which run 3 chunks ahead across tile boundaries) and A_o is
+// double-buffered.  TMEM: A_o[2] 2C | D_h/A_h[4] 256 | D_y 2C = 4C + 256 <= 512 columns.
 //
 // Both weight matrices (pre-split, pre-scaled, pre-swizzled fp16, 8*C*Hd bytes) are loaded ONCE per CTA and stay
 // resident in shared memory; per tile only o is read and y written: 2*C*4 bytes per pixel, the HBM minimum.
 // Warp roles (896 threads): 0 input TMA, 1 MMA issuer, 2 TMEM alloc + weight loader, 4..7 splitters, 8..23 hidden
-// epilogue (2 chunks in flight x 2 column halves x 4 lane quarters), 24..27 output epilogue.
+// epilogue (4 chunks in flight x 4 lane quarters), 24..27 output epilogue.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -30,6 +37,8 @@ constexpr int TILE_H = 8;
 constexpr int TILE_W = 16;
 constexpr int HC = 32;        // hidden channels per chunk
 constexpr int IN_BUFS = 2;
+constexpr int NB = 4;         // hidden chunks in flight (D_h / A_h buffers)
+constexpr int LEAD = NB - 1;  // GEMM-a runs this many chunks ahead of GEMM-b
 constexpr int NUM_THREADS = 896;
 constexpr int TMEM_COLS = 512;
 
@@ -86,8 +95,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
   } while (0)
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t in_full[IN_BUFS], in_empty[IN_BUFS];
-  __shared__ uint64_t ao_full, ao_empty, w_full;
-  __shared__ uint64_t dh_full[2], dh_empty[2], ah_full[2], ah_empty[2], dy_full[2], dy_empty[2];
+  __shared__ uint64_t ao_full[2], ao_empty[2], w_full;
+  __shared__ uint64_t dh_full[NB], ah_full[NB], ah_empty[NB], dy_full, dy_empty;
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -98,11 +107,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
   const uint32_t in_s = smem_base + static_cast<uint32_t>(p.in_off), stage_s = smem_base + static_cast<uint32_t>(p.stage_off);
   const uint32_t in_bytes = 128u * static_cast<uint32_t>(p.n_slabs * p.slab_w) * 4u;
   const uint32_t b_in_full = ptx::pin(ptx::smem_u32(in_full)), b_in_empty = ptx::pin(ptx::smem_u32(in_empty));
-  const uint32_t b_ao_full = ptx::pin(ptx::smem_u32(&ao_full)), b_ao_empty = ptx::pin(ptx::smem_u32(&ao_empty));
+  const uint32_t b_ao_full = ptx::pin(ptx::smem_u32(ao_full)), b_ao_empty = ptx::pin(ptx::smem_u32(ao_empty));
   const uint32_t b_w_full = ptx::pin(ptx::smem_u32(&w_full));
-  const uint32_t b_dh_full = ptx::pin(ptx::smem_u32(dh_full)), b_dh_empty = ptx::pin(ptx::smem_u32(dh_empty));
+  const uint32_t b_dh_full = ptx::pin(ptx::smem_u32(dh_full));
   const uint32_t b_ah_full = ptx::pin(ptx::smem_u32(ah_full)), b_ah_empty = ptx::pin(ptx::smem_u32(ah_empty));
-  const uint32_t b_dy_full = ptx::pin(ptx::smem_u32(dy_full)), b_dy_empty = ptx::pin(ptx::smem_u32(dy_empty));
+  const uint32_t b_dy_full = ptx::pin(ptx::smem_u32(&dy_full)), b_dy_empty = ptx::pin(ptx::smem_u32(&dy_empty));
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.in_map);
@@ -113,17 +122,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
       ptx::mbar_init(b_in_full + 8 * b, 1);
       ptx::mbar_init(b_in_empty + 8 * b, 8);  // 4 splitter + 4 output-epilogue warps read the tile
     }
-    ptx::mbar_init(b_ao_full, 4);
-    ptx::mbar_init(b_ao_empty, 1);
-    ptx::mbar_init(b_w_full, 1);
     for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(b_dh_full + 8 * b, 1);
-      ptx::mbar_init(b_dh_empty + 8 * b, 8);
-      ptx::mbar_init(b_ah_full + 8 * b, 8);
-      ptx::mbar_init(b_ah_empty + 8 * b, 1);
-      ptx::mbar_init(b_dy_full + 8 * b, 1);
-      ptx::mbar_init(b_dy_empty + 8 * b, 4);
+      ptx::mbar_init(b_ao_full + 8 * b, 4);
+      ptx::mbar_init(b_ao_empty + 8 * b, 1);
     }
+    ptx::mbar_init(b_w_full, 1);
+    for (int b = 0; b < NB; ++b) {
+      ptx::mbar_init(b_dh_full + 8 * b, 1);
+      ptx::mbar_init(b_ah_full + 8 * b, 4);   // the four lane-quarter warps of the buffer
+      ptx::mbar_init(b_ah_empty + 8 * b, 1);
+    }
+    ptx::mbar_init(b_dy_full, 1);
+    ptx::mbar_init(b_dy_empty, 4);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -134,13 +144,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
-  // TMEM columns: A_o [0, C) | D_h[2] 64 each | A_h[2] 32 each | D_y[2] 2C each
+  // TMEM columns: A_o[2] C each | D_h[NB] 64 each (A_h written in place: chunk half h -> hi at +16h, lo at +16h + 8) | D_y 2C
   const uint32_t t_ao = tmem_base;
-  const uint32_t t_dh = tmem_base + static_cast<uint32_t>(C);
-  const uint32_t t_ah = t_dh + 128u;
-  const uint32_t t_dy = t_ah + 64u;
+  const uint32_t t_dh = tmem_base + static_cast<uint32_t>(2 * C);
+  const uint32_t t_dy = t_dh + 64u * NB;
 
   const int total_tiles = p.tiles_x * p.tiles_y;
+  const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ------------------------------- input TMA producer -----------------------------------
@@ -188,55 +198,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
       const uint32_t w2_sub16 = (2u * static_cast<uint32_t>(C) * 32u) >> 4;  // one W2 sub-tile [2][C][16]
       const uint32_t w1_16 = (w1_s >> 4) | (1u << 16), w2_16 = (w2_s >> 4) | (1u << 16);
       const uint32_t half_c = static_cast<uint32_t>(C) >> 1;
-      uint32_t dh_mask = 0, ah_mask = 0;  // bit b: phase of buffer b's next use
-      uint32_t tphase = 0;
-      int tb = 0;
-      uint32_t dy_ph = 0;
       ptx::mbar_wait(b_w_full, 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        FFN_WAIT(0, b_ao_full, tphase);
-        FFN_WAIT(1, b_dy_empty + 8 * tb, dy_ph ^ 1u);
-        ptx::tc_fence_after();
-        uint32_t w1p = w1_16, w2p = w2_16;  // running weight descriptors of GEMM-a / GEMM-b
-        const uint32_t dy = t_dy + static_cast<uint32_t>(tb * 2 * C);
-        // GEMM-a of chunk ja runs one chunk ahead of GEMM-b of chunk j
-        for (int ja = 0; ja <= n_chunks; ++ja) {
-          if (ja < n_chunks) {
-            const uint32_t b = static_cast<uint32_t>(ja) & 1u;
-            FFN_WAIT(2, b_dh_empty + 8 * b, ((dh_mask >> b) & 1u) ^ 1u);
-            ptx::tc_fence_after();
-            const uint32_t d = t_dh + 64u * b;
-            for (int ks = 0; ks < KS1; ++ks) {
-              ptx::mma_f16_ts2(d, t_ao + ks * 8, w1p, B_HI, idesc_a1, ks != 0 ? 1u : 0u);
-              ptx::mma_f16_ts2(d + HC, t_ao + half_c + ks * 8, w1p, B_HI, idesc_a2, 1u);
-              w1p += w1_sub16;
-            }
-            ptx::mma_commit(b_dh_full + 8 * b);
-            dh_mask ^= 1u << b;
-          } else {
-            ptx::mma_commit(b_ao_empty);  // every GEMM-a of this tile has been issued
+      // software pipeline over the global chunk counter: step s issues GEMM-a of chunk s and GEMM-b of chunk s - LEAD
+      const int n_all = my_tiles * n_chunks;
+      int ta = 0, ja = 0, tb = 0, jb = 0;  // (tile, chunk) of the next GEMM-a / GEMM-b
+      for (int st = 0; st < n_all + LEAD; ++st) {
+        if (st < n_all) {
+          const uint32_t b = static_cast<uint32_t>(st) % NB, use = static_cast<uint32_t>(st) / NB;
+          if (ja == 0) FFN_WAIT(0, b_ao_full + 8 * (ta & 1), static_cast<uint32_t>(ta >> 1) & 1u);
+          FFN_WAIT(2, b_ah_empty + 8 * b, (use & 1u) ^ 1u);  // GEMM-b of the buffer's previous chunk has read A_h
+          ptx::tc_fence_after();
+          const uint32_t d = t_dh + 64u * b;
+          const uint32_t ao = t_ao + static_cast<uint32_t>((ta & 1) * C);
+          uint32_t w1p = w1_16 + static_cast<uint32_t>(ja * KS1) * w1_sub16;
+          for (int ks = 0; ks < KS1; ++ks) {
+            ptx::mma_f16_ts2(d, ao + ks * 8, w1p, B_HI, idesc_a1, ks != 0 ? 1u : 0u);
+            ptx::mma_f16_ts2(d + HC, ao + half_c + ks * 8, w1p, B_HI, idesc_a2, 1u);
+            w1p += w1_sub16;
           }
-          if (ja > 0) {
-            const int j = ja - 1;
-            const uint32_t b = static_cast<uint32_t>(j) & 1u;
-            FFN_WAIT(3, b_ah_full + 8 * b, (ah_mask >> b) & 1u);
-            ptx::tc_fence_after();
-            const uint32_t a = t_ah + 32u * b;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              ptx::mma_f16_ts2(dy, a + ks * 8, w2p, B_HI, idesc_b1, (j | ks) != 0 ? 1u : 0u);
-              ptx::mma_f16_ts2(dy + C, a + 16 + ks * 8, w2p, B_HI, idesc_b2, 1u);
-              w2p += w2_sub16;
-            }
-            ptx::mma_commit(b_ah_empty + 8 * b);
-            if (j == n_chunks - 1) ptx::mma_commit(b_dy_full + 8 * tb);
-            ah_mask ^= 1u << b;
+          ptx::mma_commit(b_dh_full + 8 * b);
+          if (++ja == n_chunks) {
+            ptx::mma_commit(b_ao_empty + 8 * (ta & 1));  // every GEMM-a of this tile has been issued
+            ja = 0;
+            ++ta;
           }
         }
-        tphase ^= 1u;
-        if (++tb == 2) {
-          tb = 0;
-          dy_ph ^= 1u;
+        if (st >= LEAD) {
+          const int g = st - LEAD;
+          const uint32_t b = static_cast<uint32_t>(g) % NB, use = static_cast<uint32_t>(g) / NB;
+          if (jb == 0) FFN_WAIT(1, b_dy_empty, (static_cast<uint32_t>(tb) & 1u) ^ 1u);  // the previous tile's epilogue has read D_y
+          FFN_WAIT(3, b_ah_full + 8 * b, use & 1u);
+          ptx::tc_fence_after();
+          const uint32_t a = t_dh + 64u * b;
+          uint32_t w2p = w2_16 + static_cast<uint32_t>(jb * 2) * w2_sub16;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            ptx::mma_f16_ts2(t_dy, a + ks * 16, w2p, B_HI, idesc_b1, (jb | ks) != 0 ? 1u : 0u);
+            ptx::mma_f16_ts2(t_dy + C, a + ks * 16 + 8, w2p, B_HI, idesc_b2, 1u);
+            w2p += w2_sub16;
+          }
+          ptx::mma_commit(b_ah_empty + 8 * b);
+          if (++jb == n_chunks) {
+            ptx::mma_commit(b_dy_full);
+            jb = 0;
+            ++tb;
+          }
         }
       }
     }
@@ -245,14 +251,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
     // ------------------------------- splitters: o tile -> A_o (TMEM) ----------------------
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const uint32_t lane_addr = t_ao + (static_cast<uint32_t>(q * 32) << 16);
-    int ib = 0;
-    uint32_t iph = 0, tphase = 0;
+    int ib = 0, ti = 0;
+    uint32_t iph = 0;
     float amax = 0.f;  // running max |operand| of this thread (range guard)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       FFN_WAIT(0, b_in_full + 8 * ib, iph);
       const uint32_t tile_s = in_s + static_cast<uint32_t>(ib) * in_bytes;
-      FFN_WAIT(1, b_ao_empty, tphase ^ 1u);  // the previous tile's GEMM-a MMAs have read A_o
+      const uint32_t lane_addr = t_ao + static_cast<uint32_t>((ti & 1) * C) + (static_cast<uint32_t>(q * 32) << 16);
+      FFN_WAIT(1, b_ao_empty + 8 * (ti & 1), (static_cast<uint32_t>(ti >> 1) & 1u) ^ 1u);  // GEMM-a of tile ti - 2 has read this A_o
       ptx::tc_fence_after();
       for (int ks = 0; ks < KS1; ++ks) {
         float4 v[4];
@@ -272,10 +278,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        ptx::mbar_arrive(b_ao_full);
+        ptx::mbar_arrive(b_ao_full + 8 * (ti & 1));
         ptx::mbar_arrive(b_in_empty + 8 * ib);
       }
-      tphase ^= 1u;
       if (++ib == IN_BUFS) {
         ib = 0;
         iph ^= 1u;
@@ -283,32 +288,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
     }
     if (amax >= lssvc::kSplitRangeLimit && p.range_flag) atomicOr(p.range_flag, 1u);
   } else if (warp >= 8 && warp < 24) {
-    // ------------------------------- hidden epilogue: D_h -> lrelu -> split -> A_h ---------
+    // ------------------------------- hidden epilogue: D_h -> lrelu -> split -> A_h (in place) ---------
+    // 16 warps = NB buffers x 4 TMEM lane quarters; a warp owns the 32 lanes x 64 columns of its buffer: D1 = columns
+    // [0, 32), D2 = [32, 64) of the chunk's 32 hidden channels.  Half h (channels 16h .. 16h+15) is read (D1[16h..], D2[32+16h..])
+    // and its split activations written back over the D1 columns just read: hi at 16h, lo at 16h + 8.
     const int hw = warp - 8;
     const int q = hw & 3;          // TMEM lane quarter (== warp % 4)
-    const int half = (hw >> 2) & 1;  // which 16 of the chunk's 32 hidden channels
-    const int b = hw >> 3;         // chunk parity = buffer
+    const int b = hw >> 2;         // buffer
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t src1 = t_dh + 64u * b + 16u * half + lane_off, src2 = src1 + HC;
-    const uint32_t dst_hi = t_ah + 32u * b + 8u * half + lane_off, dst_lo = dst_hi + 16u;
+    const uint32_t buf = t_dh + 64u * b + lane_off;
     const float scale1 = p.scale1, slope1 = p.slope1;
+    const int n_all = my_tiles * n_chunks;
     uint32_t use = 0;
     float amax = 0.f;  // running max |hidden activation| of this thread (range guard)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int j = b; j < n_chunks; j += 2) {
+    for (int g = b; g < n_all; g += NB, ++use) {
+      const int j = g % n_chunks;
+      FFN_WAIT(0, b_dh_full + 8 * b, use & 1u);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
         const float4 *bq = reinterpret_cast<const float4 *>(p.b1 + j * HC + 16 * half);
         float4 bv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) bv[i] = __ldg(bq + i);
-        FFN_WAIT(0, b_dh_full + 8 * b, use & 1u);
-        ptx::tc_fence_after();
         uint32_t r1[16], r2[16];
-        ptx::tmem_ld16(src1, r1);
-        ptx::tmem_ld16(src2, r2);
+        ptx::tmem_ld16(buf + 16u * half, r1);
+        ptx::tmem_ld16(buf + HC + 16u * half, r2);
         ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(b_dh_empty + 8 * b);
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -324,16 +330,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
           split_pair_f(h0, h1, hi[2 * i], lo[2 * i]);
           split_pair_f(h2, h3, hi[2 * i + 1], lo[2 * i + 1]);
         }
-        FFN_WAIT(1, b_ah_empty + 8 * b, (use & 1u) ^ 1u);  // GEMM-b of this buffer's previous chunk is done
-        ptx::tc_fence_after();
-        ptx::tmem_st8(dst_hi, hi);
-        ptx::tmem_st8(dst_lo, lo);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(b_ah_full + 8 * b);
-        ++use;
+        // columns [16h, 16h + 16) of D1 have just been read by this warp (its own lanes): safe to overwrite
+        ptx::tmem_st8(buf + 16u * half, hi);
+        ptx::tmem_st8(buf + 16u * half + 8u, lo);
       }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(b_ah_full + 8 * b);
     }
     if (amax >= lssvc::kSplitRangeLimit && p.range_flag) atomicOr(p.range_flag, 1u);
   } else if (warp >= 24) {
@@ -344,9 +348,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float scale2 = p.scale2, slope2 = p.slope2;
     const bool store_thread = warp == 24 && lane == 0;
-    int ib = 0, tb = 0;
-    uint32_t dy_ph = 0, iph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int ib = 0, ti = 0;
+    uint32_t iph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
       const int oy = ty * TILE_H + h, ox = tx * TILE_W + w;
       FFN_WAIT(0, b_in_full + 8 * ib, iph);  // acquire the TMA-written o tile for the residual reads below
@@ -355,9 +359,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
       // staging is free once the previous tile's TMA store has read it
       if (store_thread) ptx::bulk_wait_read_all();
       ptx::named_bar_sync(2, 128);
-      FFN_WAIT(1, b_dy_full + 8 * tb, dy_ph);
+      FFN_WAIT(1, b_dy_full, static_cast<uint32_t>(ti) & 1u);
       ptx::tc_fence_after();
-      const uint32_t src = t_dy + static_cast<uint32_t>(tb * 2 * C) + lane_off;
+      const uint32_t src = t_dy + lane_off;
       for (int n = 0; n < C; n += 16) {
         uint32_t r1[16], r2[16];
         ptx::tmem_ld16(src + n, r1);
@@ -391,7 +395,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        ptx::mbar_arrive(b_dy_empty + 8 * tb);
+        ptx::mbar_arrive(b_dy_empty);
         ptx::mbar_arrive(b_in_empty + 8 * ib);
       }
       ptx::fence_proxy_async_smem();
@@ -406,16 +410,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
         ib = 0;
         iph ^= 1u;
       }
-      if (++tb == 2) {
-        tb = 0;
-        dy_ph ^= 1u;
-      }
     }
     if (store_thread) ptx::bulk_wait_all();
   }
 
   if (DBG && p.prof && blockIdx.x == 0 && lane == 0) {
-    // rows: 0 input TMA, 1 MMA issuer, 2 splitter warp 4, 3 hidden warp 8 (buffer 0), 4 hidden warp 16 (buffer 1), 5 output warp 24
+    // rows: 0 input TMA, 1 MMA issuer, 2 splitter warp 4, 3 hidden warp 8 (buffer 0), 4 hidden warp 16 (buffer 2), 5 output warp 24
     const int row = warp == 0 ? 0 : warp == 1 ? 1 : warp == 4 ? 2 : warp == 8 ? 3 : warp == 16 ? 4 : warp == 24 ? 5 : -1;
     if (row >= 0) {
       for (int i = 0; i < 6; ++i) p.prof[row * 8 + i] = prof[i];
@@ -498,7 +498,7 @@ extern "C" int32_t lssvc_conv_ffn(const lssvc_ffn *f, void *stream) {
   p.stage_off = p.in_off + IN_BUFS * tile_bytes;
   const size_t smem = static_cast<size_t>(p.stage_off) + tile_bytes + 1024;
   LSSVC_REQUIRE(smem <= 226 * 1024, "conv_ffn: C=%d hidden=%d needs %zu bytes of shared memory", C, Hd, smem);
-  LSSVC_REQUIRE(192 + 5 * C <= TMEM_COLS, "conv_ffn: C=%d does not fit in tensor memory", C);
+  LSSVC_REQUIRE(64 * NB + 4 * C <= TMEM_COLS, "conv_ffn: C=%d does not fit in tensor memory", C);
 
   const cuuint32_t ones[3] = {1, 1, 1};
   auto make_map = [&](CUtensorMap *m, const lssvc_view &v) -> CUresult {
@@ -538,8 +538,8 @@ extern "C" int32_t lssvc_conv_ffn(const lssvc_ffn *f, void *stream) {
     LSSVC_CUDA(cudaStreamSynchronize(lssvc::as_stream(stream)));
     LSSVC_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(prof_dev);
-    static const char *names[6] = {"input_tma [wait in_empty]", "mma       [wait ao_full, dy_empty, dh_empty, ah_full]", "splitter  [wait in_full, ao_empty]",
-                                   "hidden b0 [wait dh_full, ah_empty]", "hidden b1 [wait dh_full, ah_empty]", "output    [wait in_full, dy_full]"};
+    static const char *names[6] = {"input_tma [wait in_empty]", "mma       [wait ao_full, dy_empty, ah_empty, ah_full]", "splitter  [wait in_full, ao_empty]",
+                                   "hidden b0 [wait dh_full]", "hidden b2 [wait dh_full]", "output    [wait in_full, dy_full]"};
     fprintf(stderr, "conv_ffn prof (CTA 0, cycles; C=%d hidden=%d tiles/cta~%d):\n", C, Hd, (total_tiles + grid - 1) / grid);
     for (int r = 0; r < 6; ++r)
       fprintf(stderr, "  %-58s total %8lld | %8lld %8lld %8lld %8lld\n", names[r], h[r * 8 + 7], h[r * 8], h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3]);

@@ -7,7 +7,8 @@
 #   mem        tools/mem_bench.py                       -> gpurun_out/<tag>_mem.log
 #   layers     tools/layer_times.py (per-layer table)   -> gpurun_out/<tag>_layers.log
 #   launches   ncu launch list of bench.py              -> gpurun_out/<tag>_launches.csv
-#   ncu        ncu --set full of tools/ncu_driver.py    -> gpurun_out/<tag>_kernels.ncu-rep
+#   ncu        ncu --set full of tools/ncu_driver.py    -> gpurun_out/<tag>_kernels_raw.csv (raw metrics page)
+#   ffn        tools/ffn_bench.py + pw_bench.py         -> gpurun_out/<tag>_ffn.log
 # TAG=<tag> (default r2) names the outputs.
 TAG=${TAG:-r2}
 for what in "$@"; do
@@ -19,14 +20,17 @@ for what in "$@"; do
              python -c "import json;d=json.load(open('gpurun_out/${TAG}_bench_l$k.json'));print($k,d['value'],d['e2e']['value'],d['hbm_gb'])"; done;;
     streams) timeout 300 python tools/stream_bench.py --p-frames 5 > gpurun_out/${TAG}_stream_genuine.log 2>&1; cat gpurun_out/${TAG}_stream_genuine.log
              timeout 300 python tools/stream_bench.py --p-frames 5 --single-pass > gpurun_out/${TAG}_stream_single.log 2>&1; cat gpurun_out/${TAG}_stream_single.log;;
+    ffn) (timeout 300 python tools/ffn_bench.py; timeout 300 python tools/pw_bench.py) > gpurun_out/${TAG}_ffn.log 2>&1; cat gpurun_out/${TAG}_ffn.log;;
     mem) timeout 300 python tools/mem_bench.py > gpurun_out/${TAG}_mem.log 2>&1; cat gpurun_out/${TAG}_mem.log;;
     layers) timeout 300 python tools/layer_times.py > gpurun_out/${TAG}_layers.log 2>&1; head -70 gpurun_out/${TAG}_layers.log;;
     launches) python bench.py --steps 6 --no-cpu-baseline > gpurun_out/${TAG}_plain.log 2>&1 &&
               ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv \
                   python bench.py --steps 6 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "launch list rc=$?";;
-    ncu) python tools/ncu_driver.py > gpurun_out/${TAG}_ncu_plain.log 2>&1 &&
-         ncu --set full --clock-control none --import-source on -k regex:'conv_ffn|conv_pw|conv_hs|dwconv|od_|offset_div|flow_warp|laplace|four_part|bilinear|nhwc' \
-             -c 400 -o gpurun_out/${TAG}_kernels python tools/ncu_driver.py > gpurun_out/${TAG}_ncu.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/${TAG}_ncu.log;;
+    ncu) # ~60 matched launches at ~5 s each under --set full; raw metrics as CSV (a .ncu-rep of this run exceeds the 64 MiB gpurun_out limit)
+         python tools/ncu_driver.py > gpurun_out/${TAG}_ncu_plain.log 2>&1 &&
+         ncu --set full --clock-control none -k regex:'conv_ffn|conv_pw|conv_hs|dwconv|od_|offset_div|flow_warp|laplace|four_part|bilinear|nhwc|pool2|softmax2|lrelu_copy' \
+             -c 80 --csv --page raw --log-file gpurun_out/${TAG}_kernels_raw.csv python tools/ncu_driver.py > gpurun_out/${TAG}_ncu.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/${TAG}_ncu.log
+         ls -la gpurun_out/${TAG}_kernels_raw.csv;;
     *) echo "unknown: $what";;
   esac
 done

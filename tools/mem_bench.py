@@ -11,8 +11,12 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+WARM, REPS = 3, None       # tools/ncu_driver.py sets (1, 1): one warm-up and one measured launch per kernel
+
+
 def _time(torch, fn, sets, n=12):
-    for i in range(3):
+    n = REPS or n
+    for i in range(WARM):
         fn(sets[i % len(sets)])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
