@@ -13,17 +13,20 @@
 //       D_y      += A_h[g%4] . W2[j]                    (K = 32, N = C)
 //   y = o + lrelu(D_y * 2^-s + b2) -> swizzled smem staging -> TMA store
 //
-// Pipeline (round 2): the chain GEMM-a -> hidden warps -> GEMM-b of one chunk has ~1.2 k cycles of latency (tcgen05.ld, the
-// activation, tcgen05.st, fences, two barrier round trips) against ~0.5 k cycles of tensor time; with the two chunks in
-// flight of the first version a 128-pixel tile took 10 k cycles for 4 k of MMA time.  Now FOUR chunks are in flight: A_h is
-// written in place over the D_h columns already read (so a buffer costs 64 TMEM columns instead of 96), D_y is single-buffered
-// (its epilogue hides behind the GEMM-a chunks of the next tile, which run 3 chunks ahead across tile boundaries) and A_o is
-// double-buffered.  TMEM: A_o[2] 2C | D_h/A_h[4] 256 | D_y 2C = 4C + 256 <= 512 columns.
+// Pipeline (round 2).  The first version ran ONE issuing thread through a fixed interleaving of GEMM-a and GEMM-b with two
+// chunks in flight: 10 k cycles per 128-pixel tile for 4 k of tensor time — the thread needed 6.2-6.7 k cycles just to issue
+// 96 MMAs, 24 barrier waits, commits and fences (LSSVC_FFN_DBG counters), waited 1.8 k for the single A_o buffer, and the
+// hidden warps idled 71-83 %.  Now: TWO issuing threads (warp 1: every GEMM-a, warp 3: every GEMM-b) that only meet at the
+// barriers, so the issue work is halved per thread and GEMM-a runs ahead as far as the buffers allow (across tile
+// boundaries); THREE hidden chunks in flight with A_h written in place over the D_h columns already read (a buffer costs 64
+// TMEM columns instead of 96); A_o double-buffered; D_y single-buffered with EIGHT output warps (two per TMEM lane quarter)
+// so that its epilogue — now between GEMM-b of consecutive tiles — is short.
+// TMEM: A_o[2] 2C | D_h/A_h[3] 192 | D_y 2C = 4C + 192 <= 512 columns.
 //
 // Both weight matrices (pre-split, pre-scaled, pre-swizzled fp16, 8*C*Hd bytes) are loaded ONCE per CTA and stay
 // resident in shared memory; per tile only o is read and y written: 2*C*4 bytes per pixel, the HBM minimum.
-// Warp roles (896 threads): 0 input TMA, 1 MMA issuer, 2 TMEM alloc + weight loader, 4..7 splitters, 8..23 hidden
-// epilogue (4 chunks in flight x 4 lane quarters), 24..27 output epilogue.
+// Warp roles (896 threads): 0 input TMA, 1 GEMM-a issuer, 2 TMEM alloc + weight loader, 3 GEMM-b issuer, 4..7 splitters,
+// 8..19 hidden epilogue (3 chunks in flight x 4 lane quarters), 20..27 output epilogue (4 lane quarters x 2 column sets).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -37,8 +40,8 @@ constexpr int TILE_H = 8;
 constexpr int TILE_W = 16;
 constexpr int HC = 32;        // hidden channels per chunk
 constexpr int IN_BUFS = 2;
-constexpr int NB = 4;         // hidden chunks in flight (D_h / A_h buffers)
-constexpr int LEAD = NB - 1;  // GEMM-a runs this many chunks ahead of GEMM-b
+constexpr int NB = 3;         // hidden chunks in flight (D_h / A_h buffers)
+constexpr int OUT_WARPS = 8;  // output epilogue: 4 lane quarters x 2 column interleaves
 constexpr int NUM_THREADS = 896;
 constexpr int TMEM_COLS = 512;
 
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
   if (warp == 1 && lane == 0) {
     for (int b = 0; b < IN_BUFS; ++b) {
       ptx::mbar_init(b_in_full + 8 * b, 1);
-      ptx::mbar_init(b_in_empty + 8 * b, 8);  // 4 splitter + 4 output-epilogue warps read the tile
+      ptx::mbar_init(b_in_empty + 8 * b, 4 + OUT_WARPS);  // splitter + output-epilogue warps read the tile
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(b_ao_full + 8 * b, 4);
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
       ptx::mbar_init(b_ah_empty + 8 * b, 1);
     }
     ptx::mbar_init(b_dy_full, 1);
-    ptx::mbar_init(b_dy_empty, 4);
+    ptx::mbar_init(b_dy_empty, OUT_WARPS);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -186,64 +189,69 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ------------------------------- MMA issuer -------------------------------------------
-    // One elected thread runs the whole loop: a serial instruction stream, so descriptors are (lo, hi) 32-bit words
-    // advanced by adds and buffer phases live in bit masks (see conv_hs.cu).
+    // ------------------------------- GEMM-a issuer: D_h[g % NB] = A_o . W1[j] ------------------
+    // One elected thread; descriptors are (lo, hi) 32-bit words advanced by adds (see conv_hs.cu).
     if (ptx::elect_one()) {
       const uint32_t idesc_a1 = ptx::make_idesc_f16_m128(2 * HC), idesc_a2 = ptx::make_idesc_f16_m128(HC);
-      const uint32_t idesc_b1 = ptx::make_idesc_f16_m128(static_cast<uint32_t>(2 * C));
-      const uint32_t idesc_b2 = ptx::make_idesc_f16_m128(static_cast<uint32_t>(C));
       constexpr uint32_t B_HI = (256u >> 4) | (1u << 14) | (6u << 29);  // SBO = 256 B, version 1, SWIZZLE_32B
-      const uint32_t w1_sub16 = (2u * HC * 32u) >> 4;                        // one W1 sub-tile [2][32][16] fp16, in 16-byte units
-      const uint32_t w2_sub16 = (2u * static_cast<uint32_t>(C) * 32u) >> 4;  // one W2 sub-tile [2][C][16]
-      const uint32_t w1_16 = (w1_s >> 4) | (1u << 16), w2_16 = (w2_s >> 4) | (1u << 16);
+      const uint32_t w1_sub16 = (2u * HC * 32u) >> 4;  // one W1 sub-tile [2][32][16] fp16, in 16-byte units
+      const uint32_t w1_16 = (w1_s >> 4) | (1u << 16);
       const uint32_t half_c = static_cast<uint32_t>(C) >> 1;
       ptx::mbar_wait(b_w_full, 0);
-      // software pipeline over the global chunk counter: step s issues GEMM-a of chunk s and GEMM-b of chunk s - LEAD
-      const int n_all = my_tiles * n_chunks;
-      int ta = 0, ja = 0, tb = 0, jb = 0;  // (tile, chunk) of the next GEMM-a / GEMM-b
-      for (int st = 0; st < n_all + LEAD; ++st) {
-        if (st < n_all) {
-          const uint32_t b = static_cast<uint32_t>(st) % NB, use = static_cast<uint32_t>(st) / NB;
-          if (ja == 0) FFN_WAIT(0, b_ao_full + 8 * (ta & 1), static_cast<uint32_t>(ta >> 1) & 1u);
-          FFN_WAIT(2, b_ah_empty + 8 * b, (use & 1u) ^ 1u);  // GEMM-b of the buffer's previous chunk has read A_h
+      uint32_t b = 0, ph = 1;  // buffer of the next chunk; parity to wait on ah_empty[b] (1 on a fresh barrier: free)
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        FFN_WAIT(0, b_ao_full + 8 * (ti & 1), static_cast<uint32_t>(ti >> 1) & 1u);
+        const uint32_t ao = t_ao + static_cast<uint32_t>((ti & 1) * C);
+        uint32_t w1p = w1_16;
+        for (int j = 0; j < n_chunks; ++j) {
+          FFN_WAIT(2, b_ah_empty + 8 * b, ph);  // GEMM-b of the buffer's previous chunk has read A_h
           ptx::tc_fence_after();
           const uint32_t d = t_dh + 64u * b;
-          const uint32_t ao = t_ao + static_cast<uint32_t>((ta & 1) * C);
-          uint32_t w1p = w1_16 + static_cast<uint32_t>(ja * KS1) * w1_sub16;
           for (int ks = 0; ks < KS1; ++ks) {
             ptx::mma_f16_ts2(d, ao + ks * 8, w1p, B_HI, idesc_a1, ks != 0 ? 1u : 0u);
             ptx::mma_f16_ts2(d + HC, ao + half_c + ks * 8, w1p, B_HI, idesc_a2, 1u);
             w1p += w1_sub16;
           }
           ptx::mma_commit(b_dh_full + 8 * b);
-          if (++ja == n_chunks) {
-            ptx::mma_commit(b_ao_empty + 8 * (ta & 1));  // every GEMM-a of this tile has been issued
-            ja = 0;
-            ++ta;
+          if (++b == NB) {
+            b = 0;
+            ph ^= 1u;
           }
         }
-        if (st >= LEAD) {
-          const int g = st - LEAD;
-          const uint32_t b = static_cast<uint32_t>(g) % NB, use = static_cast<uint32_t>(g) / NB;
-          if (jb == 0) FFN_WAIT(1, b_dy_empty, (static_cast<uint32_t>(tb) & 1u) ^ 1u);  // the previous tile's epilogue has read D_y
-          FFN_WAIT(3, b_ah_full + 8 * b, use & 1u);
+        ptx::mma_commit(b_ao_empty + 8 * (ti & 1));  // every GEMM-a of this tile has been issued
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ------------------------------- GEMM-b issuer: D_y += A_h[g % NB] . W2[j] -----------------
+    if (ptx::elect_one()) {
+      const uint32_t idesc_b1 = ptx::make_idesc_f16_m128(static_cast<uint32_t>(2 * C));
+      const uint32_t idesc_b2 = ptx::make_idesc_f16_m128(static_cast<uint32_t>(C));
+      constexpr uint32_t B_HI = (256u >> 4) | (1u << 14) | (6u << 29);
+      const uint32_t w2_sub16 = (2u * static_cast<uint32_t>(C) * 32u) >> 4;  // one W2 sub-tile [2][C][16]
+      const uint32_t w2_16 = (w2_s >> 4) | (1u << 16);
+      ptx::mbar_wait(b_w_full, 0);
+      uint32_t b = 0, ph = 0;  // buffer of the next chunk; parity to wait on ah_full[b]
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        FFN_WAIT(1, b_dy_empty, (static_cast<uint32_t>(ti) & 1u) ^ 1u);  // the previous tile's epilogue has read D_y
+        uint32_t w2p = w2_16;
+        for (int j = 0; j < n_chunks; ++j) {
+          FFN_WAIT(3, b_ah_full + 8 * b, ph);
           ptx::tc_fence_after();
           const uint32_t a = t_dh + 64u * b;
-          uint32_t w2p = w2_16 + static_cast<uint32_t>(jb * 2) * w2_sub16;
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
-            ptx::mma_f16_ts2(t_dy, a + ks * 16, w2p, B_HI, idesc_b1, (jb | ks) != 0 ? 1u : 0u);
+            ptx::mma_f16_ts2(t_dy, a + ks * 16, w2p, B_HI, idesc_b1, (j | ks) != 0 ? 1u : 0u);
             ptx::mma_f16_ts2(t_dy + C, a + ks * 16 + 8, w2p, B_HI, idesc_b2, 1u);
             w2p += w2_sub16;
           }
           ptx::mma_commit(b_ah_empty + 8 * b);
-          if (++jb == n_chunks) {
-            ptx::mma_commit(b_dy_full);
-            jb = 0;
-            ++tb;
+          if (++b == NB) {
+            b = 0;
+            ph ^= 1u;
           }
         }
+        ptx::mma_commit(b_dy_full);
       }
     }
     __syncwarp();
@@ -287,9 +295,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
       }
     }
     if (amax >= lssvc::kSplitRangeLimit && p.range_flag) atomicOr(p.range_flag, 1u);
-  } else if (warp >= 8 && warp < 24) {
+  } else if (warp >= 8 && warp < 8 + 4 * NB) {
     // ------------------------------- hidden epilogue: D_h -> lrelu -> split -> A_h (in place) ---------
-    // 16 warps = NB buffers x 4 TMEM lane quarters; a warp owns the 32 lanes x 64 columns of its buffer: D1 = columns
+    // 12 warps = NB buffers x 4 TMEM lane quarters; a warp owns the 32 lanes x 64 columns of its buffer: D1 = columns
     // [0, 32), D2 = [32, 64) of the chunk's 32 hidden channels.  Half h (channels 16h .. 16h+15) is read (D1[16h..], D2[32+16h..])
     // and its split activations written back over the D1 columns just read: hi at 16h, lo at 16h + 8.
     const int hw = warp - 8;
@@ -340,14 +348,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
       if (lane == 0) ptx::mbar_arrive(b_ah_full + 8 * b);
     }
     if (amax >= lssvc::kSplitRangeLimit && p.range_flag) atomicOr(p.range_flag, 1u);
-  } else if (warp >= 24) {
+  } else if (warp >= 8 + 4 * NB) {
     // ------------------------------- output epilogue ---------------------------------------
+    // 8 warps: lane quarter q = warp % 4 (the TMEM lanes a warp may read), column set cs = 0 / 1: 16-channel groups
+    // cs, cs + 2, ... of the tile
     const int q = warp & 3;
+    const int cs = (warp - (8 + 4 * NB)) >> 2;
     const int m = q * 32 + lane;
     const int h = m / TILE_W, w = m % TILE_W;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float scale2 = p.scale2, slope2 = p.slope2;
-    const bool store_thread = warp == 24 && lane == 0;
+    const bool store_thread = warp == 8 + 4 * NB && lane == 0;
     int ib = 0, ti = 0;
     uint32_t iph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
@@ -358,11 +369,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
       const uint32_t tile_s = in_s + static_cast<uint32_t>(ib) * in_bytes;
       // staging is free once the previous tile's TMA store has read it
       if (store_thread) ptx::bulk_wait_read_all();
-      ptx::named_bar_sync(2, 128);
+      ptx::named_bar_sync(2, 32 * OUT_WARPS);
       FFN_WAIT(1, b_dy_full, static_cast<uint32_t>(ti) & 1u);
       ptx::tc_fence_after();
       const uint32_t src = t_dy + lane_off;
-      for (int n = 0; n < C; n += 16) {
+      for (int n = 16 * cs; n < C; n += 32) {
         uint32_t r1[16], r2[16];
         ptx::tmem_ld16(src + n, r1);
         ptx::tmem_ld16(src + C + n, r2);
@@ -399,7 +410,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
         ptx::mbar_arrive(b_in_empty + 8 * ib);
       }
       ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(3, 128);
+      ptx::named_bar_sync(3, 32 * OUT_WARPS);
       if (store_thread) {
         for (int s = 0; s < p.n_slabs; ++s)
           ptx::tma_store_3d(&p.out_map, stage_s + static_cast<uint32_t>(s) * (128u * p.slab_w * 4u), s * p.slab_w,
@@ -415,8 +426,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
   }
 
   if (DBG && p.prof && blockIdx.x == 0 && lane == 0) {
-    // rows: 0 input TMA, 1 MMA issuer, 2 splitter warp 4, 3 hidden warp 8 (buffer 0), 4 hidden warp 16 (buffer 2), 5 output warp 24
-    const int row = warp == 0 ? 0 : warp == 1 ? 1 : warp == 4 ? 2 : warp == 8 ? 3 : warp == 16 ? 4 : warp == 24 ? 5 : -1;
+    // rows: 0 input TMA, 1 GEMM-a issuer, 2 splitter warp 4, 3 hidden warp 8 (buffer 0), 4 GEMM-b issuer, 5 first output warp
+    const int row = warp == 0 ? 0 : warp == 1 ? 1 : warp == 4 ? 2 : warp == 8 ? 3 : warp == 3 ? 4 : warp == 8 + 4 * NB ? 5 : -1;
     if (row >= 0) {
       for (int i = 0; i < 6; ++i) p.prof[row * 8 + i] = prof[i];
       p.prof[row * 8 + 7] = clock64() - t_begin;
@@ -499,6 +510,7 @@ extern "C" int32_t lssvc_conv_ffn(const lssvc_ffn *f, void *stream) {
   const size_t smem = static_cast<size_t>(p.stage_off) + tile_bytes + 1024;
   LSSVC_REQUIRE(smem <= 226 * 1024, "conv_ffn: C=%d hidden=%d needs %zu bytes of shared memory", C, Hd, smem);
   LSSVC_REQUIRE(64 * NB + 4 * C <= TMEM_COLS, "conv_ffn: C=%d does not fit in tensor memory", C);
+  static_assert(8 + 4 * NB + OUT_WARPS == NUM_THREADS / 32, "conv_ffn: warp roles");
 
   const cuuint32_t ones[3] = {1, 1, 1};
   auto make_map = [&](CUtensorMap *m, const lssvc_view &v) -> CUresult {
@@ -538,8 +550,8 @@ extern "C" int32_t lssvc_conv_ffn(const lssvc_ffn *f, void *stream) {
     LSSVC_CUDA(cudaStreamSynchronize(lssvc::as_stream(stream)));
     LSSVC_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(prof_dev);
-    static const char *names[6] = {"input_tma [wait in_empty]", "mma       [wait ao_full, dy_empty, ah_empty, ah_full]", "splitter  [wait in_full, ao_empty]",
-                                   "hidden b0 [wait dh_full]", "hidden b2 [wait dh_full]", "output    [wait in_full, dy_full]"};
+    static const char *names[6] = {"input_tma [wait in_empty]", "gemm-a    [wait ao_full, -, ah_empty, -]", "splitter  [wait in_full, ao_empty]",
+                                   "hidden b0 [wait dh_full]", "gemm-b    [-, wait dy_empty, -, ah_full]", "output    [wait in_full, dy_full]"};
     fprintf(stderr, "conv_ffn prof (CTA 0, cycles; C=%d hidden=%d tiles/cta~%d):\n", C, Hd, (total_tiles + grid - 1) / grid);
     for (int r = 0; r < 6; ++r)
       fprintf(stderr, "  %-58s total %8lld | %8lld %8lld %8lld %8lld\n", names[r], h[r * 8 + 7], h[r * 8], h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3]);
