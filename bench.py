@@ -289,7 +289,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", default="1080p", choices=sorted(SIZES))
     ap.add_argument("--gop", type=int, default=None, help="intra period; default 12 at N = 1 (config 2), 32 at N > 1 (config 3)")
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("LSSVC_LANES", "2")), help="concurrent GOPs per GPU")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("LSSVC_LANES", "1")),
+                    help="concurrent GOPs per GPU (SURVEY H9; measured: 16.8 / 16.4 / 16.4 frames/s at 1 / 2 / 3 lanes, so 1 is the default)")
     ap.add_argument("--frames", type=int, default=96)
     ap.add_argument("--seqs", type=int, default=None, help="sequences of the job; default: lanes at N = 1, 8 at N > 1")
     ap.add_argument("--full-job", action="store_true", help="code this rank's whole share (strong split of the job) instead of K rounds")
@@ -342,7 +343,7 @@ def main():
     devf = [(b.to(dev), e.to(dev)) for b, e in host]
     where = lambda seq, f: (f + gop_size * (seq + rank)) % pool_len
     coder = Coder(dev, shape_hr)
-    runner = GopRunner(coder.net_i, coder.net_p, lanes=lanes, graphs=not args.no_graphs)
+    runner = GopRunner(coder.net_i, coder.net_p, lanes=lanes, graphs=(lanes > 1 and not args.no_graphs))
 
     out_host = [(torch.empty(1, 3, H // 2, W // 2).pin_memory(), torch.empty(1, 3, H, W).pin_memory()) for _ in range(lanes)]
 
