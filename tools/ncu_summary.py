@@ -14,9 +14,12 @@ WANT = [
     ("sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active", "uniform %"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm %"),
     ("smsp__issue_active.avg.pct", "issue %"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_active", "l1tex %"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2 %"),
     ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %"),
+    ("smsp__inst_executed.sum", "Minstr"),
     ("launch__registers_per_thread", "regs"),
     ("launch__grid_size", "grid"),
     ("launch__block_size", "block"),
@@ -56,6 +59,8 @@ def main():
             if label == "MB":
                 scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1e-6)
                 f *= scale
+            if label == "Minstr":
+                f /= 1e6
             vals.append(f"{f:11.1f}" if label not in ("regs", "grid", "block") else f"{int(f):11d}")
         short = name.replace("(anonymous namespace)::", "").split("(")[0][:58]
         print(f"{short:58s} " + " ".join(vals))
