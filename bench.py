@@ -363,8 +363,10 @@ def main():
             out_host[lane][1].copy_(re, non_blocking=True)
 
     def measure(source, on_frame):
-        """cold start (weight packing, graph capture: two short GOPs per lane), W_ warm-up rounds, K timed rounds of this
-        rank's share; device time between two events on the current stream, lanes fenced on both sides, max over ranks."""
+        """cold start (weight packing, graph capture: two short GOPs per lane), W_ warm-up rounds (one more short GOP per
+        lane), then K timed rounds of this rank's share STARTING AT A GOP BOUNDARY, so that the timed frames carry the I / P
+        mix of the configuration; device time between two events on the current stream, lanes fenced on both sides, max
+        over ranks."""
         rows = []
         cold = gop.work_units(lanes, 8, 4)
         for _ in runner.rounds(cold, source, on_frame, rows):
@@ -379,9 +381,11 @@ def main():
             if on_frame is not None:
                 on_frame(lane, unit, f, r)
 
+        for _ in runner.rounds(gop.work_units(lanes, W_, W_), source, on_frame, rows):      # warm-up: W_ rounds
+            pass
+        runner.finish(rows)
+        del rows[:]
         it = runner.rounds(mine, source, tap, rows)
-        for _ in range(W_):
-            next(it, 0)
         runner.fence()
         if world > 1:
             dist.barrier()

@@ -2,7 +2,7 @@
 (SURVEY.md App. B).  For each shape: max error relative to the output scale against an fp64 torch conv (on a reduced
 height so the reference stays cheap) and CUDA-event time per launch at the full size, rotating over 3 input buffers.
 
-usage: python tools/conv_bench.py [engine ...]      (default: h2 tc3)
+usage: python tools/conv_bench.py [engine ...]      (default: h2 simt)
 """
 import math
 import os
