@@ -69,6 +69,10 @@ struct alignas(64) HsParams {
   // that the single-thread producers walk it with one LDS per stage instead of chains of parameter-space loads.
   uint4 stage_tab[MAX_ENTRIES];
   int n_entries, total_chunks;
+  // Work decomposition.  Normal: work item = one (channel tile, pixel tile) pair, `outer` = all of them, `inner` = 1.
+  // A-resident (a_res): work item = one PIXEL tile, whose converted halo tiles stay in shared memory while `inner` = n_tiles
+  // channel tiles are computed from them one after the other — the input is fetched and converted once instead of n_tiles times.
+  int a_res, outer, inner;
   int mt;                      // sub-tiles per tile (1 or 2)
   int n_acc;                   // accumulator slots in TMEM (2 or 4), each 2 * n_tile columns
   int Ho, Wo;
@@ -285,17 +289,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
   const uint32_t tmem_base = tmem_base_slot;
 
   const int tiles_per_n = p.tiles_x * p.tiles_y;
-  const int total_tiles = tiles_per_n * p.n_tiles;
+  const int outer = p.outer, inner = p.inner;
+  const bool a_res = p.a_res != 0;
   constexpr int mt = MT;
   constexpr int tile_w = SUB_W * MT;
+  // work item `item`, inner step `ni`  ->  channel tile nt, pixel tile rem
+#define HS_DECODE(item, ni, nt, rem)                 \
+  const int nt = a_res ? (ni) : (item) / tiles_per_n; \
+  const int rem = a_res ? (item) : (item) - nt * tiles_per_n
 
   if (warp == 0) {
     // ------------------------------- halo TMA producer -----------------------------------
     if (ptx::elect_one()) {
       int hb = 0;
       uint32_t hph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int rem = tile % tiles_per_n;
+      for (int item = blockIdx.x; item < outer; item += gridDim.x) {
+        const int rem = a_res ? item : item % tiles_per_n;      // (A-resident: the halos are loaded once per pixel tile)
         const int ty = rem / p.tiles_x;
         const int tx = rem - ty * p.tiles_x;
         const int oy0 = ty * TILE_H + p.q0y, ox0 = tx * tile_w + p.q0x;
@@ -330,8 +339,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
       const uint32_t tile_bytes = static_cast<uint32_t>(2 * p.n_tile) * B_ROWB;
       const int n_entries = p.n_entries;
       const uint32_t tab = ptx::smem_u32(stage_tab_s);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile / tiles_per_n) * p.n_tile;
+      for (int item = blockIdx.x; item < outer; item += gridDim.x)
+      for (int ni = 0; ni < inner; ++ni) {
+        const int n0 = (a_res ? ni : item / tiles_per_n) * p.n_tile;
         for (int j = 0; j < p.n_src; ++j) {
           for (int c = 0; c < p.chunks[j]; ++c) {
             const int k0 = p.coff[j] + c * KC;
@@ -390,7 +400,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
       const uint32_t tab = ptx::smem_u32(stage_tab_s);
       uint32_t e_x, e_y, e_z, e_w;
       ptx::lds_u4(tab, e_x, e_y, e_z, e_w);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int hb0 = 0;  // A-resident: first halo buffer of the current pixel tile
+      for (int item = blockIdx.x; item < outer; item += gridDim.x)
+      for (int ni = 0; ni < inner; ++ni) {
+        const bool first_pass = ni == 0, last_pass = ni == inner - 1;
+        if (first_pass) hb0 = hb;
+        int hb_r = hb0;  // halo buffer of the current walk when the halos are already resident (ni > 0)
 #pragma unroll
         for (int j = 0; j < MT; ++j) HS_WAIT(0, bar_tempty + 8 * (slot0 + j), acc_ph ^ 1u);
         ptx::tc_fence_after();
@@ -405,8 +420,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
               ptx::lds_u4(tab + 16u * static_cast<uint32_t>(en), e_x, e_y, e_z, e_w);
             }
             if (c_z & 0x100u) {  // first stage of a halo tile
-              HS_WAIT(1, bar_halo_conv + 8 * hb, hph);
-              a16_halo = a16_base + static_cast<uint32_t>(hb) * halo16;
+              if (first_pass) {
+                HS_WAIT(1, bar_halo_conv + 8 * hb, hph);
+                a16_halo = a16_base + static_cast<uint32_t>(hb) * halo16;
+              } else {  // converted by this pixel tile's first pass and still resident
+                a16_halo = a16_base + static_cast<uint32_t>(hb_r) * halo16;
+              }
             }
             const int items = static_cast<int>(c_z & 0xffu);
             uint32_t tap16[4] = {c_x & 0xffffu, c_x >> 16, c_y & 0xffffu, c_y >> 16};
@@ -453,11 +472,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
               s = 0;
               ph ^= 1u;
             }
-            if (c_z & 0x200u) {  // last stage of the halo tile: it is free once every MMA that reads it has completed
-              ptx::mma_commit(bar_halo_empty + 8 * hb);
-              if (++hb == halo_bufs) {
-                hb = 0;
-                hph ^= 1u;
+            if (c_z & 0x200u) {  // last stage of the halo tile
+              // it is free once every MMA that reads it has completed: after the LAST channel tile of the pixel tile
+              if (last_pass) ptx::mma_commit(bar_halo_empty + 8 * (first_pass ? hb : hb_r));
+              if (first_pass) {
+                if (++hb == halo_bufs) {
+                  hb = 0;
+                  hph ^= 1u;
+                }
+              } else if (++hb_r == halo_bufs) {
+                hb_r = 0;
               }
             }
           }
@@ -484,7 +508,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
     int hb = 0;
     uint32_t hph = 0;
     float amax = 0.f;  // running max |operand| of this thread (range guard)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < outer; item += gridDim.x) {      // (A-resident: once per pixel tile)
       for (int j = 0; j < p.n_src; ++j) {
         for (int c = 0; c < p.chunks[j]; ++c) {
           for (int g = 0; g < p.n_groups; ++g) {
@@ -560,9 +584,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
                       (res1 == nullptr || r1_tma) && (res2 == nullptr || r2_tma) &&
                       !(r2_tma && !r1_tma) && (!has_act || (slope >= 0.f && slope <= 1.f)) && (cout & 3) == 0;
     int u = 0;  // running unit counter (all units, both sets)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile / tiles_per_n;
-      const int rem = tile - nt * tiles_per_n;
+    for (int item = blockIdx.x; item < outer; item += gridDim.x)
+    for (int ni = 0; ni < inner; ++ni) {
+      HS_DECODE(item, ni, nt, rem);
       const int ty = rem / p.tiles_x;
       const int tx = rem - ty * p.tiles_x;
       for (int j = 0; j < mt; ++j, ++u) {
@@ -777,6 +801,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
     }
   }
 #undef HS_WAIT
+#undef HS_DECODE
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -1141,7 +1166,16 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
     }
   }
   const int total_tiles = p.tiles_x * p.tiles_y * p.n_tiles;
-  const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
+  // A-resident mode: several channel tiles, every halo of a pixel tile fits the ring at once, and there are enough pixel
+  // tiles to give every SM one.  (1x1 128 -> 512 at 288x480: the input was fetched and converted four times.)
+  {
+    static const bool ares_off = getenv("LSSVC_HS_NO_ARES") != nullptr;  // A/B switch
+    const int halos_per_tile = p.total_chunks * p.n_groups;
+    p.a_res = (!ares_off && p.n_tiles > 1 && halos_per_tile <= p.halo_bufs && p.tiles_x * p.tiles_y >= g_num_sms) ? 1 : 0;
+    p.outer = p.a_res ? p.tiles_x * p.tiles_y : total_tiles;
+    p.inner = p.a_res ? p.n_tiles : 1;
+  }
+  const int grid = p.outer < g_num_sms ? p.outer : g_num_sms;
   const size_t smem = static_cast<size_t>(p.stage_off) + (use_tma ? 2 * static_cast<size_t>(per_set) : 0) + 1024;
   const int ki = kc == 32 ? 0 : 1;
   cudaStream_t s = lssvc::as_stream(stream);

@@ -125,7 +125,14 @@ def test_conv_hs_large_persistent(cuda_device, mt, monkeypatch):
                          (("big_7x7", [32], [32], 64, 7, 1, 128, 256, False), False),
                          (("big_1x1", [64], [64], 256, 1, 1, 160, 264, False), True),
                          (("big_res", [64], [64], 64, 3, 1, 250, 330, False), "res"),
-                         (("big48_res", [48], [48], 48, 3, 1, 200, 312, False), "res")):
+                         (("big48_res", [48], [48], 48, 3, 1, 200, 312, False), "res"),
+                         # A-resident mode (several channel tiles computed from one converted halo set): needs >= 148 pixel tiles
+                         (("ares_1x1_128_512", [128], [128], 512, 1, 1, 144, 240, False), True),
+                         (("ares_1x1_128_512_res", [128], [128], 512, 1, 1, 150, 250, False), "res"),
+                         (("ares_3x3_128_256_ps", [128], [128], 256, 3, 1, 160, 272, True), False),
+                         (("ares_3x3_96_192", [96], [96], 192, 3, 1, 150, 260, False), True),
+                         (("ares_3x3_64_144_mt2", [64], [64], 144, 3, 1, 160, 272, False), "res"),
+                         (("ares_cat_64_64_256", [64, 64], [64, 64], 256, 3, 1, 152, 264, False), False)):
         err = _run_conv_case(case, "hs", cuda_device, extras)
         print(f"conv_hs {case[0]}: rel err {err:.3e}")
         assert err < 5e-6, (case[0], err)
