@@ -654,18 +654,20 @@ class LSSVC(Engine):
 
     def _res_encode(self, xe, c1, c2, c3):
         """ResEncoder (lssvc_modules.py:235-254): ResBlocks start with LeakyReLU(0.1) on the concatenation."""
-        f = self.conv("res_encoder.conv1", [xe, c1], stride=2)
-        f = self._cat_res_block("res_encoder.res1", f, c2)
-        f = self.conv("res_encoder.conv2", f, stride=2)
-        f = self._cat_res_block("res_encoder.res2", f, c3)
+        f = self._cat_res_block("res_encoder.res1", c2, "res_encoder.conv1", [xe, c1], stride=2)
+        f = self._cat_res_block("res_encoder.res2", c3, "res_encoder.conv2", f, stride=2)
         f = self.conv("res_encoder.conv3", f, stride=2)
         y = self.conv("res_encoder.conv4", f, stride=2)
         return y, self._prior_encoder("res_prior_encoder", y)
 
-    def _cat_res_block(self, name, f, ctx):
-        cat = View.alloc(f.H, f.W, f.real + ctx.real, self.device)
-        self.copy(f, cat.slice(0, f.real))
-        self.copy(ctx, cat.slice(f.real, cat.C))
+    def _cat_res_block(self, name, ctx, conv_name, conv_src, **conv_kw):
+        """ResBlock on cat(conv(conv_src), ctx): the convolution writes its output straight into its slice of the
+        concatenation buffer (the residual add of the block needs the concatenation as ONE view), the context is copied in."""
+        cout = self.tensor(conv_name + ".weight").shape[0] // (4 if conv_kw.get("ps") else 1)
+        assert cout % 4 == 0
+        cat = View.alloc(ctx.H, ctx.W, cout + ctx.real, self.device)
+        self.conv(conv_name, conv_src, out=cat.slice(0, cout), **conv_kw)
+        self.copy(ctx, cat.slice(cout, cat.C))
         return self.res_block(name, cat, slope=0.1, start_from_relu=True, end_with_relu=True)
 
     def _res_params(self, z_hat, c3, y_bl_hat):
@@ -713,10 +715,8 @@ class LSSVC(Engine):
     def _res_decode(self, y_hat, c1, c2, c3):
         """ResDecoder (lssvc_modules.py:257-276) + ReconGeneration (:279-292, called as (recon_image_feature, context1))."""
         f = self.conv("res_decoder.up1.0", y_hat, ps=True)
-        f = self.conv("res_decoder.up2.0", f, ps=True)
-        f = self._cat_res_block("res_decoder.res1", f, c3)
-        f = self.conv("res_decoder.up3.0", f, ps=True)
-        f = self._cat_res_block("res_decoder.res2", f, c2)
+        f = self._cat_res_block("res_decoder.res1", c3, "res_decoder.up2.0", f, ps=True)
+        f = self._cat_res_block("res_decoder.res2", c2, "res_decoder.up3.0", f, ps=True)
         rec = self.conv("res_decoder.up4.0", f, ps=True)
         f = self.conv("recon_generation_net.first_conv", [rec, c1])
         f = self._unet("recon_generation_net.unet_1", f)
