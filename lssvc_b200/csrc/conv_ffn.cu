@@ -3,7 +3,7 @@
 //     y = o + lrelu(W2 . lrelu(W1 . o + b1, s1) + b2, s2)  (+ res2)        W1: C -> Hd, W2: Hd -> C, both 1x1
 //
 // as ONE kernel: the Hd-channel intermediate (4x the width of o: 2.26 GB per tensor at 1080p) never leaves the SM.
-// Two chained GEMMs per 128-pixel tile in the split-fp16 arithmetic of conv_h2.cu (x = x_hi + x_lo, three
+// Two chained GEMMs per 128-pixel tile in the split-fp16 arithmetic of conv_hs.cu (x = x_hi + x_lo, three
 // kind::f16 MMAs per product, hi*hi and cross terms in separate fp32 TMEM accumulators):
 //
 //   o tile (TMA, fp32, stays in smem for the residual) --splitters--> A_o[tile & 1] in TMEM

@@ -2,9 +2,9 @@
 //
 //   D[M = 128 output pixels (16 rows x 8 columns), N = output channels] += A[M, K] * W[K, N],   K = (tap, input channel)
 //
-// Same arithmetic as conv_h2.cu (x = x_hi + x_lo in fp16; D1 += A_hi*W_hi, D2 += A_hi*W_lo + A_lo*W_hi in separate fp32
-// TMEM accumulators, [W_hi | W_lo] stacked so that A_hi feeds one MMA of width 2N).  What differs is how the A operand
-// reaches the tensor core:
+// Split-fp16 arithmetic (x = x_hi + x_lo in fp16; D1 += A_hi*W_hi, D2 += A_hi*W_lo + A_lo*W_hi in separate fp32
+// TMEM accumulators, [W_hi | W_lo] stacked so that A_hi feeds one MMA of width 2N).  How the A operand reaches the tensor
+// core:
 //
 //   * per (source, KC-channel chunk, stride-parity plane) ONE fp32 halo tile ((16 + kh - 1) x (8*MT + kw - 1) pixels, one
 //     pixel = one 4*KC-byte row) is fetched by a 5-D TMA box load with the 128-byte (KC = 32) / 64-byte (KC = 16) swizzle;
@@ -16,8 +16,11 @@
 //     K = 16 slices of A_hi / A_lo are byte offsets 0, 32 / 2*KC, 2*KC + 32 inside the pixel row.
 //
 // So a tap costs no data movement at all besides the MMA's own operand reads: no per-tap copies, no TMEM operand
-// staging, no splitter warps (conv_h2.cu spends most of its issue slots and shared-memory bandwidth there).
+// staging, no splitter warps (the earlier TMEM-operand kernel, tools/engines/conv_h2.cu, spent most of its issue slots and
+// shared-memory bandwidth there).
 // MT = 2 sub-tiles (16 x 16 pixels) share every weight stage, which halves the weight traffic L2 -> shared memory.
+// With several channel tiles and a halo ring that holds a whole pixel tile, the converted halos stay resident while every
+// channel tile is computed from them (A-resident mode, HsParams::a_res).
 //
 // Warp roles (640 threads): 0 halo TMA producer, 1 MMA issuer, 2 TMEM allocator + weight TMA producer, 4..11 halo
 // converters, 12..19 epilogue (two independent sets of 4 warps; a set owns whole 128-pixel accumulators: sub-tile j of

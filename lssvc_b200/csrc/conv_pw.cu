@@ -4,13 +4,13 @@
 //     y = act(W . u + b) * out_scale (+ res1) (+ res2),        u = x   or   u = dw3x3(x) + bd   (zero padding 1)
 //
 // These layers move 2*C*4 bytes per pixel for 2*Cin*Cout FLOPs per pixel: they are HBM-bound, and in the general
-// implicit-GEMM kernel (conv_h2.cu) they pay a per-tile weight reload and a deep pipeline built for 3x3 taps.
+// implicit-GEMM kernel (conv_hs.cu) they pay a per-tile weight reload and a deep pipeline built for 3x3 taps.
 // Here the split-fp16 weights (4*Cin*Cout bytes) are loaded once per CTA, the tile pipeline is
 //   TMA tile (fp32, +1-pixel apron when the depthwise conv is fused) -> 16 operand warps (dw3x3 in fp32 registers,
 //   split to fp16 hi/lo, tcgen05.st into a double-buffered A operand in TMEM) -> Cin/16 x 2 MMAs -> double-buffered
 //   accumulators -> 8 epilogue warps -> swizzled smem staging -> TMA store,
 // and fusing the depthwise conv removes its own kernel plus one write + read of the C-channel intermediate.
-// Same arithmetic as conv_h2.cu: x = x_hi + x_lo in fp16, D1 += A_hi*W_hi, D2 += A_hi*W_lo + A_lo*W_hi.
+// Same arithmetic as conv_hs.cu: x = x_hi + x_lo in fp16, D1 += A_hi*W_hi, D2 += A_hi*W_lo + A_lo*W_hi.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
