@@ -150,10 +150,14 @@ __device__ __forceinline__ void transform_row(float4 (&v)[NV], int in_transform,
 // what bounds the HBM-bound 1x1 layers (the epilogue warps are instruction-latency bound).
 // EPI = LSSVC_EPI_GDN / IGDN: v = x * rsqrt(v) / x * sqrt(v) with x (gdn_x) read from global memory, row pointer gx_row
 // (clamped to a valid pixel for the overhang of border tiles: those rows are clipped by the TMA store).
-template <bool R1, bool R2, int EPI>
+// R2: 0 no second residual, 1 staged in `stage2` by TMA, 2 read from global memory (row pointer r2_row, clamped like gx_row;
+// needs cout % 16 == 0) — the case of a 64-channel 16 x 16 tile, where a second staging buffer does not fit next to the halo
+// ring and the general path below cost twice the time of the layer (3x3 64->64 + two residuals: 0.24 ms against 0.13).
+template <bool R1, int R2, int EPI>
 __device__ __forceinline__ void epilogue_lean(uint32_t t_row, int n_tile, int n0, int cout, const float *__restrict__ bias,
                                               float acc_scale, float slope, float out_scale, uint32_t stage, uint32_t stage2,
-                                              uint32_t slab_w, int m, const float *__restrict__ gx_row) {
+                                              uint32_t slab_w, int m, const float *__restrict__ gx_row,
+                                              const float *__restrict__ r2_row = nullptr) {
   const uint32_t sswz = (slab_w == 32 ? static_cast<uint32_t>(m & 7) : static_cast<uint32_t>((m >> 1) & 3)) << 4;
   const uint32_t row_b = static_cast<uint32_t>(m) * (slab_w * 4u);
   for (int n = 0; n < n_tile; n += 16) {
@@ -177,7 +181,8 @@ __device__ __forceinline__ void epilogue_lean(uint32_t t_row, int n_tile, int n0
     for (int g = 0; g < 4; ++g) {
       const uint32_t soff = srow + ((spiece + 16u * g) ^ sswz);
       if (R1) a1[g] = ptx::lds_f4(stage + soff);
-      if (R2) a2[g] = ptx::lds_f4(stage2 + soff);
+      if (R2 == 1) a2[g] = ptx::lds_f4(stage2 + soff);
+      if (R2 == 2) a2[g] = __ldg(reinterpret_cast<const float4 *>(r2_row + cg) + g);
     }
     ptx::tmem_ld_wait();
 #pragma unroll
@@ -196,8 +201,10 @@ __device__ __forceinline__ void epilogue_lean(uint32_t t_row, int n_tile, int n0
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], v[e] * slope) * out_scale;
+      // (a residual read from global memory is added first: the order of the general path, bit for bit)
+      if (R2 == 2) { v[0] += a2[g].x; v[1] += a2[g].y; v[2] += a2[g].z; v[3] += a2[g].w; }
       if (R1) { v[0] += a1[g].x; v[1] += a1[g].y; v[2] += a1[g].z; v[3] += a1[g].w; }
-      if (R2) { v[0] += a2[g].x; v[1] += a2[g].y; v[2] += a2[g].z; v[3] += a2[g].w; }
+      if (R2 == 1) { v[0] += a2[g].x; v[1] += a2[g].y; v[2] += a2[g].z; v[3] += a2[g].w; }
       const uint32_t soff = srow + ((spiece + 16u * g) ^ sswz);
       ptx::sts_u4(stage + soff, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
     }
@@ -583,8 +590,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
     uint32_t res_ph = 0;
     // the common case runs the branch-free epilogue_lean: TMA store, plain epilogue, one output, residuals only via staging,
     // LeakyReLU slope within [0, 1] (max(v, slope v) form)
+    const bool r2_glob = res2 != nullptr && !r2_tma && epi == LSSVC_EPI_PLAIN && (cout & 15) == 0 && !ps;  // lean with res2 from global
     const bool lean = use_tma && (epi == LSSVC_EPI_PLAIN || ((cout & 15) == 0 && !r2_tma && (gdn_pitch & 3) == 0)) && out2 == nullptr &&
-                      (res1 == nullptr || r1_tma) && (res2 == nullptr || r2_tma) &&
+                      (res1 == nullptr || r1_tma) && (res2 == nullptr || r2_tma || r2_glob) &&
                       !(r2_tma && !r1_tma) && (!has_act || (slope >= 0.f && slope <= 1.f)) && (cout & 3) == 0;
     int u = 0;  // running unit counter (all units, both sets)
     for (int item = blockIdx.x; item < outer; item += gridDim.x)
@@ -637,15 +645,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
             const int cy = oy < p.Ho ? oy : p.Ho - 1, cx = ox < Wo ? ox : Wo - 1;
             const float *gx_row = gdn_x + (static_cast<long long>(cy) * Wo + cx) * gdn_pitch;
             if (epi == LSSVC_EPI_GDN) {
-              if (r1_tma) epilogue_lean<true, false, LSSVC_EPI_GDN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, gx_row);
-              else epilogue_lean<false, false, LSSVC_EPI_GDN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, gx_row);
+              if (r1_tma) epilogue_lean<true, 0, LSSVC_EPI_GDN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, gx_row);
+              else epilogue_lean<false, 0, LSSVC_EPI_GDN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, gx_row);
             } else {
-              if (r1_tma) epilogue_lean<true, false, LSSVC_EPI_IGDN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, gx_row);
-              else epilogue_lean<false, false, LSSVC_EPI_IGDN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, gx_row);
+              if (r1_tma) epilogue_lean<true, 0, LSSVC_EPI_IGDN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, gx_row);
+              else epilogue_lean<false, 0, LSSVC_EPI_IGDN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, gx_row);
             }
-          } else if (r1_tma && r2_tma) epilogue_lean<true, true, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr);
-          else if (r1_tma) epilogue_lean<true, false, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr);
-          else epilogue_lean<false, false, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr);
+          } else if (r2_glob) {
+            const int cy = oy < p.Ho ? oy : p.Ho - 1, cx = ox < Wo ? ox : Wo - 1;  // overhang rows are clipped by the TMA store
+            const float *r2_row = res2 + (static_cast<long long>(cy) * Wo + cx) * res2_pitch;
+            if (r1_tma) epilogue_lean<true, 2, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr, r2_row);
+            else epilogue_lean<false, 2, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr, r2_row);
+          } else if (r1_tma && r2_tma) epilogue_lean<true, 1, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr);
+          else if (r1_tma) epilogue_lean<true, 0, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr);
+          else epilogue_lean<false, 0, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr);
         }
         for (int n = 0; n < n_tile && !(dbgf & 8) && !lean; n += 16) {
           const int cg = n0 + n;
