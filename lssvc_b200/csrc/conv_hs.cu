@@ -1022,7 +1022,8 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
   }
 
   // ---- pipeline geometry --------------------------------------------------------------------------
-  const int tps = STAGE_K / kc;
+  // build_stages(tps): the per-chunk table of weight stages with at most `tps` taps per stage; returns false on overflow
+  auto build_stages = [&](int tps) -> bool {
   for (int g = 0; g < p.n_groups; ++g) {
     const int nt = p.g_tap0[g + 1] - p.g_tap0[g];
     const int n_st = (nt + tps - 1) / tps;
@@ -1035,7 +1036,7 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
       const int t1 = p.g_tap0[g + 1], step = p.g_step[g];
       for (int t = p.g_tap0[g]; t < t1; t += step) {
         const int items = t1 - t < step ? t1 - t : step;
-        LSSVC_REQUIRE(ne < MAX_ENTRIES && items <= 4, "conv_hs: stage table overflow");
+        if (ne >= MAX_ENTRIES || items > 4) return false;
         uint32_t t16[4] = {0, 0, 0, 0}, tw = 0;
         for (int i = 0; i < items; ++i) {
           t16[i] = p.tap16[t + i];
@@ -1050,6 +1051,15 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
     p.n_entries = ne;
     p.total_chunks = total_chunks;
   }
+  // a weight stage holds the taps of ONE pipeline step: a 1x1 conv (one tap per step) needs half / a quarter of the room of a
+  // 3x3 one, and the shared memory it gives back goes to the halo ring below — 1x1 layers are latency-bound on that ring
+  // (one 32-channel chunk feeds only two MMA pairs per TMA round trip)
+  int max_step = 1;
+  for (int g = 0; g < p.n_groups; ++g) max_step = p.g_step[g] > max_step ? p.g_step[g] : max_step;
+  p.b_bytes = max_step * (2 * n_tile * kc * 2);  // n_tile % 16 == 0 keeps every tile 1024-byte aligned
+  return true;
+  };
+  LSSVC_REQUIRE(build_stages(STAGE_K / kc), "conv_hs: stage table overflow");
   p.Ho = Ho; p.Wo = Wo;
   p.tiles_x = lssvc::ceil_div(Wo, SUB_W * mt);
   p.tiles_y = lssvc::ceil_div(Ho, TILE_H);
@@ -1058,12 +1068,6 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
   p.halo_tx = halo_w * halo_h * row_bytes;
   p.halo_rows = halo_w * halo_h;
   p.halo_bytes = (p.halo_tx + 1023) & ~1023;
-  // a weight stage holds the taps of ONE pipeline step: a 1x1 conv (one tap per step) needs half / a quarter of the room of a
-  // 3x3 one, and the shared memory it gives back goes to the halo ring below — 1x1 layers are latency-bound on that ring
-  // (one 32-channel chunk feeds only two MMA pairs per TMA round trip)
-  int max_step = 1;
-  for (int g = 0; g < p.n_groups; ++g) max_step = p.g_step[g] > max_step ? p.g_step[g] : max_step;
-  p.b_bytes = max_step * (2 * n_tile * kc * 2);  // n_tile % 16 == 0 keeps every tile 1024-byte aligned
   p.in_transform = c->in_transform;
   p.in_slope = c->in_slope;
   p.range_flag = lssvc::range_flag();
@@ -1120,6 +1124,13 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
   if (r2_tma && !fits(2, 3, true)) {  // no room for a second staging buffer: res2 is read from global in the epilogue
     r2_tma = false;
     per_set = stage_bytes * (p.out2 ? 2 : 1);
+  }
+  if (use_tma && !fits(2, 2, true) && STAGE_K / kc > 1) {
+    // a 128-channel tile of a 3x3 layer: 128 KB of staging + two halos + two 2-tap weight stages exceed the budget by a few
+    // KB.  One tap per stage (twice the stages, half the slot) keeps the TMA-store / lean epilogue, which is worth far more
+    // than the longer stage list (3x3 64->128 + residual at 576x960 ran the general epilogue: 228 TFLOP/s)
+    const bool ok = build_stages(1) && fits(2, 2, true);
+    if (!ok) build_stages(STAGE_K / kc);  // (7x7: 49 one-tap stages overflow the table) back to the default
   }
   if (use_tma && !fits(2, 2, true)) use_tma = false;
   LSSVC_REQUIRE(fits(2, 2, use_tma), "conv_hs: pipeline does not fit in shared memory (halo %d B, weight stage %d B, staging %d B)",
