@@ -270,7 +270,7 @@ def in_frame_roofline(torch, coder, frames_dev, peaks, gop):
                     "unit": "TFLOP/s", "frac_of_bf16_sustained": round(tf / sustained, 4),
                     "of_kernel_ceiling": round(tf / (sustained / 3.0), 4),
                     "share_of_frame": round(hs["ms"] / total_ms, 4)})
-    for k in ("ffn", "pw", "simt"):
+    for k in ("ffn", "pw", "head", "simt"):
         if k in fam and fam[k]["ms"] > 0:
             out[k] = {"launches": fam[k]["launches"], "ms": round(fam[k]["ms"], 2), "tflops": round(fam[k]["flops"] / fam[k]["ms"] / 1e9, 1)}
     other = {}

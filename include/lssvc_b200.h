@@ -163,6 +163,13 @@ int32_t lssvc_conv_ffn(const lssvc_ffn *f, void *stream);
 int32_t lssvc_conv_pw(const lssvc_pw *f, void *stream);
 /* fp32 CUDA-core implicit GEMM: any shape, also hosts the GDN epilogue and input transforms. */
 int32_t lssvc_conv_simt(const lssvc_conv *c, void *stream);
+/* Narrow heads on the fp32 CUDA cores (csrc/conv_head.cu): k = 3 (2 <= cout <= 4) or k = 7 (cout = 2), stride 1, pad k/2,
+ * one source with C % 8 == 0, plain epilogue (bias, LeakyReLU, out_scale, res1, res2) — SpyNet's 7x7 16->2 (video_net_component.py:
+ * 213-230), the 3x3 64->2 flow heads and the 3x3 48->3 / 64->3 reconstruction heads (lssvc_modules.py:279-292, 339-365),
+ * for which a 128 x 16 MMA tile is 12 % used.  Reads lssvc_conv::weight (fp32 [k*k][n_pad][cin]).
+ * lssvc_conv_head_supported: 1 when the descriptor is one this kernel takes, else 0 (no error is set). */
+int32_t lssvc_conv_head(const lssvc_conv *c, void *stream);
+int32_t lssvc_conv_head_supported(const lssvc_conv *c);
 /* depthwise 3x3, pad 1 (lssvc_modules.py:23-24): weight [9][C], bias [C] */
 int32_t lssvc_dwconv3x3(const lssvc_view *in, const float *weight, const float *bias,
                         const lssvc_view *out, void *stream);

@@ -77,6 +77,8 @@ _SIGNATURES = {
     "lssvc_conv_ffn": (c_int32, [POINTER(CFfn), c_void_p]),
     "lssvc_conv_pw": (c_int32, [POINTER(CPw), c_void_p]),
     "lssvc_conv_simt": (c_int32, [POINTER(CConv), c_void_p]),
+    "lssvc_conv_head": (c_int32, [POINTER(CConv), c_void_p]),
+    "lssvc_conv_head_supported": (c_int32, [POINTER(CConv)]),
     "lssvc_dwconv3x3": (c_int32, [_PV, c_void_p, c_void_p, _PV, c_void_p]),
     "lssvc_deconv3x3_s2": (c_int32, [_PV, c_void_p, c_void_p, c_int32, c_float, _PV, c_void_p]),
     "lssvc_nchw_to_nhwc": (c_int32, [c_void_p, c_int32, _PV, c_void_p]),

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "liblssvc_b200.so")
-SOURCES = ["conv_hs.cu", "conv_ffn.cu", "conv_pw.cu", "conv_simt.cu", "image_ops.cu", "frontend.cu", "entropy.cu", "range.cu", "rans.cpp", "lib.cpp"]
+SOURCES = ["conv_hs.cu", "conv_ffn.cu", "conv_pw.cu", "conv_simt.cu", "conv_head.cu", "image_ops.cu", "frontend.cu", "entropy.cu", "range.cu", "rans.cpp", "lib.cpp"]
 HEADERS = ["ptx.cuh", "common.cuh", os.path.join("..", "..", "include", "lssvc_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

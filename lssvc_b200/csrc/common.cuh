@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "../../include/lssvc_b200.h"
 
@@ -51,6 +52,29 @@ inline bool view_present(const lssvc_view *v) { return v && v->ptr != nullptr; }
     }                                                                             \
     lssvc::count_launch();                                                        \
   } while (0)
+
+// Launch with programmatic stream serialization (see ptx::pdl_wait): the kernel may start its prologue while its predecessor
+// in the stream drains.  Not used while the stream is being captured into a CUDA graph; LSSVC_NO_PDL=1 switches it off (A/B).
+template <typename P>
+inline cudaError_t launch_pdl(void (*kernel)(const P), int grid, int block, size_t smem, cudaStream_t s, const P &p) {
+  static const bool off = getenv("LSSVC_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(static_cast<unsigned>(block));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  bool capturing = true;
+  if (cudaStreamIsCapturing(s, &cap) == cudaSuccess) capturing = cap != cudaStreamCaptureStatusNone;
+  else cudaGetLastError();  // (the query itself failed: launch plainly and let the launch report what is wrong)
+  cfg.attrs = attr;
+  cfg.numAttrs = (off || capturing) ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

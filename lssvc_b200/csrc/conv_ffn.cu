@@ -84,6 +84,7 @@ __device__ __forceinline__ uint32_t tile_addr(uint32_t base, int slab_w, int m, 
 // DBG = true: instrumented variant (per-role wait-time counters), never on the product path
 template <bool DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_constant__ FfnParams p) {
+  ptx::pdl_launch_dependents();
   long long prof[6] = {0, 0, 0, 0, 0, 0};
   const long long t_begin = DBG ? clock64() : 0;
 #define FFN_WAIT(slot, bar, parity)       \
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_ffn_kernel(const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  ptx::pdl_wait();  // first global-memory access below (ptx.cuh: programmatic dependent launch)
   // TMEM columns: A_o[2] C each | D_h[NB] 64 each (A_h written in place: chunk half h -> hi at +16h, lo at +16h + 8) | D_y 2C
   const uint32_t t_ao = tmem_base;
   const uint32_t t_dh = tmem_base + static_cast<uint32_t>(2 * C);
@@ -557,7 +559,7 @@ extern "C" int32_t lssvc_conv_ffn(const lssvc_ffn *f, void *stream) {
       fprintf(stderr, "  %-58s total %8lld | %8lld %8lld %8lld %8lld\n", names[r], h[r * 8 + 7], h[r * 8], h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3]);
     return LSSVC_OK;
   }
-  conv_ffn_kernel<false><<<grid, NUM_THREADS, smem, lssvc::as_stream(stream)>>>(p);
+  LSSVC_CUDA(lssvc::launch_pdl(conv_ffn_kernel<false>, grid, NUM_THREADS, smem, lssvc::as_stream(stream), p));
   LSSVC_LAUNCHED();
   return LSSVC_OK;
 }

@@ -214,6 +214,7 @@ __device__ __forceinline__ void epilogue_lean(uint32_t t_row, int n_tile, int n0
 // DBG = true: the instrumented variant (LSSVC_HS_DBG switches + per-role wait-time counters), never on the product path
 template <int KC, int MT, bool DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_constant__ HsParams p) {
+  ptx::pdl_launch_dependents();  // the next kernel of the stream may take SMs as they fall idle (it waits in its own pdl_wait)
   const int dbgf = DBG ? p.dbg : 0;
   long long prof[6] = {0, 0, 0, 0, 0, 0};
   const long long t_begin = DBG ? clock64() : 0;
@@ -297,6 +298,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  // everything above touched only parameters, shared memory and TMEM; from here on global memory is read and written
+  ptx::pdl_wait();
 
   const int tiles_per_n = p.tiles_x * p.tiles_y;
   const int outer = p.outer, inner = p.inner;
@@ -1215,7 +1218,7 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
       LSSVC_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     g_attr_set[0] = true;
   }
-  fns[(dbg_on ? 4 : 0) + ki * 2 + (mt - 1)]<<<grid, NUM_THREADS, smem, s>>>(p);
+  LSSVC_CUDA(lssvc::launch_pdl(fns[(dbg_on ? 4 : 0) + ki * 2 + (mt - 1)], grid, NUM_THREADS, smem, s, p));
   LSSVC_LAUNCHED();
   if (prof_dev) {
     long long h[48];

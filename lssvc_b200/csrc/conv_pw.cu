@@ -65,6 +65,7 @@ __device__ __forceinline__ uint32_t slab_addr(uint32_t base, int slab_w, uint32_
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_constant__ PwParams p) {
+  ptx::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t in_full[MAX_IN_BUFS], in_empty[MAX_IN_BUFS];
   __shared__ uint64_t a_full[2], a_empty[2], d_full[2], d_empty[2], w_full, res_full;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_pw_kernel(const __grid_co
     ptx::tmem_alloc(ptx::smem_u32(&tmem_base_slot), TMEM_COLS);
     ptx::tmem_relinquish();
   }
+  ptx::pdl_wait();  // first global-memory access below (ptx.cuh: programmatic dependent launch)
   if (dw) {
     // depthwise weights [9][Cin] + bias [Cin] -> shared memory (read as broadcast float4 by the operand warps)
     float *dst = reinterpret_cast<float *>(smem_gen + p.dw_off);
@@ -476,7 +478,7 @@ extern "C" int32_t lssvc_conv_pw(const lssvc_pw *f, void *stream) {
   }
   const int total_tiles = p.tiles_x * p.tiles_y;
   const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
-  conv_pw_kernel<<<grid, NUM_THREADS, smem, lssvc::as_stream(stream)>>>(p);
+  LSSVC_CUDA(lssvc::launch_pdl(conv_pw_kernel, grid, NUM_THREADS, smem, lssvc::as_stream(stream), p));
   LSSVC_LAUNCHED();
   return LSSVC_OK;
 }

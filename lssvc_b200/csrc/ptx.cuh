@@ -142,6 +142,14 @@ __device__ __forceinline__ void tc_fence_after() {
 }
 
 // ---- TMA -----------------------------------------------------------------------------------
+// Programmatic dependent launch (launch attribute cudaLaunchAttributeProgrammaticStreamSerialization, common.cuh launch_pdl):
+// launch_dependents lets the NEXT kernel of the stream be scheduled onto SMs as they fall idle, while this grid is still
+// running; that kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) then overlaps our tail and its launch
+// latency disappears.  pdl_wait blocks until every prerequisite grid has completed and its memory is visible: nothing that
+// reads or writes global memory may precede it.  Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_tensormap(const void *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

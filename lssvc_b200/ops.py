@@ -264,6 +264,10 @@ ENGINES = {
                    "read from shared memory, taps = shifted descriptors on one converted halo tile, hi*hi and cross terms in "
                    "separate fp32 TMEM accumulators); FLOPs counted are algorithmic, so the kernel's own ceiling is peak/3"},
 }
+# Cout <= 4 heads leave the tensor-core engine for the register-blocked fp32 kernel (csrc/conv_head.cu) when the caller did not
+# name an engine; LSSVC_NO_HEAD=1 keeps them on conv_hs (A/B)
+HEAD_KERNEL = os.environ.get("LSSVC_NO_HEAD", "0") in ("", "0")
+HEAD_MIN_PIXELS = 400_000     # below ~1/2 of 1080p per side the launch is latency-bound on either kernel (tools/head_bench.py)
 _ENGINE = os.environ.get("LSSVC_CONV_ENGINE", "h2")
 assert _ENGINE in ENGINES, _ENGINE
 
@@ -331,10 +335,14 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
     d.res1, d.res2, d.out2, d.gdn_x = _cv(res1), _cv(res2), _cv(out2), _cv(gdn_x)
     d.slope2 = float(slope2)
     lib = _lib.load()
+    auto = engine is None
     engine = engine or _ENGINE
     if engine == "hs":
         engine = "h2"
-    assert engine in ENGINES, engine
+    assert engine in ENGINES or engine == "head", engine
+    if (engine == "h2" and auto and HEAD_KERNEL and pc.cout <= 4 and out.H * out.W >= HEAD_MIN_PIXELS
+            and lib.lssvc_conv_head_supported(byref(d))):
+        engine = "head"       # narrow heads (Cout 2..4): fp32 CUDA-core direct convolution, csrc/conv_head.cu
     if engine == "h2":
         ok = (all(s.C % 4 == 0 and s.pitch % 4 == 0 and (s.coff % 4 == 0) for s in srcs) and pc.kh * pc.kw <= 49
               and pc.stride in (1, 2) and srcs[0].H % pc.stride == 0 and srcs[0].W % pc.stride == 0)
@@ -351,6 +359,8 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
                       "flops": 2.0 * Ho * Wo * pc.kh * pc.kw * sum(s.real for s in srcs) * pc.cout})
     if engine == "simt":
         _lib.check(lib.lssvc_conv_simt(byref(d), _stream()), "conv_simt")
+    elif engine == "head":
+        _lib.check(lib.lssvc_conv_head(byref(d), _stream()), "conv_head")
     else:
         wh, cin16, acc_scale = pc.weight_h2()
         d.precision = _lib.PREC_H2

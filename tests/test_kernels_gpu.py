@@ -114,6 +114,60 @@ def test_conv_hs(case, extras, cuda_device):
     assert err < 5e-6, err
 
 
+HEAD_CASES = [
+    # (name, cin, cout, k, H, W, out view channels, act, out_scale, n residuals)
+    ("3x3_64_2", 64, 2, 3, 50, 70, 8, None, 1.0, 0),
+    ("3x3_64_2_scaled", 64, 2, 3, 33, 129, 8, None, 2.0, 0),
+    ("7x7_16_2_res", 16, 2, 7, 45, 100, 8, None, 1.0, 1),
+    ("7x7_16_2_tiny", 16, 2, 7, 9, 15, 8, None, 1.0, 1),
+    ("3x3_48_3", 48, 3, 3, 64, 64, 8, None, 1.0, 0),
+    ("3x3_64_3_act_res2", 64, 3, 3, 40, 66, 8, 0.1, 1.5, 2),
+    ("3x3_128_4", 128, 4, 3, 17, 65, 4, 0.0, 1.0, 1),
+]
+
+
+@pytest.mark.parametrize("case", HEAD_CASES, ids=[c[0] for c in HEAD_CASES])
+def test_conv_head(case, cuda_device, monkeypatch):
+    """Narrow heads (Cout 2..4) on the register-blocked fp32 CUDA-core kernel (csrc/conv_head.cu) against fp64; the default
+    engine routes such layers there by itself.  Tolerance: fp32 summation order only."""
+    ops = _ops()
+    name, cin, cout, k, H, W, cview, act, out_scale, nres = case
+    g = torch.Generator(device="cpu").manual_seed(hash(name) % 10000)
+    x = torch.randn(1, cin, H, W, generator=g).to(cuda_device)
+    w = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(cuda_device)
+    b = torch.randn(cout, generator=g).to(cuda_device)
+    pc = ops.PackedConv(w, b, stride=1, pad=k // 2, device=cuda_device)
+    src = make_view(x, ops)
+    buf = ops.View.alloc(H, W, cview, cuda_device, zero=True)
+    out = buf.slice(0, cout)
+    res = [torch.randn(1, cout, H, W, generator=g).to(cuda_device) for _ in range(nres)]
+    rv = [make_view(r, ops, C_view=cview).slice(0, cout) for r in res]
+    kw = {}
+    if nres >= 1:
+        kw["res1"] = rv[0]
+    if nres >= 2:
+        kw["res2"] = rv[1]
+    monkeypatch.setattr(ops, "HEAD_MIN_PIXELS", 0)                       # (the routing skips images this small)
+    prev, ops.TRACE = ops.TRACE, []
+    try:
+        ops.conv(pc, src, out, act=act, out_scale=out_scale, **kw)        # engine=None: the default engine's own routing
+        assert ops.TRACE[-1]["engine"] == "head", ops.TRACE[-1]
+    finally:
+        ops.TRACE = prev
+    torch.cuda.synchronize()
+    ref = ref_conv([x], w, b, 1, k // 2, act=act, res=res or None, out_scale=out_scale)
+    got = out.to_nchw()
+    err = rel_err(got, ref)
+    # and against the tensor-core kernel the layer ran on before (explicit engine: no routing)
+    out_hs = ops.View.alloc(H, W, cview, cuda_device, zero=True).slice(0, cout)
+    ops.conv(pc, src, out_hs, act=act, out_scale=out_scale, engine="hs", **kw)
+    err_hs = rel_err(out_hs.to_nchw(), ref)
+    print(f"conv_head {name}: rel err {err:.2e} (conv_hs {err_hs:.2e})")
+    assert err < 2e-6, err
+    if cview > cout:      # the pad channels of the buffer are not touched
+        assert float(buf.as_tensor()[..., cout:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("mt", ["1", "2"])
 def test_conv_hs_large_persistent(cuda_device, mt, monkeypatch):
     """More tiles than SMs: persistent loop, accumulator slots, barrier phase wrap; both sub-tile modes where allowed."""
