@@ -56,7 +56,7 @@ class ClockSampler:
 
     def __enter__(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -80,8 +80,19 @@ class ClockSampler:
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        def col(i):
+            out = []
+            for r in self.rows:
+                try:
+                    out.append(float(r[i]))
+                except (IndexError, ValueError):
+                    pass
+            return sorted(out)
+        draw, limit = col(6), col(7)
+        # power: the board runs this load AT its power limit (sw_power_cap): frames/s follows energy per frame, not idle gaps
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": round(draw[len(draw) // 2], 1) if draw else None,
+                "power_limit_w": round(limit[-1], 1) if limit else None}
 
 
 def frame_is_intra(idx, gop):

@@ -55,6 +55,14 @@ typedef struct {
 #define LSSVC_EPI_PLAIN 0
 #define LSSVC_EPI_GDN 1  /* out = gdn_x * rsqrt(acc + bias)   (gdn.py:29-44, video_net_component.py:83-105) */
 #define LSSVC_EPI_IGDN 2 /* out = gdn_x * sqrt(acc + bias)                                               */
+/* Entropy epilogues (lssvc_conv_hs; see lssvc_conv::ent_*): the convolution that PRODUCES the entropy parameters codes the
+ * latent in its own epilogue — no separate pass over the parameters, no extra launch. */
+#define LSSVC_EPI_LAPLACE 3 /* conv output = (scale | mean), 2C channels, written to `out` as usual; then
+                               q = rint(ent_y - mean), ent_y_hat = q + mean, bits += clamp(-log2(Laplace(0, scale) mass of
+                               [q - .5, q + .5] + 1e-5), 0, 50), symbol and CDF-row dumps: exactly lssvc_laplace_quant
+                               (LSSVC_net.py:154-167, 288-296; dmc_net.py:421-488) */
+#define LSSVC_EPI_BITPARM 4 /* conv output = z; out = rint(z), bits from the factorised BitEstimator prior (ent_coef),
+                               symbol dump: exactly lssvc_bitparm_quant (video_entropy_models.py Bitparm / BitEstimator) */
 
 /*
  * One convolution with its fused epilogue.  Replaces nn.Conv2d / nn.ConvTranspose2d(stride 1)
@@ -101,6 +109,25 @@ typedef struct {
   const void *weight_h2;
   int32_t cin_pad16;
   float acc_scale;
+  /* entropy epilogue (epi = LSSVC_EPI_LAPLACE / LSSVC_EPI_BITPARM, lssvc_conv_hs only; needs act = NONE, out_scale = 1, no
+   * residuals / PixelShuffle / out2, cout a multiple of 16; LAPLACE beyond one channel tile: see ent_tile):
+   *   ent_y      LAPLACE: the latent, C = cout / 2 channels, same H x W as the output
+   *   ent_y_hat  LAPLACE: the quantised latent (C channels)
+   *   ent_coef   BITPARM: [cout][11] coefficient table (lssvc_bitparm_quant)
+   *   ent_bits   device double the bits are added to (may be NULL)
+   *   ent_sym / ent_index  int32 NCHW dumps for the rANS coder (may be NULL); ent_thr / ent_n_thr: the scale thresholds
+   *                        of the CDF rows (needed with ent_index) */
+  lssvc_view ent_y, ent_y_hat;
+  const float *ent_coef;
+  double *ent_bits;
+  int32_t *ent_sym, *ent_index;
+  const float *ent_thr;
+  int32_t ent_n_thr;
+  /* LAPLACE over SEVERAL channel tiles (2C > 128, e.g. the 2 x 96 parameters of the base-layer y): the packed output channels
+   * are interleaved per tile so that a channel's scale and mean meet in one accumulator — tile t (ent_tile packed channels)
+   * holds [scale of channels t*ent_tile/2 .. | their means]; `out` still receives (scale | mean) in natural order.
+   * ent_tile = that tile width (a multiple of 32 dividing cout, = the kernel's own channel tile); 0 = natural order, one tile. */
+  int32_t ent_tile;
 } lssvc_conv;
 
 /*

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liblssvc_b200.so")
 MAX_SRC = 3
 ACT_NONE, ACT_LRELU = 0, 1
 IN_NONE, IN_SQUARE, IN_LRELU = 0, 1, 2
-EPI_PLAIN, EPI_GDN, EPI_IGDN = 0, 1, 2
+EPI_PLAIN, EPI_GDN, EPI_IGDN, EPI_LAPLACE, EPI_BITPARM = 0, 1, 2, 3, 4
 PREC_TF32, PREC_3XTF32, PREC_H2 = 0, 1, 2
 
 
@@ -49,6 +49,13 @@ class CConv(Structure):
         ("weight_h2", c_void_p),
         ("cin_pad16", c_int32),
         ("acc_scale", c_float),
+        ("ent_y", CView), ("ent_y_hat", CView),
+        ("ent_coef", c_void_p),
+        ("ent_bits", c_void_p),
+        ("ent_sym", c_void_p), ("ent_index", c_void_p),
+        ("ent_thr", c_void_p),
+        ("ent_n_thr", c_int32),
+        ("ent_tile", c_int32),
     ]
 
 

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "liblssvc_b200.so")
 SOURCES = ["conv_hs.cu", "conv_ffn.cu", "conv_pw.cu", "conv_simt.cu", "conv_head.cu", "image_ops.cu", "frontend.cu", "entropy.cu", "range.cu", "rans.cpp", "lib.cpp"]
-HEADERS = ["ptx.cuh", "common.cuh", os.path.join("..", "..", "include", "lssvc_b200.h")]
+HEADERS = ["ptx.cuh", "common.cuh", "entropy_math.cuh", os.path.join("..", "..", "include", "lssvc_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

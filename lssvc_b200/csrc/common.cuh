@@ -58,8 +58,7 @@ inline bool view_present(const lssvc_view *v) { return v && v->ptr != nullptr; }
 template <typename P>
 inline cudaError_t launch_pdl(void (*kernel)(const P), int grid, int block, size_t smem, cudaStream_t s, const P &p) {
   static const bool off = getenv("LSSVC_NO_PDL") != nullptr;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(static_cast<unsigned>(block));
   cfg.dynamicSmemBytes = smem;

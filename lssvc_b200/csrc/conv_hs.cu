@@ -31,6 +31,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "entropy_math.cuh"
 #include "ptx.cuh"
 
 namespace {
@@ -103,6 +104,16 @@ struct alignas(64) HsParams {
   int out2_pitch;
   float slope2;
   unsigned int *range_flag;  // raised when a split operand leaves the fp16 range (range.cu)
+  // entropy epilogue (LSSVC_EPI_LAPLACE / LSSVC_EPI_BITPARM): see epilogue_entropy
+  const float *ent_y;
+  int ent_y_pitch;
+  float *ent_y_hat;
+  int ent_h_pitch;
+  const float *ent_coef;
+  double *ent_bits;
+  int *ent_sym, *ent_index;
+  const float *ent_thr;
+  int ent_n_thr;
   long long *prof;  // DBG variant: [5 roles][8] cycle counters of CTA 0
   int dbg;  // LSSVC_HS_DBG: bottleneck-isolation switches (results are wrong when non-zero); see lssvc_conv_hs
 };
@@ -208,6 +219,89 @@ __device__ __forceinline__ void epilogue_lean(uint32_t t_row, int n_tile, int n0
       const uint32_t soff = srow + ((spiece + 16u * g) ^ sswz);
       ptx::sts_u4(stage + soff, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
     }
+  }
+}
+
+// Entropy epilogue: the convolution that produces the entropy parameters codes the latent while the parameters are still in
+// registers (one channel tile holds every output channel; direct global stores, no staging).  The arithmetic is the
+// stand-alone kernels' own (entropy_math.cuh), applied to the very values the plain epilogue would have stored, so symbols,
+// CDF rows, quantised latents and per-element bits are bit-identical to conv + lssvc_laplace_quant / lssvc_bitparm_quant;
+// only the order in which the per-element bits are summed (warp shuffles, one double atomicAdd per warp) differs.
+//   LAPLACE: accumulator columns [0, C) = scale, [C, 2C) = mean (C = cout / 2): both are written to `out`; q = rint(y - mean),
+//            y_hat = q + mean, bits, symbol / CDF-row dumps (NCHW int32).
+//   BITPARM: accumulator = z: out = rint(z), bits from the per-channel BitEstimator coefficients, symbol dump.
+template <int MODE>
+__device__ __forceinline__ void epilogue_entropy(const HsParams &p, uint32_t t_row, int n_tile, int n0, bool valid, long long pix) {
+  const int cout = p.cout;
+  const float acc_scale = p.acc_scale;
+  const long long HW = static_cast<long long>(p.Ho) * p.Wo;
+  double local = 0.0;
+  // (D1 + D2) * acc_scale + bias for accumulator columns col .. col + 15 of this channel tile (packed channels n0 + col ..)
+  auto load16 = [&](int col, float (&v)[16]) {
+    uint32_t r1[16], r2[16];
+    ptx::tmem_ld16(t_row + static_cast<uint32_t>(col), r1);
+    ptx::tmem_ld16(t_row + static_cast<uint32_t>(n_tile + col), r2);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = (__uint_as_float(r1[e]) + __uint_as_float(r2[e])) * acc_scale + __ldg(p.bias + n0 + col + e);
+  };
+  if (MODE == LSSVC_EPI_BITPARM) {
+    for (int n = 0; n < n_tile && n0 + n < cout; n += 16) {
+      float z[16];
+      load16(n, z);
+      if (valid) {
+        float *const o = p.out + pix * p.out_pitch + n0 + n;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float q[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = n0 + n + 4 * g + e;
+            q[e] = rintf(z[4 * g + e]);
+            local += static_cast<double>(lssvc_ent::bitparm_bits(q[e], p.ent_coef + c * 11));
+            if (p.ent_sym) p.ent_sym[static_cast<long long>(c) * HW + pix] = static_cast<int>(q[e]);
+          }
+          reinterpret_cast<float4 *>(o)[g] = make_float4(q[0], q[1], q[2], q[3]);
+        }
+      }
+    }
+  } else {
+    // this tile: [scale of latent channels c0 .. c0 + Ct | their means] (one tile: c0 = 0, Ct = C, the natural order)
+    const int C = cout >> 1, Ct = n_tile >> 1, c0 = n0 >> 1;
+    for (int n = 0; n < Ct; n += 16) {
+      float sc[16], mu[16];
+      load16(n, sc);
+      load16(Ct + n, mu);
+      if (valid) {
+        float *const o = p.out + pix * p.out_pitch + c0;
+        const float4 *const yq = reinterpret_cast<const float4 *>(p.ent_y + pix * p.ent_y_pitch + c0 + n);
+        float4 *const yh = reinterpret_cast<float4 *>(p.ent_y_hat + pix * p.ent_h_pitch + c0 + n);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          reinterpret_cast<float4 *>(o + n)[g] = make_float4(sc[4 * g], sc[4 * g + 1], sc[4 * g + 2], sc[4 * g + 3]);
+          reinterpret_cast<float4 *>(o + C + n)[g] = make_float4(mu[4 * g], mu[4 * g + 1], mu[4 * g + 2], mu[4 * g + 3]);
+          const float4 y4 = __ldg(yq + g);
+          const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+          float h[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c0 + n + 4 * g + e;
+            const float m = mu[4 * g + e], s = sc[4 * g + e];
+            const float q = rintf(yv[e] - m);
+            h[e] = q + m;
+            local += static_cast<double>(lssvc_ent::laplace_bits(q, s));
+            const long long nchw = static_cast<long long>(c) * HW + pix;
+            if (p.ent_sym) p.ent_sym[nchw] = static_cast<int>(q);
+            if (p.ent_index) p.ent_index[nchw] = lssvc_ent::scale_index(s, p.ent_thr, p.ent_n_thr);
+          }
+          yh[g] = make_float4(h[0], h[1], h[2], h[3]);
+        }
+      }
+    }
+  }
+  if (p.ent_bits) {
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local != 0.0) atomicAdd(p.ent_bits, local);
   }
 }
 
@@ -663,7 +757,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
           else if (r1_tma) epilogue_lean<true, 0, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr);
           else epilogue_lean<false, 0, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr);
         }
-        for (int n = 0; n < n_tile && !(dbgf & 8) && !lean; n += 16) {
+        const bool ent = epi == LSSVC_EPI_LAPLACE || epi == LSSVC_EPI_BITPARM;
+        if (ent && !(dbgf & 8)) {
+          if (epi == LSSVC_EPI_LAPLACE) epilogue_entropy<LSSVC_EPI_LAPLACE>(p, t_row, n_tile, n0, valid, pix);
+          else epilogue_entropy<LSSVC_EPI_BITPARM>(p, t_row, n_tile, n0, valid, pix);
+        }
+        for (int n = 0; n < n_tile && !(dbgf & 8) && !lean && !ent; n += 16) {
           const int cg = n0 + n;
           uint32_t r1[16], r2[16];
           ptx::tmem_ld16(t_row + static_cast<uint32_t>(n), r1);
@@ -1095,7 +1194,35 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
   LSSVC_REQUIRE(opt(c->out2, &o2, &p.out2_pitch), "conv_hs: out2 shape mismatch");
   p.out2 = const_cast<float *>(o2);
   p.slope2 = c->slope2;
-  if (c->epi != LSSVC_EPI_PLAIN) {
+  const bool ent_epi = c->epi == LSSVC_EPI_LAPLACE || c->epi == LSSVC_EPI_BITPARM;
+  if (ent_epi) {
+    LSSVC_REQUIRE(c->act == LSSVC_ACT_NONE && c->out_scale == 1.f && !c->pixel_shuffle && !p.res1 && !p.res2 && !p.out2,
+                  "conv_hs: an entropy epilogue takes no activation, scale, residuals, PixelShuffle or second output");
+    LSSVC_REQUIRE(c->cout % 16 == 0 && c->cout == c->n_pad && vec,
+                  "conv_hs: entropy epilogue needs cout %% 16 == 0 and 16-byte aligned views (cout=%d)", c->cout);
+    if (c->epi == LSSVC_EPI_LAPLACE) {
+      const int C = c->cout / 2;
+      // several channel tiles: the packed channels must have been interleaved for exactly this tile width (lssvc_conv::ent_tile)
+      LSSVC_REQUIRE(n_tile % 32 == 0 && (p.n_tiles == 1 ? (c->ent_tile == 0 || c->ent_tile == n_tile) : c->ent_tile == n_tile),
+                    "conv_hs: Laplace epilogue over %d channel tiles of %d needs weights interleaved for that tile (ent_tile=%d)",
+                    p.n_tiles, n_tile, c->ent_tile);
+      LSSVC_REQUIRE(C % 16 == 0 && lssvc::view_ok(&c->ent_y) && lssvc::view_ok(&c->ent_y_hat) && c->ent_y.H == Ho && c->ent_y.W == Wo &&
+                        c->ent_y.C == C && c->ent_y_hat.H == Ho && c->ent_y_hat.W == Wo && c->ent_y_hat.C == C,
+                    "conv_hs: Laplace epilogue needs ent_y / ent_y_hat views of %dx%dx%d", Ho, Wo, C);
+      LSSVC_REQUIRE(c->ent_y.pitch % 4 == 0 && c->ent_y_hat.pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(c->ent_y.ptr) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(c->ent_y_hat.ptr) & 15) == 0,
+                    "conv_hs: ent_y / ent_y_hat must be 16-byte aligned");
+      LSSVC_REQUIRE(!c->ent_index || (c->ent_thr && c->ent_n_thr > 0), "conv_hs: ent_index needs the scale thresholds");
+      p.ent_y = c->ent_y.ptr; p.ent_y_pitch = c->ent_y.pitch;
+      p.ent_y_hat = c->ent_y_hat.ptr; p.ent_h_pitch = c->ent_y_hat.pitch;
+      p.ent_index = c->ent_index; p.ent_thr = c->ent_thr; p.ent_n_thr = c->ent_n_thr;
+    } else {
+      LSSVC_REQUIRE(c->ent_coef != nullptr, "conv_hs: BitEstimator epilogue needs ent_coef");
+      p.ent_coef = c->ent_coef;
+    }
+    p.ent_bits = c->ent_bits;
+    p.ent_sym = c->ent_sym;
+  } else if (c->epi != LSSVC_EPI_PLAIN) {
     LSSVC_REQUIRE(!c->pixel_shuffle && lssvc::view_ok(&c->gdn_x) && c->gdn_x.H == Ho && c->gdn_x.W == Wo &&
                       c->gdn_x.C == c->cout,
                   "conv_hs: GDN epilogue needs a matching gdn_x view");
@@ -1111,7 +1238,7 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
   const int cq = c->cout / 4;
   int slab_w = 32;
   static const bool no_tma_env = getenv("LSSVC_H2_NOTMA") != nullptr;
-  bool use_tma = vec && !no_tma_env && (!c->pixel_shuffle || cq % 16 == 0);
+  bool use_tma = vec && !no_tma_env && (!c->pixel_shuffle || cq % 16 == 0) && !ent_epi;  // (entropy epilogues store directly)
   if (n_tile % 32 != 0 || (c->pixel_shuffle && cq % 32 != 0)) slab_w = 16;
   p.slab_w = slab_w;
   p.n_slabs = (n_tile + slab_w - 1) / slab_w;

@@ -3,11 +3,13 @@
 // Element-wise over NHWC fp32 views, one thread per element, bits reduced by warp shuffles and one
 // double atomicAdd per block.
 #include "common.cuh"
+#include "entropy_math.cuh"
 
 namespace {
 
+using namespace lssvc_ent;
+
 constexpr int TPB = 256;
-constexpr float LN2 = 0.693147180559945309f;
 
 inline int blocks_for(long long total) { return static_cast<int>((total + TPB - 1) / TPB); }
 
@@ -21,32 +23,6 @@ __device__ __forceinline__ void block_add(double local, double *out) {
     for (int i = 0; i < TPB / 32; ++i) s += warp_sums[i];
     if (s != 0.0) atomicAdd(out, s);
   }
-}
-
-// torch.distributions.Laplace(0, s).cdf(v) = 0.5 - 0.5 * sign(v) * expm1(-|v| / s)
-__device__ __forceinline__ float laplace_cdf(float v, float s) {
-  const float sg = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);
-  return 0.5f - 0.5f * sg * expm1f(-fabsf(v) / s);
-}
-// clamp(-log(p + 1e-5) / ln 2, 0, 50)
-__device__ __forceinline__ float prob_bits(float p) {
-  const float b = -1.0f * logf(p + 1e-5f) / LN2;
-  return fminf(fmaxf(b, 0.f), 50.f);
-}
-__device__ __forceinline__ float laplace_bits(float q, float scale) {
-  const float s = fminf(fmaxf(scale, 1e-5f), 1e10f);
-  return prob_bits(laplace_cdf(q + 0.5f, s) - laplace_cdf(q - 0.5f, s));
-}
-// number of thresholds <= s: the CDF-table row (build_indexes is a monotone step function of s)
-__device__ __forceinline__ int scale_index(float s, const float *__restrict__ thr, int n) {
-  s = fmaxf(s, 1e-5f);
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (thr[mid] <= s) lo = mid + 1;
-    else hi = mid;
-  }
-  return lo;
 }
 
 __global__ void laplace_quant_kernel(const float *__restrict__ y, int yp, const float *__restrict__ mean, int mp,
@@ -173,18 +149,6 @@ __global__ void gaussian_quant_kernel(const float *__restrict__ y, int yp, const
   if (bits) block_add(local, bits);
 }
 
-__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
-
-// BitEstimator: f1..f3: x = x * softplus(h) + b; x += tanh(x) * tanh(a); f4: sigmoid(x * softplus(h) + b)
-__device__ __forceinline__ float bitparm_cdf(float x, const float *__restrict__ k) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    x = x * k[i] + k[4 + i];
-    x = x + tanhf(x) * k[8 + i];
-  }
-  return sigmoidf(x * k[3] + k[7]);
-}
-
 __global__ void bitparm_quant_kernel(const float *__restrict__ z, int zp, const float *__restrict__ coef,
                                      float *__restrict__ zhat, int hp, double *__restrict__ bits, int *__restrict__ sym,
                                      int H, int W, int C) {
@@ -197,8 +161,7 @@ __global__ void bitparm_quant_kernel(const float *__restrict__ z, int zp, const 
     const float q = rintf(z[pix * zp + c]);
     if (zhat) zhat[pix * hp + c] = q;
     const float *k = coef + c * 11;
-    const float p = bitparm_cdf(q + 0.5f, k) - bitparm_cdf(q - 0.5f, k);
-    local = static_cast<double>(prob_bits(p));
+    local = static_cast<double>(bitparm_bits(q, k));
     if (sym) sym[static_cast<long long>(c) * H * W + pix] = static_cast<int>(q);
   }
   if (bits) block_add(local, bits);

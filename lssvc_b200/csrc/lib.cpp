@@ -24,7 +24,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace lssvc
 
 extern "C" {
-int32_t lssvc_abi_version(void) { return 3; }
+int32_t lssvc_abi_version(void) { return 4; }
 const char *lssvc_last_error(void) { return lssvc::g_error; }
 int64_t lssvc_launch_count(void) { return lssvc::g_launches.load(std::memory_order_relaxed); }
 void lssvc_launch_count_add(int64_t n) { lssvc::count_launch(static_cast<int>(n)); }

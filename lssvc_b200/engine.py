@@ -61,13 +61,13 @@ class Engine(nets.ParamBag):
             raise _lib.LssvcError("lssvc_b200 models run on a CUDA (sm_100a) device only; call .to('cuda') first — "
                                   "there is no CPU fallback")
 
-    def pack(self, name, srcs, stride, ps, transposed, pad, exact_in=False):
-        key = (name, tuple((v.real, v.C) for v in srcs), stride, ps, transposed, pad, exact_in)
+    def pack(self, name, srcs, stride, ps, transposed, pad, exact_in=False, pair_tile=0):
+        key = (name, tuple((v.real, v.C) for v in srcs), stride, ps, transposed, pad, exact_in, pair_tile)
         pc = self._packs.get(key)
         if pc is None:
             pc = ops.PackedConv(self.tensor(name + ".weight"), self.tensor(name + ".bias"), stride=stride, pad=pad,
                                 src_channels=[(v.real, v.C) for v in srcs], pixel_shuffle=ps, transposed=transposed,
-                                device=self.device, exact_in=exact_in)
+                                device=self.device, exact_in=exact_in, pair_tile=pair_tile)
             self._packs[key] = pc
         return pc
 
@@ -83,9 +83,10 @@ class Engine(nets.ParamBag):
         return View.alloc_padded(H, W, C, self.device)
 
     def conv(self, name, srcs, stride=1, act=None, ps=False, transposed=False, pad=None, res1=None, res2=None,
-             out=None, act_copy=None, act_copy_out=None, out_scale=1.0, engine=None, in_lrelu=None, exact_in=False):
+             out=None, act_copy=None, act_copy_out=None, out_scale=1.0, engine=None, in_lrelu=None, exact_in=False,
+             entropy=None):
         """conv (+PixelShuffle) with fused epilogue.  Returns the output view, or (out, lrelu(out, act_copy)).
-        exact_in: the source holds quantised symbols (ops.PackedConv)."""
+        exact_in: the source holds quantised symbols (ops.PackedConv).  entropy: entropy epilogue (ops.conv)."""
         if isinstance(srcs, View):
             srcs = [srcs]
         # un-materialised activations (ops.LazyAct): one common slope -> LeakyReLU in the conv's operand path, else write them out
@@ -95,7 +96,11 @@ class Engine(nets.ParamBag):
                 in_lrelu, srcs = lazy[0], [s.base for s in srcs]
             else:
                 srcs = [self.lrelu(s.base, s.slope) if isinstance(s, ops.LazyAct) else s for s in srcs]
-        pc = self.pack(name, srcs, stride, ps, transposed, pad, exact_in)
+        pair_tile = 0
+        if entropy is not None and entropy["mode"] == "laplace" and act is None and out_scale == 1.0 and not ps:
+            # 2C parameter channels beyond one channel tile: interleave (scale, mean) per tile at pack time (ops.PackedConv)
+            pair_tile = ops.laplace_pair_tile(2 * entropy["y"].C, engine)
+        pc = self.pack(name, srcs, stride, ps, transposed, pad, exact_in, pair_tile)
         Hi, Wi = srcs[0].H, srcs[0].W
         Ho = (Hi + 2 * pc.pad - pc.kh) // stride + 1
         Wo = (Wi + 2 * pc.pad - pc.kw) // stride + 1
@@ -110,6 +115,8 @@ class Engine(nets.ParamBag):
         ex = lambda v: None if v is None else v.exact()
         ops.TRACE_NAME = name
         kw = {} if in_lrelu is None else {"in_transform": _lib.IN_LRELU, "in_slope": float(in_lrelu)}
+        if entropy is not None:
+            kw["entropy"] = entropy
         ops.conv(pc, srcs, out.exact(), act=act, res1=ex(res1), res2=ex(res2), out2=ex(out2),
                  slope2=0.0 if act_copy is None else act_copy, out_scale=out_scale, engine=engine, **kw)
         if lazy_copy:

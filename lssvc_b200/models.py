@@ -448,10 +448,22 @@ class LSSVC(Engine):
     def _thr(self):
         return self.cached("thr_vid", lambda: entropy.video_scale_thresholds().to(self.device))
 
-    def _prior_encoder(self, name, y):
+    @staticmethod
+    def _laplace(y, y_hat, bits, w, key, thr):
+        """Laplace entropy epilogue (ops.conv `entropy`) for latent y coded against the (scale | mean) the convolution emits."""
+        return {"mode": "laplace", "y": y.exact(), "y_hat": y_hat.exact(), "bits": bits, "sym": w.buf(key, y) if w else None,
+                "index": w.buf(key + "_idx", y) if w else None, "thresholds": thr}
+
+    def _prior_encoder(self, name, y, coef, bits, w, key):
+        """Hyper-encoder + the factorised quantiser of z (BitEstimator prior): the last convolution rounds z, counts its bits and
+        dumps its symbols in its own epilogue (LSSVC_EPI_BITPARM; stand-alone lssvc_bitparm_quant when it cannot).  Returns z_hat."""
         t = self.conv(name + ".0", y, act=0.01)
         t = self.conv(name + ".2", t, stride=2, act=0.01)
-        return self.conv(name + ".4", t, stride=2)
+        wt = self.tensor(name + ".4.weight")
+        k = wt.shape[-1]
+        z_hat = self.new((t.H + 2 * (k // 2) - k) // 2 + 1, (t.W + 2 * (k // 2) - k) // 2 + 1, wt.shape[0])
+        ent = {"mode": "bitparm", "coef": coef, "bits": bits, "sym": w.buf(key, z_hat) if w else None}
+        return self.conv(name + ".4", t, stride=2, out=z_hat, entropy=ent)
 
     # ---- base layer: DMC.get_inter_layer_information (dmc_net.py:421-488) ------------------------------------------
     def _bl_motion(self, p, xb, ref):
@@ -462,14 +474,13 @@ class LSSVC(Engine):
             t = self.gdn(f"{p}mv_encoder.{base + 1}", t)
             # ResBlock(start_from_relu=False) then LeakyReLU(0.1): take the activated copy
             _, t = self.res_block(f"{p}mv_encoder.{base + 2}", t, start_from_relu=False, act_copy=0.1)
-        mv_y = self.conv(p + "mv_encoder.12", t, stride=2)
-        mv_z = self._prior_encoder(p + "mv_prior_encoder", mv_y)
-        return mv_y, mv_z
+        return self.conv(p + "mv_encoder.12", t, stride=2)
 
-    def _bl_mv_params(self, p, mv_z_hat):
+    def _bl_mv_params(self, p, mv_z_hat, entropy=None):
+        """entropy: Laplace epilogue of the convolution that emits (scale | mean) (encoder side; ops.conv)."""
         t = self.deconv_s2(p + "mv_prior_decoder.0", mv_z_hat, act=0.01, exact_in=True)
         t = self.deconv_s2(p + "mv_prior_decoder.2", t, act=0.01)
-        return self.conv(p + "mv_prior_decoder.4", t, transposed=True)
+        return self.conv(p + "mv_prior_decoder.4", t, transposed=True, entropy=entropy)
 
     def _bl_mv_decode(self, p, mv_y_hat):
         t = self.deconv_s2(p + "mv_decoder.0", mv_y_hat, act=0.1)
@@ -491,7 +502,7 @@ class LSSVC(Engine):
         c1, c2, c3 = self.warp(f1, mv_hat), self.warp(f2, mv2), self.warp(f3, mv3)
         return self.fusion3(p + "context_fusion_net", c1, c2, c3)
 
-    def _bl_res_params(self, p, z_hat, c1, c2, c3):
+    def _bl_res_params(self, p, z_hat, c1, c2, c3, entropy=None):
         t = self.deconv_s2(p + "res_prior_decoder.0", z_hat, act=0.01, exact_in=True)
         t = self.deconv_s2(p + "res_prior_decoder.2", t, act=0.01)
         hier = self.conv(p + "res_prior_decoder.4", t, transposed=True)
@@ -502,36 +513,28 @@ class LSSVC(Engine):
         temporal = self.conv(tp + ".conv4", t, stride=2)
         g = self.conv(p + "res_entropy_parameter.0", [temporal, hier], act=0.01)
         g = self.conv(p + "res_entropy_parameter.2", g, act=0.01)
-        return self.conv(p + "res_entropy_parameter.4", g)
+        return self.conv(p + "res_entropy_parameter.4", g, entropy=entropy)
 
     def _base_layer(self, xb, ref_frame, ref_feature, bits, w=None):
         p = "base_layer_model."
         thr = self._thr() if w else None
-        mv_y, mv_z = self._bl_motion(p, xb, ref_frame)
-        mv_z_hat = self.new(mv_z.H, mv_z.W, mv_z.real)
-        ops.bitparm_quant(mv_z, self._bitparm_coef(p + "bit_estimator_z_mv."), mv_z_hat, bits.ptr(0),
-                          sym=w.buf("bl_mv_z", mv_z) if w else None)
+        mv_y = self._bl_motion(p, xb, ref_frame)
+        mv_z_hat = self._prior_encoder(p + "mv_prior_encoder", mv_y, self._bitparm_coef(p + "bit_estimator_z_mv."), bits.ptr(0),
+                                       w, "bl_mv_z")
         _force(self, "bl_mv_z_hat", mv_z_hat)
-        mv_prm = self._bl_mv_params(p, mv_z_hat)
         C = mv_y.real
         mv_y_hat = self.new(mv_y.H, mv_y.W, C)
-        ops.laplace_quant(mv_y, mv_prm.slice(C, 2 * C), mv_prm.slice(0, C), None, mv_y_hat, bits.ptr(0),
-                          sym=w.buf("bl_mv_y", mv_y) if w else None, index=w.buf("bl_mv_y_idx", mv_y) if w else None,
-                          thresholds=thr)
+        mv_prm = self._bl_mv_params(p, mv_z_hat, entropy=self._laplace(mv_y, mv_y_hat, bits.ptr(0), w, "bl_mv_y", thr))
         _force(self, "bl_mv_y_q", mv_y_hat, mean=mv_prm.slice(C, 2 * C))
         mv_hat = self._bl_mv_decode(p, mv_y_hat)
         c1, c2, c3 = self._bl_contexts(p, ref_frame, ref_feature, mv_hat)
         y = self._res_encoder_gdn(p + "res_encoder", xb, c1, c2, c3, intra=False)
-        z = self._prior_encoder(p + "res_prior_encoder", y)
-        z_hat = self.new(z.H, z.W, z.real)
-        ops.bitparm_quant(z, self._bitparm_coef(p + "bit_estimator_z."), z_hat, bits.ptr(0),
-                          sym=w.buf("bl_z", z) if w else None)
+        z_hat = self._prior_encoder(p + "res_prior_encoder", y, self._bitparm_coef(p + "bit_estimator_z."), bits.ptr(0), w, "bl_z")
         _force(self, "bl_z_hat", z_hat)
-        prm = self._bl_res_params(p, z_hat, c1, c2, c3)
         C = y.real
         y_hat = self.new(y.H, y.W, C)
-        ops.laplace_quant(y, prm.slice(C, 2 * C), prm.slice(0, C), None, y_hat, bits.ptr(0),
-                          sym=w.buf("bl_y", y) if w else None, index=w.buf("bl_y_idx", y) if w else None, thresholds=thr)
+        # (2 x 96 parameter channels = two channel tiles of 96: scale / mean interleaved per tile at pack time, ops.PackedConv)
+        prm = self._bl_res_params(p, z_hat, c1, c2, c3, entropy=self._laplace(y, y_hat, bits.ptr(0), w, "bl_y", thr))
         _force(self, "bl_y_q", y_hat, mean=prm.slice(C, 2 * C))
         if w:
             w.layer_done("bl")      # every symbol of the BL string is on its way to the host while the synthesis runs
@@ -589,16 +592,15 @@ class LSSVC(Engine):
         _, t = self.res_block("mv_encoder.encoder2.2", t, start_from_relu=False, act_copy=0.1)
         t = self.gdn("mv_encoder.encoder2.5", self.conv("mv_encoder.encoder2.4", t, stride=2))
         _, t = self.res_block("mv_encoder.encoder2.6", t, start_from_relu=False, act_copy=0.1)
-        mv_y = self.conv("mv_encoder.encoder2.8", t, stride=2)
-        return mv_y, self._prior_encoder("mv_prior_encoder", mv_y)
+        return self.conv("mv_encoder.encoder2.8", t, stride=2)
 
-    def _mv_params(self, mv_z_hat, mv_ctx_prior):
+    def _mv_params(self, mv_z_hat, mv_ctx_prior, entropy=None):
         h = self.conv("mv_prior_decoder.0.0", mv_z_hat, ps=True, act=0.01, exact_in=True)
         h = self.conv("mv_prior_decoder.2.0", h, ps=True, act=0.01)
         h = self.conv("mv_prior_decoder.4", h)
         g = self.conv("mv_prior_fusion.0", [h, mv_ctx_prior], act=0.01)
         g = self.conv("mv_prior_fusion.2", g, act=0.01)
-        return self.conv("mv_prior_fusion.4", g)
+        return self.conv("mv_prior_fusion.4", g, entropy=entropy)
 
     def _mv_decode(self, mv_y_hat, mv_ctx):
         """MVResDecoder (lssvc_modules.py:472-494)."""
@@ -657,8 +659,7 @@ class LSSVC(Engine):
         f = self._cat_res_block("res_encoder.res1", c2, "res_encoder.conv1", [xe, c1], stride=2)
         f = self._cat_res_block("res_encoder.res2", c3, "res_encoder.conv2", f, stride=2)
         f = self.conv("res_encoder.conv3", f, stride=2)
-        y = self.conv("res_encoder.conv4", f, stride=2)
-        return y, self._prior_encoder("res_prior_encoder", y)
+        return self.conv("res_encoder.conv4", f, stride=2)
 
     def _cat_res_block(self, name, ctx, conv_name, conv_src, **conv_kw):
         """ResBlock on cat(conv(conv_src), ctx): the convolution writes its output straight into its slice of the
@@ -773,25 +774,19 @@ class LSSVC(Engine):
         # EL motion
         mv_ctx_prior, mv_ctx = self._mv_contexts(mv_hat_bl)
         mv = self.spynet("optic_flow", xe, re)
-        mv_y, mv_z = self._mv_encode(mv, mv_ctx)
-        mv_z_hat = self.new(mv_z.H, mv_z.W, mv_z.real)
-        ops.bitparm_quant(mv_z, self._bitparm_coef("bit_estimator_z_mv."), mv_z_hat, bits.ptr(1),
-                          sym=w.buf("el_mv_z", mv_z) if w else None)
+        mv_y = self._mv_encode(mv, mv_ctx)
+        mv_z_hat = self._prior_encoder("mv_prior_encoder", mv_y, self._bitparm_coef("bit_estimator_z_mv."), bits.ptr(1), w, "el_mv_z")
         _force(self, "mv_z_hat", mv_z_hat)
-        mv_prm = self._mv_params(mv_z_hat, mv_ctx_prior)
         C = mv_y.real
         mv_y_hat = self.new(mv_y.H, mv_y.W, C)
-        ops.laplace_quant(mv_y, mv_prm.slice(C, 2 * C), mv_prm.slice(0, C), None, mv_y_hat, bits.ptr(1),
-                          sym=w.buf("el_mv_y", mv_y) if w else None, index=w.buf("el_mv_y_idx", mv_y) if w else None,
-                          thresholds=self._thr() if w else None)
+        mv_prm = self._mv_params(mv_z_hat, mv_ctx_prior,
+                                 entropy=self._laplace(mv_y, mv_y_hat, bits.ptr(1), w, "el_mv_y", self._thr() if w else None))
         _force(self, "mv_y_q", mv_y_hat, mean=mv_prm.slice(C, 2 * C))
         mv_hat = self._mv_decode(mv_y_hat, mv_ctx)
         # contexts, residual coding
         c1, c2, c3, warp_frame = self._hybrid_contexts(texture_bl, mv_hat, re, fe)
-        y, z = self._res_encode(xe, c1, c2, c3)
-        z_hat = self.new(z.H, z.W, z.real)
-        ops.bitparm_quant(z, self._bitparm_coef("bit_estimator_z."), z_hat, bits.ptr(1),
-                          sym=w.buf("el_z", z) if w else None)
+        y = self._res_encode(xe, c1, c2, c3)
+        z_hat = self._prior_encoder("res_prior_encoder", y, self._bitparm_coef("bit_estimator_z."), bits.ptr(1), w, "el_z")
         _force(self, "z_hat", z_hat)
         params = self._res_params(z_hat, c3, y_hat_bl)
         y_hat = self._four_part(y, params, bits, w)

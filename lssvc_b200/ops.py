@@ -170,10 +170,10 @@ class PackedConv:
     """Weights of one Conv2d repacked for the kernels: [kh*kw][n_pad][cin_total] + bias[n_pad]."""
 
     __slots__ = ("weight", "bias", "kh", "kw", "stride", "pad", "cout", "n_pad", "cin_total", "src_c", "pixel_shuffle",
-                 "_h2", "exact_in", "coherent")
+                 "_h2", "exact_in", "coherent", "pair_tile")
 
     def __init__(self, w, b, stride=1, pad=None, src_channels=None, pixel_shuffle=False, transposed=False, device=None,
-                 exact_in=False, coherent=False):
+                 exact_in=False, coherent=False, pair_tile=0):
         """w: [Cout, Cin, kh, kw] (Conv2d) or, with transposed=True, a stride-1 ConvTranspose2d weight
         [Cin, Cout, kh, kw] (turned into the equivalent flipped Conv2d).  src_channels: list of
         (real, view) channel counts per source when sources are padded; default one unpadded source.
@@ -181,6 +181,9 @@ class PackedConv:
         truncation), so the accumulator-truncation compensation (acc_comp) must stay off for this layer."""
         self.exact_in = exact_in
         self.coherent = coherent      # sign-coherent products (GDN norm pool): acc_comp(..., coherent=True)
+        # pair_tile: the layer emits (scale | mean) for a Laplace entropy epilogue spanning several channel tiles of this width:
+        # packed tile t = [scale of channels t*pair_tile/2 .. | their means] (lssvc_conv::ent_tile); usable ONLY with that epilogue
+        self.pair_tile = pair_tile
         w = w.detach().to(torch.float32).cpu()
         if transposed:
             w = w.permute(1, 0, 2, 3).flip(2, 3)
@@ -189,6 +192,11 @@ class PackedConv:
         if src_channels is None:
             src_channels = [(cin, cin)]
         assert sum(r for r, _ in src_channels) == cin, (src_channels, cin)
+        if pair_tile:
+            assert not pixel_shuffle and pair_tile % 32 == 0 and cout % pair_tile == 0, (cout, pair_tile)
+            C, Ct = cout // 2, pair_tile // 2
+            perm = torch.tensor([(C if r >= Ct else 0) + t * Ct + (r % Ct) for t in range(cout // pair_tile) for r in range(pair_tile)])
+            w, b = w[perm], b[perm]
         if pixel_shuffle:
             assert cout % 4 == 0
             cq = cout // 4
@@ -267,6 +275,9 @@ ENGINES = {
 # Cout <= 4 heads leave the tensor-core engine for the register-blocked fp32 kernel (csrc/conv_head.cu) when the caller did not
 # name an engine; LSSVC_NO_HEAD=1 keeps them on conv_hs (A/B)
 HEAD_KERNEL = os.environ.get("LSSVC_NO_HEAD", "0") in ("", "0")
+# Entropy epilogues: the convolution that produces (scale | mean) / z quantises the latent, counts the bits and dumps the symbols
+# in its own epilogue (csrc/conv_hs.cu epilogue_entropy); LSSVC_NO_ENT_FUSE=1 runs the stand-alone entropy kernels instead (A/B)
+ENT_FUSE = os.environ.get("LSSVC_NO_ENT_FUSE", "0") in ("", "0")
 HEAD_MIN_PIXELS = 400_000     # below ~1/2 of 1080p per side the launch is latency-bound on either kernel (tools/head_bench.py)
 _ENGINE = os.environ.get("LSSVC_CONV_ENGINE", "h2")
 assert _ENGINE in ENGINES, _ENGINE
@@ -311,13 +322,70 @@ SIMT_DOWNGRADES = 0
 RANGE_FALLBACKS = 0
 
 
+def hs_channel_tile(n_pad):
+    """The channel tile lssvc_conv_hs picks for n_pad packed output channels (csrc/conv_hs.cu: equal tiles of at most 128)."""
+    n_tile = n_pad
+    if n_tile > 128:
+        n_tile = 128
+        while n_tile >= 16 and n_pad % n_tile:
+            n_tile -= 16
+    return n_tile
+
+
+def laplace_pair_tile(cout, engine=None):
+    """pair_tile to pack a (scale | mean) convolution with so that its Laplace epilogue can span several channel tiles; 0 when one
+    tile holds all 2C channels (natural order) or when the epilogue will not be fused anyway."""
+    if cout <= 128 or not ENT_FUSE or (engine or _ENGINE) not in ("h2", "hs") or cout % 16:
+        return 0
+    t = hs_channel_tile(cout)
+    return t if t % 32 == 0 else 0
+
+
+def _entropy_fusable(pc, out, act, res1, res2, out2, out_scale, epi, ent):
+    """Can lssvc_conv_hs take this entropy epilogue?  (16-byte aligned views, plain epilogue, scale / mean pairs inside a tile)"""
+    if not ENT_FUSE or act is not None or res1 is not None or res2 is not None or out2 is not None or out_scale != 1.0:
+        return False
+    if epi != _lib.EPI_PLAIN or pc.pixel_shuffle or pc.cout % 16 or pc.cout != pc.n_pad or not view_aligned(out):
+        return False
+    if ent["mode"] == "laplace":
+        tile = hs_channel_tile(pc.n_pad)
+        paired = pc.pair_tile == tile if pc.cout > 128 else pc.pair_tile in (0, tile)
+        return tile % 32 == 0 and paired and view_aligned(ent["y"]) and view_aligned(ent["y_hat"])
+    return ent["mode"] == "bitparm"
+
+
 def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, out_scale=1.0,
-         in_transform=_lib.IN_NONE, in_slope=0.0, epi=_lib.EPI_PLAIN, gdn_x=None, engine=None):
+         in_transform=_lib.IN_NONE, in_slope=0.0, epi=_lib.EPI_PLAIN, gdn_x=None, engine=None, entropy=None):
     """Run one packed convolution.  act: None or the LeakyReLU slope (0.0 = ReLU).
-    engine: None (the default engine), 'h2' / 'hs' or 'simt'."""
+    engine: None (the default engine), 'h2' / 'hs' or 'simt'.
+    entropy: the convolution produces entropy parameters and codes the latent in its epilogue (LSSVC_EPI_LAPLACE / _BITPARM):
+      {"mode": "laplace", "y": View (C ch), "y_hat": View, "bits": tensor | None, "sym": int32 tensor | None,
+       "index": int32 tensor | None, "thresholds": tensor | None}  — `out` receives (scale | mean) as usual;
+      {"mode": "bitparm", "coef": tensor [C][11], "bits": ..., "sym": ...}  — `out` receives rint(conv output).
+    When the tensor-core kernel cannot take it (other engine, several channel tiles, LSSVC_NO_ENT_FUSE=1) the convolution and the
+    stand-alone entropy kernel run one after the other: same results bit for bit."""
     if isinstance(srcs, View):
         srcs = [srcs]
     assert len(srcs) == len(pc.src_c), (len(srcs), pc.src_c)
+    if entropy is not None:
+        eng = engine or _ENGINE
+        fuse = eng in ("h2", "hs") and _entropy_fusable(pc, out, act, res1, res2, out2, out_scale, epi, entropy)
+        fuse = (fuse and all(s.C % 4 == 0 and s.pitch % 4 == 0 and s.coff % 4 == 0 for s in srcs) and pc.stride in (1, 2)
+                and pc.kh * pc.kw <= 49 and srcs[0].H % pc.stride == 0 and srcs[0].W % pc.stride == 0)   # conv_hs's own conditions
+        assert fuse or not pc.pair_tile, "weights interleaved for a Laplace epilogue (pair_tile) cannot run without it"
+        if not fuse:
+            kw = dict(act=act, res1=res1, res2=res2, out2=out2, slope2=slope2, out_scale=out_scale, in_transform=in_transform,
+                      in_slope=in_slope, epi=epi, gdn_x=gdn_x, engine=engine)
+            if entropy["mode"] == "laplace":
+                conv(pc, srcs, out, **kw)
+                C = pc.cout // 2
+                laplace_quant(entropy["y"], out.slice(C, 2 * C), out.slice(0, C), None, entropy["y_hat"], entropy.get("bits"),
+                              sym=entropy.get("sym"), index=entropy.get("index"), thresholds=entropy.get("thresholds"))
+            else:
+                z = View.alloc(out.H, out.W, out.C, out.device)
+                conv(pc, srcs, z, **kw)
+                bitparm_quant(z, entropy["coef"], out, entropy.get("bits"), sym=entropy.get("sym"))
+            return out
     d = CConv()
     d.n_src = len(srcs)
     for i, s in enumerate(srcs):
@@ -334,6 +402,18 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
     d.out = out.c()
     d.res1, d.res2, d.out2, d.gdn_x = _cv(res1), _cv(res2), _cv(out2), _cv(gdn_x)
     d.slope2 = float(slope2)
+    if entropy is not None:                          # (fusable: checked above)
+        g = lambda k: None if entropy.get(k) is None else entropy[k].data_ptr()
+        d.ent_bits, d.ent_sym = g("bits"), g("sym")
+        if entropy["mode"] == "laplace":
+            d.epi = _lib.EPI_LAPLACE
+            d.ent_y, d.ent_y_hat = entropy["y"].c(), entropy["y_hat"].c()
+            d.ent_index, d.ent_thr = g("index"), g("thresholds")
+            d.ent_n_thr = 0 if entropy.get("thresholds") is None else entropy["thresholds"].numel()
+            d.ent_tile = pc.pair_tile
+        else:
+            d.epi = _lib.EPI_BITPARM
+            d.ent_coef = entropy["coef"].data_ptr()
     lib = _lib.load()
     auto = engine is None
     engine = engine or _ENGINE
@@ -350,12 +430,14 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
             global SIMT_DOWNGRADES
             SIMT_DOWNGRADES += 1
             engine = "simt"
+    assert entropy is None or engine == "h2", engine
     if TRACE is not None:
         Ho, Wo = (out.H // 2, out.W // 2) if pc.pixel_shuffle else (out.H, out.W)
         TRACE.append({"name": TRACE_NAME, "engine": "hs" if engine == "h2" else engine, "k": pc.kh, "stride": pc.stride, "cin": pc.cin_total,
                       "src_c": list(pc.src_c), "cout": pc.cout, "Ho": Ho, "Wo": Wo, "ps": bool(pc.pixel_shuffle),
                       "extras": ("r" if res1 is not None else "") + ("s" if res2 is not None else "") + ("o" if out2 is not None else "")
-                                + ("l" if in_transform == _lib.IN_LRELU else "") + ("g" if epi != _lib.EPI_PLAIN else ""),
+                                + ("l" if in_transform == _lib.IN_LRELU else "") + ("g" if epi != _lib.EPI_PLAIN else "")
+                                + ("e" if entropy is not None else ""),
                       "flops": 2.0 * Ho * Wo * pc.kh * pc.kw * sum(s.real for s in srcs) * pc.cout})
     if engine == "simt":
         _lib.check(lib.lssvc_conv_simt(byref(d), _stream()), "conv_simt")

@@ -31,7 +31,7 @@ static unsigned lcg(unsigned &s) { return s = s * 1664525u + 1013904223u; }
 static float frand(unsigned &s) { return (lcg(s) >> 8) * (1.0f / 16777216.0f) * 2.f - 1.f; }
 
 static int host_checks() {
-  CHECK(lssvc_abi_version() == 3, "abi version %d", lssvc_abi_version());
+  CHECK(lssvc_abi_version() == 4, "abi version %d", lssvc_abi_version());
   // ---- pmf_to_quantized_cdf: sums to 2^16, strictly increasing (every symbol keeps a non-zero frequency)
   const int n = 40;
   std::vector<float> pmf(n);

@@ -28,7 +28,7 @@ def test_binding_covers_header():
 
 def test_library_reports_version_and_errors_without_gpu():
     lib = _lib.load()
-    assert lib.lssvc_abi_version() == 3
+    assert lib.lssvc_abi_version() == 4
     # argument validation happens before any CUDA call
     rc = lib.lssvc_conv_hs(None, None)
     assert rc == -1 and b"null descriptor" in lib.lssvc_last_error()

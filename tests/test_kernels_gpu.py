@@ -586,6 +586,73 @@ def test_gaussian_and_factorized(cuda_device):
     assert abs(bits.item() - ref_bits) / ref_bits < 1e-4
 
 
+@pytest.mark.parametrize("shape", [(20, 30), (37, 53), (160, 272)], ids=["small", "ragged", "persistent"])
+def test_entropy_epilogues(cuda_device, monkeypatch, shape):
+    """LSSVC_EPI_LAPLACE / LSSVC_EPI_BITPARM: the convolution that produces (scale | mean) / z codes the latent in its own
+    epilogue.  Against the same convolution followed by the stand-alone entropy kernel: parameters, quantised latent, symbols
+    and CDF rows bit for bit; bits to 1e-12 relative (only the order of the double sum differs)."""
+    ops = _ops()
+    from lssvc_b200 import entropy
+    dev = cuda_device
+    H, W = shape
+    g = torch.Generator().manual_seed(H * 131 + W)
+    thr = entropy.video_scale_thresholds().to(dev)
+
+    def run_laplace(fuse, C):
+        monkeypatch.setattr(ops, "ENT_FUSE", fuse)
+        x = torch.randn(1, 64, H, W, generator=torch.Generator().manual_seed(1))
+        w = torch.randn(2 * C, 64, 3, 3, generator=torch.Generator().manual_seed(2)) / math.sqrt(64 * 9)
+        b = torch.randn(2 * C, generator=torch.Generator().manual_seed(3)) * 0.5
+        y = torch.randn(1, C, H, W, generator=torch.Generator().manual_seed(4)) * 4
+        # 2C = 192 spans two channel tiles of 96: (scale, mean) interleaved per tile at pack time (the engine layer does this)
+        pc = ops.PackedConv(w, b, pad=1, device=dev, pair_tile=ops.laplace_pair_tile(2 * C) if fuse else 0)
+        assert pc.pair_tile == (96 if fuse and C == 96 else 0)
+        prm = ops.View.alloc(H, W, 2 * C, dev, zero=True)
+        y_hat = ops.View.alloc(H, W, C, dev, zero=True)
+        bits = torch.zeros(1, dtype=torch.float64, device=dev)
+        sym = torch.zeros(C * H * W, dtype=torch.int32, device=dev)
+        idx = torch.zeros(C * H * W, dtype=torch.int32, device=dev)
+        prev, ops.TRACE = ops.TRACE, []
+        try:
+            ops.conv(pc, make_view(x.to(dev), ops), prm, entropy={"mode": "laplace", "y": make_view(y.to(dev), ops), "y_hat": y_hat,
+                                                                   "bits": bits, "sym": sym, "index": idx, "thresholds": thr})
+            assert ("e" in ops.TRACE[-1]["extras"]) == fuse, ops.TRACE[-1]
+        finally:
+            ops.TRACE = prev
+        torch.cuda.synchronize()
+        return prm.to_nchw(), y_hat.to_nchw(), sym, idx, bits.item(), y
+
+    for C in (64, 96):
+        a, b_ = run_laplace(True, C), run_laplace(False, C)
+        for i in range(4):
+            assert torch.equal(a[i], b_[i]), (C, i)
+        assert abs(a[4] - b_[4]) <= 1e-12 * abs(b_[4]) and b_[4] > 0
+        # sanity against torch: symbols = round(y - mean)
+        assert torch.equal(a[2].view(C, H, W).cpu(), torch.round(a[5][0] - a[0][0, C:].cpu()).int())
+
+    def run_bitparm(fuse):
+        monkeypatch.setattr(ops, "ENT_FUSE", fuse)
+        Cz = 64
+        x = torch.randn(1, 64, 2 * H, 2 * W, generator=torch.Generator().manual_seed(5)) * 3
+        w = torch.randn(Cz, 64, 3, 3, generator=torch.Generator().manual_seed(6)) / math.sqrt(64 * 9)
+        b = torch.randn(Cz, generator=torch.Generator().manual_seed(7))
+        gg = torch.Generator().manual_seed(8)
+        coef = torch.cat([F.softplus(torch.randn(4, Cz, generator=gg) * 0.5), torch.randn(4, Cz, generator=gg) * 0.5,
+                          torch.tanh(torch.randn(3, Cz, generator=gg) * 0.5)], 0).t().contiguous().to(dev)
+        pc = ops.PackedConv(w, b, stride=2, pad=1, device=dev)
+        z_hat = ops.View.alloc(H, W, Cz, dev, zero=True)
+        bits = torch.zeros(1, dtype=torch.float64, device=dev)
+        sym = torch.zeros(Cz * H * W, dtype=torch.int32, device=dev)
+        ops.conv(pc, make_view(x.to(dev), ops), z_hat, entropy={"mode": "bitparm", "coef": coef, "bits": bits, "sym": sym})
+        torch.cuda.synchronize()
+        return z_hat.to_nchw(), sym, bits.item()
+
+    a, b_ = run_bitparm(True), run_bitparm(False)
+    assert torch.equal(a[0], b_[0]) and torch.equal(a[1], b_[1])
+    assert torch.equal(a[0], torch.round(a[0])) and float(a[0].abs().max()) > 0
+    assert abs(a[2] - b_[2]) <= 1e-12 * abs(b_[2]) and b_[2] > 0
+
+
 def test_layout_roundtrip(cuda_device):
     ops = _ops()
     dev = cuda_device
