@@ -61,6 +61,10 @@ typedef struct {
                                q = rint(ent_y - mean), ent_y_hat = q + mean, bits += clamp(-log2(Laplace(0, scale) mass of
                                [q - .5, q + .5] + 1e-5), 0, 50), symbol and CDF-row dumps: exactly lssvc_laplace_quant
                                (LSSVC_net.py:154-167, 288-296; dmc_net.py:421-488) */
+#define LSSVC_EPI_FOURPART 5 /* LAPLACE restricted to step ent_step of the four-part spatial prior (LSSVC_net.py:338-443): only the
+                                channel quarter / pixel parity pairs of that step are coded (step 0 zeroes the rest of ent_y_hat):
+                                exactly lssvc_four_part_step.  The producing convolution is the last 1x1 of a ConvFFN, so this
+                                mode (like LAPLACE / BITPARM) takes a LeakyReLU and res1 in front of the entropy arithmetic */
 #define LSSVC_EPI_BITPARM 4 /* conv output = z; out = rint(z), bits from the factorised BitEstimator prior (ent_coef),
                                symbol dump: exactly lssvc_bitparm_quant (video_entropy_models.py Bitparm / BitEstimator) */
 
@@ -109,8 +113,8 @@ typedef struct {
   const void *weight_h2;
   int32_t cin_pad16;
   float acc_scale;
-  /* entropy epilogue (epi = LSSVC_EPI_LAPLACE / LSSVC_EPI_BITPARM, lssvc_conv_hs only; needs act = NONE, out_scale = 1, no
-   * residuals / PixelShuffle / out2, cout a multiple of 16; LAPLACE beyond one channel tile: see ent_tile):
+  /* entropy epilogue (epi = LSSVC_EPI_LAPLACE / _FOURPART / _BITPARM, lssvc_conv_hs only; needs out_scale = 1, no res2 /
+   * PixelShuffle / out2, cout a multiple of 16; LAPLACE / FOURPART beyond one channel tile: see ent_tile):
    *   ent_y      LAPLACE: the latent, C = cout / 2 channels, same H x W as the output
    *   ent_y_hat  LAPLACE: the quantised latent (C channels)
    *   ent_coef   BITPARM: [cout][11] coefficient table (lssvc_bitparm_quant)
@@ -128,6 +132,7 @@ typedef struct {
    * holds [scale of channels t*ent_tile/2 .. | their means]; `out` still receives (scale | mean) in natural order.
    * ent_tile = that tile width (a multiple of 32 dividing cout, = the kernel's own channel tile); 0 = natural order, one tile. */
   int32_t ent_tile;
+  int32_t ent_step; /* FOURPART: coding step 0..3 */
 } lssvc_conv;
 
 /*

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liblssvc_b200.so")
 MAX_SRC = 3
 ACT_NONE, ACT_LRELU = 0, 1
 IN_NONE, IN_SQUARE, IN_LRELU = 0, 1, 2
-EPI_PLAIN, EPI_GDN, EPI_IGDN, EPI_LAPLACE, EPI_BITPARM = 0, 1, 2, 3, 4
+EPI_PLAIN, EPI_GDN, EPI_IGDN, EPI_LAPLACE, EPI_BITPARM, EPI_FOURPART = 0, 1, 2, 3, 4, 5
 PREC_TF32, PREC_3XTF32, PREC_H2 = 0, 1, 2
 
 
@@ -56,6 +56,7 @@ class CConv(Structure):
         ("ent_thr", c_void_p),
         ("ent_n_thr", c_int32),
         ("ent_tile", c_int32),
+        ("ent_step", c_int32),
     ]
 
 

@@ -114,6 +114,7 @@ struct alignas(64) HsParams {
   int *ent_sym, *ent_index;
   const float *ent_thr;
   int ent_n_thr;
+  int ent_step;
   long long *prof;  // DBG variant: [5 roles][8] cycle counters of CTA 0
   int dbg;  // LSSVC_HS_DBG: bottleneck-isolation switches (results are wrong when non-zero); see lssvc_conv_hs
 };
@@ -223,32 +224,55 @@ __device__ __forceinline__ void epilogue_lean(uint32_t t_row, int n_tile, int n0
 }
 
 // Entropy epilogue: the convolution that produces the entropy parameters codes the latent while the parameters are still in
-// registers (one channel tile holds every output channel; direct global stores, no staging).  The arithmetic is the
-// stand-alone kernels' own (entropy_math.cuh), applied to the very values the plain epilogue would have stored, so symbols,
-// CDF rows, quantised latents and per-element bits are bit-identical to conv + lssvc_laplace_quant / lssvc_bitparm_quant;
-// only the order in which the per-element bits are summed (warp shuffles, one double atomicAdd per warp) differs.
-//   LAPLACE: accumulator columns [0, C) = scale, [C, 2C) = mean (C = cout / 2): both are written to `out`; q = rint(y - mean),
-//            y_hat = q + mean, bits, symbol / CDF-row dumps (NCHW int32).
-//   BITPARM: accumulator = z: out = rint(z), bits from the per-channel BitEstimator coefficients, symbol dump.
+// registers (direct global stores, no staging).  The arithmetic is the stand-alone kernels' own (entropy_math.cuh), applied to
+// the very values the plain epilogue would have stored ((D1 + D2) * acc_scale + bias, LeakyReLU, + res1), so symbols, CDF rows,
+// quantised latents and per-element bits are bit-identical to conv + lssvc_laplace_quant / lssvc_four_part_step /
+// lssvc_bitparm_quant; only the order in which the per-element bits are summed (warp shuffles, one double atomicAdd per warp)
+// differs.
+//   LAPLACE:  a channel tile holds [scale of latent channels c0 .. c0 + Ct | their means] (one tile: the natural (scale | mean)
+//             order; several tiles: interleaved at pack time, lssvc_conv::ent_tile); both go to `out` in natural order;
+//             q = rint(y - mean), y_hat = q + mean, bits, symbol / CDF-row dumps (NCHW int32).
+//   FOURPART: the same for coding step p.ent_step of the four-part prior: a 16-channel chunk lies in one channel quarter and is
+//             coded only at the pixels of that step's parity; step 0 zeroes y_hat elsewhere.
+//   BITPARM:  accumulator = z: out = rint(z), bits from the per-channel BitEstimator coefficients, symbol dump.
+// (__noinline__: its register needs — two 16-channel parameter chunks live at once — stay out of the kernel's 96-register budget)
 template <int MODE>
-__device__ __forceinline__ void epilogue_entropy(const HsParams &p, uint32_t t_row, int n_tile, int n0, bool valid, long long pix) {
+__device__ __noinline__ void epilogue_entropy(const HsParams &p, uint32_t t_row, int n_tile, int n0, bool valid, long long pix) {
   const int cout = p.cout;
-  const float acc_scale = p.acc_scale;
+  const float acc_scale = p.acc_scale, slope = p.slope;
+  const bool has_act = p.act != 0;
   const long long HW = static_cast<long long>(p.Ho) * p.Wo;
+  const float *const res_row = (p.res1 && valid) ? p.res1 + pix * p.res1_pitch : nullptr;
   double local = 0.0;
-  // (D1 + D2) * acc_scale + bias for accumulator columns col .. col + 15 of this channel tile (packed channels n0 + col ..)
-  auto load16 = [&](int col, float (&v)[16]) {
+  // the plain epilogue's value for accumulator columns col .. col + 15 of this channel tile (packed channels n0 + col ..);
+  // nat = the natural (reference) index of the first of these channels, where the residual lives
+  auto load16 = [&](int col, int nat, float (&v)[16]) {
     uint32_t r1[16], r2[16];
     ptx::tmem_ld16(t_row + static_cast<uint32_t>(col), r1);
     ptx::tmem_ld16(t_row + static_cast<uint32_t>(n_tile + col), r2);
+    float4 rv[4];
+    if (res_row) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) rv[g] = __ldg(reinterpret_cast<const float4 *>(res_row + nat) + g);
+    }
     ptx::tmem_ld_wait();
 #pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = (__uint_as_float(r1[e]) + __uint_as_float(r2[e])) * acc_scale + __ldg(p.bias + n0 + col + e);
+    for (int e = 0; e < 16; ++e) {
+      float t = (__uint_as_float(r1[e]) + __uint_as_float(r2[e])) * acc_scale + __ldg(p.bias + n0 + col + e);
+      if (has_act) t = t > 0.f ? t : t * slope;
+      v[e] = t;
+    }
+    if (res_row) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        v[4 * g] += rv[g].x; v[4 * g + 1] += rv[g].y; v[4 * g + 2] += rv[g].z; v[4 * g + 3] += rv[g].w;
+      }
+    }
   };
   if (MODE == LSSVC_EPI_BITPARM) {
     for (int n = 0; n < n_tile && n0 + n < cout; n += 16) {
       float z[16];
-      load16(n, z);
+      load16(n, n0 + n, z);
       if (valid) {
         float *const o = p.out + pix * p.out_pitch + n0 + n;
 #pragma unroll
@@ -266,35 +290,50 @@ __device__ __forceinline__ void epilogue_entropy(const HsParams &p, uint32_t t_r
       }
     }
   } else {
-    // this tile: [scale of latent channels c0 .. c0 + Ct | their means] (one tile: c0 = 0, Ct = C, the natural order)
-    const int C = cout >> 1, Ct = n_tile >> 1, c0 = n0 >> 1;
+    const int C = cout >> 1, Ct = n_tile >> 1, c0 = n0 >> 1, cq = C >> 2;
+    const int step = MODE == LSSVC_EPI_FOURPART ? p.ent_step : -1;
+    int parity = 0;
+    if (MODE == LSSVC_EPI_FOURPART && valid) {
+      const int oy = static_cast<int>(pix / p.Wo), ox = static_cast<int>(pix - static_cast<long long>(oy) * p.Wo);
+      parity = ((oy & 1) << 1) | (ox & 1);
+    }
     for (int n = 0; n < Ct; n += 16) {
       float sc[16], mu[16];
-      load16(n, sc);
-      load16(Ct + n, mu);
+      load16(n, c0 + n, sc);
+      load16(Ct + n, C + c0 + n, mu);
       if (valid) {
         float *const o = p.out + pix * p.out_pitch + c0;
-        const float4 *const yq = reinterpret_cast<const float4 *>(p.ent_y + pix * p.ent_y_pitch + c0 + n);
         float4 *const yh = reinterpret_cast<float4 *>(p.ent_y_hat + pix * p.ent_h_pitch + c0 + n);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           reinterpret_cast<float4 *>(o + n)[g] = make_float4(sc[4 * g], sc[4 * g + 1], sc[4 * g + 2], sc[4 * g + 3]);
           reinterpret_cast<float4 *>(o + C + n)[g] = make_float4(mu[4 * g], mu[4 * g + 1], mu[4 * g + 2], mu[4 * g + 3]);
-          const float4 y4 = __ldg(yq + g);
-          const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
-          float h[4];
+        }
+        const int quarter = MODE == LSSVC_EPI_FOURPART ? (c0 + n) / cq : 0;   // (a 16-channel chunk never straddles two quarters)
+        const bool active = MODE != LSSVC_EPI_FOURPART || lssvc_ent::four_part_mask(step, quarter) == parity;
+        if (active) {
+          const float4 *const yq = reinterpret_cast<const float4 *>(p.ent_y + pix * p.ent_y_pitch + c0 + n);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = c0 + n + 4 * g + e;
-            const float m = mu[4 * g + e], s = sc[4 * g + e];
-            const float q = rintf(yv[e] - m);
-            h[e] = q + m;
-            local += static_cast<double>(lssvc_ent::laplace_bits(q, s));
-            const long long nchw = static_cast<long long>(c) * HW + pix;
-            if (p.ent_sym) p.ent_sym[nchw] = static_cast<int>(q);
-            if (p.ent_index) p.ent_index[nchw] = lssvc_ent::scale_index(s, p.ent_thr, p.ent_n_thr);
+          for (int g = 0; g < 4; ++g) {
+            const float4 y4 = __ldg(yq + g);
+            const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+            float h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c0 + n + 4 * g + e;
+              const float m = mu[4 * g + e], sv = sc[4 * g + e];
+              const float q = rintf(yv[e] - m);
+              h[e] = q + m;
+              local += static_cast<double>(lssvc_ent::laplace_bits(q, sv));
+              const long long nchw = static_cast<long long>(c - quarter * cq) * HW + pix;   // (FOURPART dumps hold one quarter)
+              if (p.ent_sym) p.ent_sym[nchw] = static_cast<int>(q);
+              if (p.ent_index) p.ent_index[nchw] = lssvc_ent::scale_index(sv, p.ent_thr, p.ent_n_thr);
+            }
+            yh[g] = make_float4(h[0], h[1], h[2], h[3]);
           }
-          yh[g] = make_float4(h[0], h[1], h[2], h[3]);
+        } else if (step == 0) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) yh[g] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     }
@@ -757,9 +796,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_hs_kernel(const __grid_co
           else if (r1_tma) epilogue_lean<true, 0, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr);
           else epilogue_lean<false, 0, LSSVC_EPI_PLAIN>(t_row, n_tile, n0, cout, bias, acc_scale, sl, out_scale, stage, stage2, slab_w, m, nullptr);
         }
-        const bool ent = epi == LSSVC_EPI_LAPLACE || epi == LSSVC_EPI_BITPARM;
+        const bool ent = epi == LSSVC_EPI_LAPLACE || epi == LSSVC_EPI_BITPARM || epi == LSSVC_EPI_FOURPART;
         if (ent && !(dbgf & 8)) {
           if (epi == LSSVC_EPI_LAPLACE) epilogue_entropy<LSSVC_EPI_LAPLACE>(p, t_row, n_tile, n0, valid, pix);
+          else if (epi == LSSVC_EPI_FOURPART) epilogue_entropy<LSSVC_EPI_FOURPART>(p, t_row, n_tile, n0, valid, pix);
           else epilogue_entropy<LSSVC_EPI_BITPARM>(p, t_row, n_tile, n0, valid, pix);
         }
         for (int n = 0; n < n_tile && !(dbgf & 8) && !lean && !ent; n += 16) {
@@ -1194,14 +1234,19 @@ extern "C" int32_t lssvc_conv_hs(const lssvc_conv *c, void *stream) {
   LSSVC_REQUIRE(opt(c->out2, &o2, &p.out2_pitch), "conv_hs: out2 shape mismatch");
   p.out2 = const_cast<float *>(o2);
   p.slope2 = c->slope2;
-  const bool ent_epi = c->epi == LSSVC_EPI_LAPLACE || c->epi == LSSVC_EPI_BITPARM;
+  const bool ent_epi = c->epi == LSSVC_EPI_LAPLACE || c->epi == LSSVC_EPI_BITPARM || c->epi == LSSVC_EPI_FOURPART;
   if (ent_epi) {
-    LSSVC_REQUIRE(c->act == LSSVC_ACT_NONE && c->out_scale == 1.f && !c->pixel_shuffle && !p.res1 && !p.res2 && !p.out2,
-                  "conv_hs: an entropy epilogue takes no activation, scale, residuals, PixelShuffle or second output");
+    LSSVC_REQUIRE(c->out_scale == 1.f && !c->pixel_shuffle && !p.res2 && !p.out2,
+                  "conv_hs: an entropy epilogue takes no output scale, second residual, PixelShuffle or second output");
     LSSVC_REQUIRE(c->cout % 16 == 0 && c->cout == c->n_pad && vec,
                   "conv_hs: entropy epilogue needs cout %% 16 == 0 and 16-byte aligned views (cout=%d)", c->cout);
-    if (c->epi == LSSVC_EPI_LAPLACE) {
+    if (c->epi != LSSVC_EPI_BITPARM) {
       const int C = c->cout / 2;
+      if (c->epi == LSSVC_EPI_FOURPART) {
+        LSSVC_REQUIRE(c->ent_step >= 0 && c->ent_step < 4 && C % 64 == 0, "conv_hs: four-part epilogue: step %d, C = %d (needs C %% 64 == 0)",
+                      c->ent_step, C);
+        p.ent_step = c->ent_step;
+      }
       // several channel tiles: the packed channels must have been interleaved for exactly this tile width (lssvc_conv::ent_tile)
       LSSVC_REQUIRE(n_tile % 32 == 0 && (p.n_tiles == 1 ? (c->ent_tile == 0 || c->ent_tile == n_tile) : c->ent_tile == n_tile),
                     "conv_hs: Laplace epilogue over %d channel tiles of %d needs weights interleaved for that tile (ent_tile=%d)",

@@ -48,8 +48,6 @@ __global__ void laplace_quant_kernel(const float *__restrict__ y, int yp, const 
   if (bits) block_add(local, bits);
 }
 
-__constant__ int c_mask_for[4][4] = {{0, 1, 2, 3}, {3, 2, 1, 0}, {2, 3, 0, 1}, {1, 0, 3, 2}};
-
 __global__ void four_part_step_kernel(const float *__restrict__ y, int yp, const float *__restrict__ prm, int pp,
                                       int step, float *__restrict__ yhat, int hp, float *__restrict__ yq, int qp,
                                       float *__restrict__ sh, int shp, double *__restrict__ bits, int *__restrict__ sym,
@@ -65,7 +63,7 @@ __global__ void four_part_step_kernel(const float *__restrict__ y, int yp, const
     const int cq = C >> 2;
     const int quarter = c / cq;
     const int parity = ((yy & 1) << 1) | (x & 1);
-    const bool active = c_mask_for[step][quarter] == parity;
+    const bool active = four_part_mask(step, quarter) == parity;
     if (active) {
       const float s = prm[pix * pp + c];
       const float m = prm[pix * pp + C + c];
@@ -95,7 +93,7 @@ __global__ void four_part_index_kernel(const float *__restrict__ prm, int pp, in
   const int x = static_cast<int>(pix % W), yy = static_cast<int>(pix / W);
   const int cq = C >> 2;
   const int quarter = c / cq;
-  if (c_mask_for[step][quarter] != (((yy & 1) << 1) | (x & 1))) return;
+  if (four_part_mask(step, quarter) != (((yy & 1) << 1) | (x & 1))) return;
   index[static_cast<long long>(c - quarter * cq) * H * W + pix] = scale_index(prm[pix * pp + c], thr, n_thr);
 }
 
@@ -108,7 +106,7 @@ __global__ void four_part_dec_kernel(const int *__restrict__ sym, const float *_
   const int x = static_cast<int>(pix % W), yy = static_cast<int>(pix / W);
   const int cq = C >> 2;
   const int quarter = c / cq;
-  const bool active = c_mask_for[step][quarter] == (((yy & 1) << 1) | (x & 1));
+  const bool active = four_part_mask(step, quarter) == (((yy & 1) << 1) | (x & 1));
   if (active) {
     const float q = static_cast<float>(sym[static_cast<long long>(c - quarter * cq) * H * W + pix]);
     yhat[pix * hp + c] = q + prm[pix * pp + C + c];

@@ -48,4 +48,8 @@ __device__ __forceinline__ float bitparm_bits(float q, const float *__restrict__
   return prob_bits(bitparm_cdf(q + 0.5f, k) - bitparm_cdf(q - 0.5f, k));
 }
 
+// Four-part spatial prior (LSSVC_net.py:338-443): at coding step `step` the channel quarter `quarter` is coded at the pixels of
+// parity ((y & 1) << 1 | (x & 1)) == four_part_mask(step, quarter); rows {0,1,2,3}, {3,2,1,0}, {2,3,0,1}, {1,0,3,2} packed 2 bits each
+__device__ __forceinline__ int four_part_mask(int step, int quarter) { return (0xb14e1be4u >> (2 * (4 * step + quarter))) & 3; }
+
 }  // namespace lssvc_ent

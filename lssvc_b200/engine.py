@@ -97,7 +97,8 @@ class Engine(nets.ParamBag):
             else:
                 srcs = [self.lrelu(s.base, s.slope) if isinstance(s, ops.LazyAct) else s for s in srcs]
         pair_tile = 0
-        if entropy is not None and entropy["mode"] == "laplace" and act is None and out_scale == 1.0 and not ps:
+        if (entropy is not None and entropy["mode"] in ("laplace", "fourpart") and out_scale == 1.0 and not ps and res2 is None
+                and act_copy is None and entropy.get("y_q") is None and entropy.get("s_hat") is None):
             # 2C parameter channels beyond one channel tile: interleave (scale, mean) per tile at pack time (ops.PackedConv)
             pair_tile = ops.laplace_pair_tile(2 * entropy["y"].C, engine)
         pc = self.pack(name, srcs, stride, ps, transposed, pad, exact_in, pair_tile)
@@ -264,9 +265,10 @@ class Engine(nets.ParamBag):
         return self.conv(name + ".conv2", t, act=slope if end_with_relu else None, res1=x, res2=res2, out=out,
                          act_copy=act_copy, act_copy_out=act_copy_out)
 
-    def depth_conv_block(self, name, x, res2=None, out=None):
+    def depth_conv_block(self, name, x, res2=None, out=None, entropy=None):
         """DepthConvBlock (lssvc_modules.py:15-72): DepthConv (1x1, lrelu .01, dw3x3, 1x1, + identity/adaptor)
-        then ConvFFN (x + lrelu(1x1(lrelu(1x1 x, .1)), .1))."""
+        then ConvFFN (x + lrelu(1x1(lrelu(1x1 x, .1)), .1)).
+        entropy: the block emits entropy parameters — its last 1x1 codes the latent in its epilogue (ops.conv `entropy`)."""
         dc, ffn = name + ".block.0", name + ".block.1"
         has_adaptor = (dc + ".adaptor.weight") in self._spec
         t = self.pointwise(dc + ".conv1.0", x, act=0.01)
@@ -284,9 +286,11 @@ class Engine(nets.ParamBag):
             ox = out.exact()
             if ox.pitch % 4 == 0 and ox.coff % 4 == 0 and (res2 is None or (res2.pitch % 4 == 0 and res2.coff % 4 == 0)):
                 ops.ffn(pf, o.exact(), ox, res2=None if res2 is None else res2.exact())
+                if entropy is not None:
+                    ops.entropy_standalone(entropy, ox)
                 return out
         f = self.conv(ffn + ".conv.0", o, act=0.1, pad=0)
-        return self.conv(ffn + ".conv.2", f, act=0.1, pad=0, res1=o, res2=res2, out=out)
+        return self.conv(ffn + ".conv.2", f, act=0.1, pad=0, res1=o, res2=res2, out=out, entropy=entropy)
 
     def extractor3(self, name, x):
         """conv1/res_block1, conv2 s2/res_block2, conv3 s2/res_block3

@@ -671,7 +671,8 @@ class LSSVC(Engine):
         self.copy(ctx, cat.slice(cout, cat.C))
         return self.res_block(name, cat, slope=0.1, start_from_relu=True, end_with_relu=True)
 
-    def _res_params(self, z_hat, c3, y_bl_hat):
+    def _res_params(self, z_hat, c3, y_bl_hat, entropy=None):
+        """entropy: step 0 of the four-part prior, coded in the epilogue of the block's last convolution (encoder side)."""
         h = self.conv("res_prior_decoder.0", z_hat, act=0.01, exact_in=True)
         h = self.conv("res_prior_decoder.2.0", h, ps=True, act=0.01, pad=0)
         h = self.conv("res_prior_decoder.4", h, act=0.01)
@@ -683,35 +684,40 @@ class LSSVC(Engine):
         self.copy(self._layer_prior_resampler(y_bl_hat), cat.slice(256, 384))
         # PriorFusion (lssvc_modules.py:432-442)
         t = self.depth_conv_block("prior_fusion_net.prior_fusion_conv.0", cat)
-        return self.depth_conv_block("prior_fusion_net.prior_fusion_conv.1", t)
+        return self.depth_conv_block("prior_fusion_net.prior_fusion_conv.1", t, entropy=entropy)
 
-    def _spatial_prior(self, step, y_hat_so_far, common):
+    def _spatial_prior(self, step, y_hat_so_far, common, entropy=None):
         """y_spatial_prior(y_spatial_prior_adaptor_k(cat(y_hat_so_far, common_params)))   LSSVC_net.py:372-404"""
         t = self.conv(f"y_spatial_prior_adaptor_{step}", [y_hat_so_far, common], pad=0)
         for i in range(3):
-            t = self.depth_conv_block(f"y_spatial_prior.{i}", t)
+            t = self.depth_conv_block(f"y_spatial_prior.{i}", t, entropy=entropy if i == 2 else None)
         return t
 
-    def _four_part(self, y, common, bits, w=None):
-        """forward_four_part_prior (LSSVC_net.py:338-443)."""
+    def _four_part(self, y, z_hat, c3, y_bl_hat, bits, w=None):
+        """forward_four_part_prior (LSSVC_net.py:338-443) together with the networks that produce its parameters: step k is coded
+        in the epilogue of the last convolution of the block that emits step k's (scale | mean) — the prior-fusion net for step 0,
+        y_spatial_prior for steps 1-3 (LSSVC_EPI_FOURPART; lssvc_four_part_step after the block when that cannot be fused, e.g.
+        with the debug outputs on).  Returns (y_hat, common parameters)."""
         C = y.real
         y_hat = self.new(y.H, y.W, C)
         thr = self._thr() if w else None
-        prm = common
         dbg = getattr(self, "_debug", None)
         y_q = self.new(y.H, y.W, C) if dbg is not None else None
         s_hat = self.new(y.H, y.W, C) if dbg is not None else None
         _dbg(self, y_q=y_q, scales_hat=s_hat)
+        common = None
         for step in range(4):
-            ops.four_part_step(y, prm, step, y_hat, y_q, s_hat, bits.ptr(1),
-                               sym=w.buf(f"el_y{step}", y, C // 4) if w else None,
-                               index=w.buf(f"el_y{step}_idx", y, C // 4) if w else None, thresholds=thr)
+            ent = {"mode": "fourpart", "step": step, "y": y.exact(), "y_hat": y_hat.exact(), "y_q": y_q, "s_hat": s_hat,
+                   "bits": bits.ptr(1), "sym": w.buf(f"el_y{step}", y, C // 4) if w else None,
+                   "index": w.buf(f"el_y{step}_idx", y, C // 4) if w else None, "thresholds": thr}
+            if step == 0:
+                common = self._res_params(z_hat, c3, y_bl_hat, entropy=ent)
+            else:
+                self._spatial_prior(step, y_hat, common, entropy=ent)
             if y_q is not None and getattr(self, "_force", None) and "y_q" in self._force:
                 # coded-so-far positions are the ones with a (strictly positive) scale recorded
                 _force(self, "y_q", y_hat, mask=s_hat.exact().as_tensor() != 0, q_view=y_q)
-            if step < 3:
-                prm = self._spatial_prior(step + 1, y_hat, common)
-        return y_hat
+        return y_hat, common
 
     def _res_decode(self, y_hat, c1, c2, c3):
         """ResDecoder (lssvc_modules.py:257-276) + ReconGeneration (:279-292, called as (recon_image_feature, context1))."""
@@ -788,8 +794,7 @@ class LSSVC(Engine):
         y = self._res_encode(xe, c1, c2, c3)
         z_hat = self._prior_encoder("res_prior_encoder", y, self._bitparm_coef("bit_estimator_z."), bits.ptr(1), w, "el_z")
         _force(self, "z_hat", z_hat)
-        params = self._res_params(z_hat, c3, y_hat_bl)
-        y_hat = self._four_part(y, params, bits, w)
+        y_hat, params = self._four_part(y, z_hat, c3, y_hat_bl, bits, w)
         if w:
             w.layer_done("el")
         feature, recon = self._res_decode(y_hat, c1, c2, c3)

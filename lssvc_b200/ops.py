@@ -333,8 +333,8 @@ def hs_channel_tile(n_pad):
 
 
 def laplace_pair_tile(cout, engine=None):
-    """pair_tile to pack a (scale | mean) convolution with so that its Laplace epilogue can span several channel tiles; 0 when one
-    tile holds all 2C channels (natural order) or when the epilogue will not be fused anyway."""
+    """pair_tile to pack a (scale | mean) convolution with so that its Laplace / four-part epilogue can span several channel tiles;
+    0 when one tile holds all 2C channels (natural order) or when the epilogue will not be fused anyway."""
     if cout <= 128 or not ENT_FUSE or (engine or _ENGINE) not in ("h2", "hs") or cout % 16:
         return 0
     t = hs_channel_tile(cout)
@@ -342,16 +342,32 @@ def laplace_pair_tile(cout, engine=None):
 
 
 def _entropy_fusable(pc, out, act, res1, res2, out2, out_scale, epi, ent):
-    """Can lssvc_conv_hs take this entropy epilogue?  (16-byte aligned views, plain epilogue, scale / mean pairs inside a tile)"""
-    if not ENT_FUSE or act is not None or res1 is not None or res2 is not None or out2 is not None or out_scale != 1.0:
+    """Can lssvc_conv_hs take this entropy epilogue?  (16-byte aligned views, LeakyReLU + one residual at most in front of it,
+    scale / mean pairs inside a channel tile, no debug outputs)"""
+    if not ENT_FUSE or res2 is not None or out2 is not None or out_scale != 1.0 or (res1 is not None and not view_aligned(res1)):
         return False
     if epi != _lib.EPI_PLAIN or pc.pixel_shuffle or pc.cout % 16 or pc.cout != pc.n_pad or not view_aligned(out):
         return False
-    if ent["mode"] == "laplace":
+    if ent["mode"] in ("laplace", "fourpart"):
         tile = hs_channel_tile(pc.n_pad)
         paired = pc.pair_tile == tile if pc.cout > 128 else pc.pair_tile in (0, tile)
+        if ent["mode"] == "fourpart" and (pc.cout % 128 or ent.get("y_q") is not None or ent.get("s_hat") is not None):
+            return False
         return tile % 32 == 0 and paired and view_aligned(ent["y"]) and view_aligned(ent["y_hat"])
     return ent["mode"] == "bitparm"
+
+
+def entropy_standalone(ent, prm):
+    """The stand-alone entropy kernel for an `entropy` request of ops.conv, on parameters `prm` = (scale | mean) already in
+    memory (or, for "bitparm", prm = z and ent["z_hat"] the destination)."""
+    if ent["mode"] == "bitparm":
+        return bitparm_quant(prm, ent["coef"], ent["z_hat"], ent.get("bits"), sym=ent.get("sym"))
+    C = prm.C // 2
+    if ent["mode"] == "fourpart":
+        return four_part_step(ent["y"], prm, ent["step"], ent["y_hat"], ent.get("y_q"), ent.get("s_hat"), ent.get("bits"),
+                              sym=ent.get("sym"), index=ent.get("index"), thresholds=ent.get("thresholds"))
+    return laplace_quant(ent["y"], prm.slice(C, 2 * C), prm.slice(0, C), None, ent["y_hat"], ent.get("bits"),
+                         sym=ent.get("sym"), index=ent.get("index"), thresholds=ent.get("thresholds"))
 
 
 def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, out_scale=1.0,
@@ -376,15 +392,13 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
         if not fuse:
             kw = dict(act=act, res1=res1, res2=res2, out2=out2, slope2=slope2, out_scale=out_scale, in_transform=in_transform,
                       in_slope=in_slope, epi=epi, gdn_x=gdn_x, engine=engine)
-            if entropy["mode"] == "laplace":
-                conv(pc, srcs, out, **kw)
-                C = pc.cout // 2
-                laplace_quant(entropy["y"], out.slice(C, 2 * C), out.slice(0, C), None, entropy["y_hat"], entropy.get("bits"),
-                              sym=entropy.get("sym"), index=entropy.get("index"), thresholds=entropy.get("thresholds"))
-            else:
+            if entropy["mode"] == "bitparm":
                 z = View.alloc(out.H, out.W, out.C, out.device)
                 conv(pc, srcs, z, **kw)
-                bitparm_quant(z, entropy["coef"], out, entropy.get("bits"), sym=entropy.get("sym"))
+                entropy_standalone(dict(entropy, z_hat=out), z)
+            else:
+                conv(pc, srcs, out, **kw)
+                entropy_standalone(entropy, out)
             return out
     d = CConv()
     d.n_src = len(srcs)
@@ -405,8 +419,9 @@ def conv(pc, srcs, out, act=None, res1=None, res2=None, out2=None, slope2=0.0, o
     if entropy is not None:                          # (fusable: checked above)
         g = lambda k: None if entropy.get(k) is None else entropy[k].data_ptr()
         d.ent_bits, d.ent_sym = g("bits"), g("sym")
-        if entropy["mode"] == "laplace":
-            d.epi = _lib.EPI_LAPLACE
+        if entropy["mode"] in ("laplace", "fourpart"):
+            d.epi = _lib.EPI_LAPLACE if entropy["mode"] == "laplace" else _lib.EPI_FOURPART
+            d.ent_step = int(entropy.get("step") or 0)
             d.ent_y, d.ent_y_hat = entropy["y"].c(), entropy["y_hat"].c()
             d.ent_index, d.ent_thr = g("index"), g("thresholds")
             d.ent_n_thr = 0 if entropy.get("thresholds") is None else entropy["thresholds"].numel()

@@ -630,6 +630,38 @@ def test_entropy_epilogues(cuda_device, monkeypatch, shape):
         # sanity against torch: symbols = round(y - mean)
         assert torch.equal(a[2].view(C, H, W).cpu(), torch.round(a[5][0] - a[0][0, C:].cpu()).int())
 
+    def run_fourpart(fuse):
+        """the last 1x1 of a ConvFFN (LeakyReLU + residual) emitting 2 x 128 parameters = two channel tiles, four coding steps"""
+        monkeypatch.setattr(ops, "ENT_FUSE", fuse)
+        C = 128
+        x = torch.randn(1, 64, H, W, generator=torch.Generator().manual_seed(11))
+        wt = torch.randn(2 * C, 64, 1, 1, generator=torch.Generator().manual_seed(12)) / 8
+        b = torch.randn(2 * C, generator=torch.Generator().manual_seed(13)) * 0.5
+        r = torch.randn(1, 2 * C, H, W, generator=torch.Generator().manual_seed(14))
+        y = torch.randn(1, C, H, W, generator=torch.Generator().manual_seed(15)) * 4
+        pc = ops.PackedConv(wt, b, pad=0, device=dev, pair_tile=ops.laplace_pair_tile(2 * C) if fuse else 0)
+        assert pc.pair_tile == (128 if fuse else 0)
+        xv, rv, yv = make_view(x.to(dev), ops), make_view(r.to(dev), ops), make_view(y.to(dev), ops)
+        y_hat = ops.View.alloc(H, W, C, dev)
+        y_hat.buf.fill_(float("nan"))                      # step 0 must define every element
+        bits = torch.zeros(1, dtype=torch.float64, device=dev)
+        outs = []
+        for step in range(4):
+            prm = ops.View.alloc(H, W, 2 * C, dev, zero=True)
+            sym = torch.zeros(C // 4 * H * W, dtype=torch.int32, device=dev)
+            idx = torch.zeros(C // 4 * H * W, dtype=torch.int32, device=dev)
+            ops.conv(pc, xv, prm, act=0.1, res1=rv, entropy={"mode": "fourpart", "step": step, "y": yv, "y_hat": y_hat, "bits": bits,
+                                                             "sym": sym, "index": idx, "thresholds": thr})
+            torch.cuda.synchronize()
+            outs += [prm.to_nchw(), y_hat.to_nchw(), sym, idx]
+        return outs, bits.item()
+
+    (fa, fbits), (fb, fbits_ref) = run_fourpart(True), run_fourpart(False)
+    for i, (u, v) in enumerate(zip(fa, fb)):
+        assert torch.equal(u, v), ("fourpart", i)
+    assert abs(fbits - fbits_ref) <= 1e-12 * abs(fbits_ref) and fbits_ref > 0
+    assert torch.isfinite(fa[-3]).all() and float(fa[-3].abs().max()) > 0     # y_hat after step 3: every position coded
+
     def run_bitparm(fuse):
         monkeypatch.setattr(ops, "ENT_FUSE", fuse)
         Cz = 64
