@@ -13,6 +13,7 @@ Stream order per layer (one string, one flush): BL [mv_z | mv_y | z | y], EL [mv
 """
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 from . import entropy, ops, stream
 from .ops import View
@@ -271,14 +272,15 @@ def el_decompress(model, string, height, width, dpb):
     rd = _Reader(model, string)
     ref = _to_view(model, dpb["ref_frame_el"], image=True)
     ref_feature = _to_view(model, dpb.get("ref_feature_el"))
-    mv_ctx_prior, mv_ctx = model._mv_contexts(_to_view(model, dpb["mv_hat_bl"]))
+    # (de-padded base-layer tensors: LSSVC_net_extend.py:97-99)
+    mv_ctx_prior, mv_ctx = model._mv_contexts(model.depad(_to_view(model, dpb["mv_hat_bl"])))
     zh, zw = stream.get_downsampled_shape(height, width, 64)
     mv_z_hat = rd.factorized(t["el_mv_z"], zh, zw)
     mv_y_hat = rd.laplace(model._mv_params(mv_z_hat, mv_ctx_prior), t["laplace"], "el_mv_y")
     mv_hat = model._mv_decode(mv_y_hat, mv_ctx)
-    c1, c2, c3, _ = model._hybrid_contexts(_to_view(model, dpb["texture"]), mv_hat, ref, ref_feature)
+    c1, c2, c3, _ = model._hybrid_contexts(model.depad(_to_view(model, dpb["texture"])), mv_hat, ref, ref_feature)
     z_hat = rd.factorized(t["el_z"], zh, zw)
-    params = model._res_params(z_hat, c3, _to_view(model, dpb["y_hat_bl"]))
+    params = model._res_params(z_hat, c3, model.depad(_to_view(model, dpb["y_hat_bl"]), 16))
     y_hat = rd.four_part(params, t["laplace"])
     feature, recon = model._res_decode(y_hat, c1, c2, c3)
     return {"dpb": {"ref_frame_el": recon.to_nchw(), "ref_feature_el": feature.to_nchw()}}
@@ -440,14 +442,16 @@ def intra_encode_decode(model, x_bl, x_el, bin_path_bl, bin_path_el, pic_height_
     stream.encode_i(pic_height_bl, pic_width_bl, comp["strings"][0][0], comp["strings"][1][0], bin_path_bl)
     bit_bl = stream.filesize(bin_path_bl) * 8
     enc = intra_bl_get_y_hat_recon(model, y_bl, z_bl)
-    y_el, z_el, ctx = intra_get_y_z_ctx(model, enc["x_hat"], x_el)
-    comp = intra_compress(model, y=y_el, z=z_el, ctx3=ctx[2], y_hat_bl=enc["y_hat"])
+    dp = lambda t, p=1: t if not any(int(a / p) for a in model.pad_size) else F.pad(t, [int(a / p) for a in model.pad_size])
+    # (x_hat_bl_depadded / y_hat_bl_depadded: IntraSS.py:262-263, 285-286)
+    y_el, z_el, ctx = intra_get_y_z_ctx(model, dp(enc["x_hat"]), x_el)
+    comp = intra_compress(model, y=y_el, z=z_el, ctx3=ctx[2], y_hat_bl=dp(enc["y_hat"], 16))
     stream.encode_i(pic_height_el, pic_width_el, comp["strings"][0][0], comp["strings"][1][0], bin_path_el)
     bit_el = stream.filesize(bin_path_el) * 8
     # ---- decode
     h, w, y_string, z_string = stream.decode_i(bin_path_bl)
     dec_bl = intra_bl_decompress(model, [[y_string], [z_string]], stream.get_downsampled_shape(h, w, 64))
     h, w, y_string, z_string = stream.decode_i(bin_path_el)
-    dec = intra_decompress(model, [[y_string], [z_string]], {"x_hat_bl": dec_bl["x_hat"], "y_hat_bl": dec_bl["y_hat"]},
+    dec = intra_decompress(model, [[y_string], [z_string]], {"x_hat_bl": dp(dec_bl["x_hat"]), "y_hat_bl": dp(dec_bl["y_hat"], 16)},
                            stream.get_downsampled_shape(h, w, 64))
     return {"bit_bl": bit_bl, "bit_el": bit_el, "x_hat_bl": dec_bl["x_hat"], "x_hat_el": dec["x_hat"], "feature_el": dec["feature"]}

@@ -5,6 +5,7 @@ A model is a nets.ParamBag (reference-layout tensors) + this mixin.  Activations
 import os
 
 import torch
+import torch.nn.functional as F
 
 from . import _lib, nets, ops
 from .ops import View
@@ -34,9 +35,20 @@ class Engine(nets.ParamBag):
         if new != (self.scale_factor, self.shape_hr, self.pad_size):     # test.py:212-213 calls this before every frame
             self._graphs = {}
         self.scale_factor, self.shape_hr, self.pad_size = new
-        if any(int(p) != 0 for p in self.pad_size):
-            # the reference's test.py always passes (0, 0, 0, 0) (test.py:212-213)
-            raise NotImplementedError("inter-layer de-padding with a non-zero pad_size is not implemented")
+
+    def depad(self, v, p=1):
+        """get_depadded_feature (LSSVC_net.py:271-282, IntraSS.py:124-135): F.pad of a base-layer tensor by pad_size / p (left, right,
+        top, bottom; negative = crop, the case the inter-layer padding produces) before it is resampled for the enhancement
+        layer.  test.py:212-213 always passes zeros, for which this is the identity; otherwise one strided copy (torch plumbing)."""
+        if v is None:
+            return None
+        pads = [int(a / p) for a in self.pad_size]
+        if not any(pads):
+            return v
+        t = F.pad(v.exact().as_tensor().permute(2, 0, 1), pads, mode="constant", value=0).permute(1, 2, 0)
+        out = self.new(t.shape[0], t.shape[1], v.real)
+        out.exact().as_tensor().copy_(t)
+        return out
 
     # ---- weight cache ---------------------------------------------------------------------------------------
     def _invalidate(self):

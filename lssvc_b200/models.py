@@ -305,13 +305,13 @@ class IntraSS(Engine):
         _force(self, "bl_y_q", y_hat_bl, mean=prm.slice(C, 2 * C))
         _dbg(self, params_bl=prm)
         x_hat_bl = self._bl_synthesis(y_hat_bl)
-        # ---- enhancement layer
-        c1, c2, c3 = self._context_mining(x_hat_bl)
+        # ---- enhancement layer (the base-layer tensors it reads are de-padded first: IntraSS.py:145-147)
+        c1, c2, c3 = self._context_mining(self.depad(x_hat_bl))
         y, z = self._el_analysis(xe, c1, c2, c3)
         z_hat = self.new(z.H, z.W, z.real)
         ops.eb_quant(z, self._eb_coef("entropy_bottleneck."), z_hat, bits.ptr(1), sym=w.buf("el_z", z) if w else None)
         _force(self, "z_hat", z_hat)
-        prm = self._el_params(z_hat, y_hat_bl, c3)
+        prm = self._el_params(z_hat, self.depad(y_hat_bl, 16), c3)
         C = y.real
         y_hat = self.new(y.H, y.W, C)
         ops.gaussian_quant(y, prm.slice(C, 2 * C), prm.slice(0, C), y_hat, bits.ptr(1),
@@ -777,6 +777,8 @@ class LSSVC(Engine):
 
     def _el_layer(self, xe, re, fe, texture_bl, y_hat_bl, mv_hat_bl, bits, w):
         """Enhancement layer of one P-frame given the decoded base layer (LSSVC_net.py:455-508, LSSVC_net_extend.py:24-86)."""
+        # inter-layer processing: de-padded base-layer texture / motion / latent (LSSVC_net.py:453-456)
+        texture_bl, mv_hat_bl, y_hat_bl = self.depad(texture_bl), self.depad(mv_hat_bl), self.depad(y_hat_bl, 16)
         # EL motion
         mv_ctx_prior, mv_ctx = self._mv_contexts(mv_hat_bl)
         mv = self.spynet("optic_flow", xe, re)

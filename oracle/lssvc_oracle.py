@@ -318,11 +318,20 @@ def _recon_generation_bl(p, first, second):
     return f, conv(p.sub("recon_conv"), f)
 
 
-def intra_ss(sd, x_bl, x_el, shape_hr):
+def depad(feature, pad_size, p=1):
+    """get_depadded_feature   LSSVC_net.py:271-282, IntraSS.py:124-135: F.pad by pad_size / p (negative = crop)."""
+    if feature is None:
+        return None
+    return F.pad(feature, tuple(int(a / p) for a in pad_size), mode="constant", value=0)
+
+
+def intra_ss(sd, x_bl, x_el, shape_hr, pad_size=(0, 0, 0, 0)):
     """IntraSS.forward   IntraSS.py:137-172 (pad_size is (0,0,0,0) on the test.py path, :212-213)."""
     p = Params(sd)
     bl = intra_noar(p.sub("base_layer_model"), x_bl)
-    x_hat_bl, y_hat_bl = bl["x_hat"], bl["y_hat"]
+    x_hat_bl_full, y_hat_bl_full = bl["x_hat"], bl["y_hat"]
+    # de-padded copies feed the enhancement layer; the returned x_hat_bl is the full one   IntraSS.py:145-147
+    x_hat_bl, y_hat_bl = depad(x_hat_bl_full, pad_size), depad(y_hat_bl_full, pad_size, 16)
     # multi_scale_context_mining   IntraSS.py:119-122; TextureResampler layers.py:258-270
     tr = p.sub("texture_resampler.conv_adaptor")
     texture = conv(tr.sub("2"), lrelu(conv(tr.sub("0"), x_hat_bl)))
@@ -358,7 +367,7 @@ def intra_ss(sd, x_bl, x_el, shape_hr):
     bit_el = (torch.log(y_lik).sum() + torch.log(z_lik).sum()) / (-LN2)
     return {
         "bit_bl": bl["bits"].item(), "bit_el": bit_el.item(),
-        "x_hat_bl": x_hat_bl, "x_hat_el": x_hat, "feature_el": feature,
+        "x_hat_bl": x_hat_bl_full, "x_hat_el": x_hat, "feature_el": feature,
         # internals for parity tests
         "bl": bl, "y": y, "z": z, "z_hat": z_hat, "scales": scales, "means": means, "y_hat": y_hat,
         "ctx": (c1, c2, c3),
@@ -580,11 +589,12 @@ def four_part_prior(p, y, common_params):
             "scales_hat": torch.cat(s_hat, 1), "y_q_w": y_q_w, "scales_w": scales_w}
 
 
-def lssvc(sd, x_bl, x_el, dpb, shape_hr, scale_factor):
+def lssvc(sd, x_bl, x_el, dpb, shape_hr, scale_factor, pad_size=(0, 0, 0, 0)):
     """LSSVC.forward_one_frame   LSSVC_net.py:445-528."""
     p = Params(sd)
     bl = dmc(p.sub("base_layer_model"), x_bl, dpb["ref_frame_bl"], dpb["ref_feature_bl"])
-    texture_bl, mv_bl_hat, y_bl_hat = bl["feature"], bl["mv_hat"], bl["y_hat"]
+    # inter-layer processing on the de-padded base-layer tensors   LSSVC_net.py:453-456
+    texture_bl, mv_bl_hat, y_bl_hat = depad(bl["feature"], pad_size), depad(bl["mv_hat"], pad_size), depad(bl["y_hat"], pad_size, 16)
     ref_el, feat_el = dpb["ref_frame_el"], dpb["ref_feature_el"]
 
     mv_up = _mv_resampler(p.sub("mv_resampler"), mv_bl_hat, shape_hr, scale_factor)

@@ -14,7 +14,9 @@ from lssvc_b200 import nets, synth  # noqa: E402
 from oracle import lssvc_oracle as orc  # noqa: E402
 
 
-def main(H=128, W=128, n_frames=4, seed=0, ratio=2.0):
+def main(H=128, W=128, n_frames=4, seed=0, ratio=2.0, bl_pad=0):
+    """bl_pad > 0: the base layer is coded on a frame padded by bl_pad more pixels (right / bottom) than the enhancement layer's
+    size / ratio, and the models de-pad its tensors with pad_size = (0, -bl_pad, 0, -bl_pad) (get_depadded_feature)."""
     torch.manual_seed(0)
     IntraSS, LSSVC_extend = ref_harness.import_reference()
     sd_i = nets.ParamBag(nets.intra_ss_spec(), seed=seed, gains=nets.model_gains("I")).state_dict()
@@ -23,16 +25,19 @@ def main(H=128, W=128, n_frames=4, seed=0, ratio=2.0):
     ref_p = LSSVC_extend().eval()
     ref_p.load_dict(dict(sd_p))
     frames = synth.make_sequence(H, W, n_frames, seed=seed, ratio=ratio)
+    pad_size = (0, -bl_pad, 0, -bl_pad)
+    if bl_pad:
+        frames = [(torch.nn.functional.pad(b, (0, bl_pad, 0, bl_pad), mode="replicate"), e) for b, e in frames]
     worst = 0.0
     with torch.no_grad():
         dpb_r = dpb_o = None
         for t, (x_bl, x_el) in enumerate(frames):
-            ref_i.set_scale_information(ratio, (H, W), (0, 0, 0, 0))
-            ref_p.set_scale_information(ratio, (H, W), (0, 0, 0, 0))
+            ref_i.set_scale_information(ratio, (H, W), pad_size)
+            ref_p.set_scale_information(ratio, (H, W), pad_size)
             t0 = time.time()
             if t == 0:
                 r = ref_i.encode_decode(x_bl, x_el, None, None, x_bl.shape[2], x_bl.shape[3], H, W)
-                o = orc.intra_ss(sd_i, x_bl, x_el, (H, W))
+                o = orc.intra_ss(sd_i, x_bl, x_el, (H, W), pad_size)
                 pairs = [("x_hat_bl", r["x_hat_bl"], o["x_hat_bl"]), ("x_hat_el", r["x_hat_el"], o["x_hat_el"]),
                          ("feature_el", r["feature_el"], o["feature_el"])]
                 dpb_r = {"ref_frame_bl": r["x_hat_bl"], "ref_frame_el": r["x_hat_el"], "ref_feature_bl": None,
@@ -41,7 +46,7 @@ def main(H=128, W=128, n_frames=4, seed=0, ratio=2.0):
                          "ref_feature_el": o["feature_el"]}
             else:
                 r = ref_p.encode_decode(x_bl, x_el, dpb_r, None, None, W, H, x_bl.shape[3], x_bl.shape[2])
-                o = orc.lssvc(sd_p, x_bl, x_el, dpb_o, (H, W), ratio)
+                o = orc.lssvc(sd_p, x_bl, x_el, dpb_o, (H, W), ratio, pad_size)
                 pairs = [(k, r["dpb"][k], o["dpb"][k]) for k in r["dpb"]] + [("mv_hat", r["mv_hat"], o["mv_hat"]),
                                                                              ("warp_frame", r["warp_frame"], o["warp_frame"])]
                 dpb_r, dpb_o = r["dpb"], o["dpb"]
@@ -73,6 +78,8 @@ def main(H=128, W=128, n_frames=4, seed=0, ratio=2.0):
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     if len(sys.argv) > 2:          # e.g. "3 1.5 192": the x1_5 ratio of recommend_test_config.json at EL 192x192 / BL 128x128
-        main(H=int(sys.argv[3]), W=int(sys.argv[3]), n_frames=n, ratio=float(sys.argv[2]))
+        # "3 2 128 64": BL coded at 128x128 for an EL of 128x128 (64 px of extra BL padding, pad_size = (0, -64, 0, -64))
+        main(H=int(sys.argv[3]), W=int(sys.argv[3]), n_frames=n, ratio=float(sys.argv[2]),
+             bl_pad=int(sys.argv[4]) if len(sys.argv) > 4 else 0)
     else:
         main(n_frames=n)

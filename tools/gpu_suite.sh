@@ -9,6 +9,7 @@
 #   launches   ncu launch list of bench.py              -> gpurun_out/<tag>_launches.csv
 #   ncu        ncu --set full of tools/ncu_driver.py    -> gpurun_out/<tag>_kernels_raw.csv (raw metrics page)
 #   ffn        tools/ffn_bench.py + pw_bench.py         -> gpurun_out/<tag>_ffn.log
+#   ncu2       ncu --set full of tools/ncu_driver2.py   -> gpurun_out/<tag>_head_entropy.ncu-rep (conv_head, entropy epilogues)
 # TAG=<tag> (default r2) names the outputs.
 TAG=${TAG:-r2}
 for what in "$@"; do
@@ -31,6 +32,10 @@ for what in "$@"; do
          ncu --set full --clock-control none -k regex:'conv_ffn|conv_pw|conv_hs|dwconv|od_|offset_div|flow_warp|laplace|four_part|bilinear|nhwc|pool2|softmax2|lrelu_copy' \
              -c 80 --csv --page raw --log-file gpurun_out/${TAG}_kernels_raw.csv python tools/ncu_driver.py > gpurun_out/${TAG}_ncu.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/${TAG}_ncu.log
          ls -la gpurun_out/${TAG}_kernels_raw.csv;;
+    ncu2) # conv_head + the entropy epilogues of conv_hs (tools/ncu_driver2.py); the .ncu-rep is small enough to travel
+         python tools/ncu_driver2.py > gpurun_out/${TAG}_ncu2_plain.log 2>&1 &&
+         ncu --set full --clock-control none --import-source on -k regex:'conv_head|conv_hs' -c 16 -f -o gpurun_out/${TAG}_head_entropy \
+             python tools/ncu_driver2.py > gpurun_out/${TAG}_ncu2.log 2>&1; echo "ncu2 rc=$?"; tail -2 gpurun_out/${TAG}_ncu2.log; ls -la gpurun_out/${TAG}_head_entropy.ncu-rep;;
     *) echo "unknown: $what";;
   esac
 done
