@@ -55,3 +55,26 @@ def test_empty_taps_do_not_count_as_accumulation_steps():
         m = base[:, ch].abs() > 0.5
         ratio = (got[:, ch][m] / base[:, ch][m]).mean().item()
         assert abs(ratio - float(ops.acc_comp(steps))) < 2e-7, (ch, steps, ratio)
+
+
+def test_laplace_pair_tile_interleaves_scale_and_mean_per_channel_tile():
+    """Entropy epilogues over several channel tiles: the channel tile conv_hs picks, and the pack-time permutation that
+    puts a latent channel's scale and mean into the same tile ([scale of Ct channels | their means] per tile of 2 Ct)."""
+    assert ops.hs_channel_tile(128) == 128 and ops.hs_channel_tile(192) == 96 and ops.hs_channel_tile(256) == 128
+    assert ops.hs_channel_tile(1152) == 128 and ops.hs_channel_tile(144) == 48
+    assert ops.laplace_pair_tile(128) == 0                      # one tile: natural (scale | mean) order
+    assert ops.laplace_pair_tile(192) == 96 and ops.laplace_pair_tile(256) == 128
+    assert ops.laplace_pair_tile(192, engine="simt") == 0       # nothing to interleave for an engine without the epilogue
+    assert ops.laplace_pair_tile(144) == 0                      # tile 48: its halves are not 16-channel aligned -> not fused
+    C = 96
+    w = torch.arange(2 * C, dtype=torch.float32).reshape(2 * C, 1, 1, 1).repeat(1, 16, 1, 1)      # every weight of channel c is c
+    b = torch.arange(2 * C, dtype=torch.float32)
+    pc = ops.PackedConv(w, b, pad=0, exact_in=True, pair_tile=96)
+    order = pc.bias[:2 * C].to(torch.int64).tolist()
+    for t in range(2):
+        tile = order[96 * t:96 * (t + 1)]
+        assert tile[:48] == list(range(48 * t, 48 * t + 48))                   # scales of latent channels 48 t ..
+        assert tile[48:] == list(range(C + 48 * t, C + 48 * t + 48))           # ... and their means
+    assert torch.equal(pc.weight[0, :, 0].to(torch.int64), pc.bias.to(torch.int64))   # weights permuted with the bias
+    plain = ops.PackedConv(w, b, pad=0, exact_in=True)
+    assert plain.bias[:2 * C].tolist() == list(range(2 * C)) and plain.pair_tile == 0
