@@ -3,6 +3,9 @@
 // written for coalesced, 128-bit accesses along the channel axis.
 #include <stdlib.h>
 
+#include <algorithm>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -551,16 +554,35 @@ __global__ void spynet_prep_kernel(const float *__restrict__ im1, int p1, const 
 // channels (2n, 2n+1) of the 2*G*O-channel tensor; mask n is channel n of the mask chunk; warp n acts on
 // x-group (n mod G) ("x.repeat(offset_num)") and its output lands in channels n*cg .. n*cg+cg-1 of the
 // (C*O)-channel tensor, which the grouped 1x1 fusion conv (groups=G, 2*cg inputs per group) consumes.
-template <int CG, int O, bool VEC_OFF>
+// VEC_X (CG == 3, feature base 8-byte aligned, even pitch): the 12-byte group of a corner is fetched with ONE 8-byte and ONE
+// 4-byte load (which of the two comes first follows the address parity) instead of three scalar loads, and the 18 fusion
+// weights + 3 biases of a group are read from shared memory instead of global memory.  ncu on the scalar version
+// (profiles/r2_kernels_ncu.txt): 1.28 G L1 sectors for 61 M load requests, l1tex 81 % busy = L1-throughput bound; a warp issued
+// 24 feature + 21 weight requests of ~16-21 sectors each per 2 pixels.  Same arithmetic in the same order: bit-identical.
+constexpr int OD_MAX_FW = 16 * 3 * 6 + 16 * 3;   // fusion weights + biases staged in shared memory (G <= 16, CG = 3, O = 2)
+
+// I32: every element index of the tensors involved fits 31 bits (all sizes up to 4K do): 32-bit index arithmetic — the 64-bit
+// divisions and multiplies of the general version were ~200 of its ~900 instructions per thread.
+template <int CG, int O, bool VEC_OFF, bool VEC_X, bool I32>
 __global__ void __launch_bounds__(TPB) offset_diversity_kernel(const float *__restrict__ xin, int xp, const float *__restrict__ off, int op,
                                         const float *__restrict__ flow, int fp, const float *__restrict__ fw,
                                         const float *__restrict__ fb, int G, float mag, float *__restrict__ out,
                                         int outp, int H, int W) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<long long>(H) * W * G) return;
-  const int g = static_cast<int>(idx % G);
-  const long long pix = idx / G;
-  const int x = static_cast<int>(pix % W), y = static_cast<int>(pix / W);
+  __shared__ float s_fw[VEC_X ? OD_MAX_FW : 1];
+  if (VEC_X) {
+    const int n_w = G * CG * O * CG, n_b = G * CG;
+    for (int i = threadIdx.x; i < n_w + n_b; i += TPB) s_fw[i] = i < n_w ? fw[i] : fb[i - n_w];
+    __syncthreads();
+  }
+  const float *const wsrc = VEC_X ? s_fw : fw;
+  const float *const bsrc = VEC_X ? s_fw + G * CG * O * CG : fb;
+  using idx_t = typename std::conditional<I32, int, long long>::type;
+  using uidx_t = typename std::conditional<I32, unsigned int, long long>::type;
+  const uidx_t idx = static_cast<uidx_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<uidx_t>(H) * W * G) return;
+  const int g = static_cast<int>(idx % static_cast<uidx_t>(G));
+  const idx_t pix = static_cast<idx_t>(idx / static_cast<uidx_t>(G));
+  const int y = static_cast<int>(static_cast<uidx_t>(pix) / static_cast<uidx_t>(W)), x = static_cast<int>(pix - static_cast<idx_t>(y) * W);
   const int Hc = H / 2, Wc = W / 2;
   const int n_off = G * O;
   int bx0, bx1, by0, by1;
@@ -568,8 +590,8 @@ __global__ void __launch_bounds__(TPB) offset_diversity_kernel(const float *__re
   resize_coord(x, 0.5f, Wc, bx0, bx1, bwx);
   resize_coord(y, 0.5f, Hc, by0, by1, bwy);
   const float hx = 1.f - bwx, hy = 1.f - bwy;
-  const float *q00 = off + (static_cast<long long>(by0) * Wc + bx0) * op, *q01 = off + (static_cast<long long>(by0) * Wc + bx1) * op;
-  const float *q10 = off + (static_cast<long long>(by1) * Wc + bx0) * op, *q11 = off + (static_cast<long long>(by1) * Wc + bx1) * op;
+  const float *q00 = off + (static_cast<idx_t>(by0) * Wc + bx0) * op, *q01 = off + (static_cast<idx_t>(by0) * Wc + bx1) * op;
+  const float *q10 = off + (static_cast<idx_t>(by1) * Wc + bx0) * op, *q11 = off + (static_cast<idx_t>(by1) * Wc + bx1) * op;
   // this thread's 2*O offset channels (2n, 2n+1 for n = g*O .. g*O+O-1) and O mask channels are contiguous: with O == 2
   // one float4 + one float2 per corner of the x2 upsampling instead of 6 scalar loads
   float upv[3 * O];
@@ -598,7 +620,7 @@ __global__ void __launch_bounds__(TPB) offset_diversity_kernel(const float *__re
   // n = (g*2cg + j) / cg for j in [0, 2cg): n = 2g and 2g + 1 when O == 2.
   float acc[CG];
 #pragma unroll
-  for (int k = 0; k < CG; ++k) acc[k] = fb[g * CG + k];
+  for (int k = 0; k < CG; ++k) acc[k] = bsrc[g * CG + k];
 #pragma unroll
   for (int t = 0; t < O; ++t) {
     const int n = g * O + t;          // warp index in the (C*O)-channel tensor
@@ -609,15 +631,32 @@ __global__ void __launch_bounds__(TPB) offset_diversity_kernel(const float *__re
     int x0, x1, y0, y1;
     float wx, wy;
     warp_coords(x, y, ox, oy, W, H, x0, x1, y0, y1, wx, wy);
-    const float *a = xin + (static_cast<long long>(y0) * W + x0) * xp + xg * CG;
-    const float *b = xin + (static_cast<long long>(y0) * W + x1) * xp + xg * CG;
-    const float *d = xin + (static_cast<long long>(y1) * W + x0) * xp + xg * CG;
-    const float *e = xin + (static_cast<long long>(y1) * W + x1) * xp + xg * CG;
+    const float *a = xin + (static_cast<idx_t>(y0) * W + x0) * xp + xg * CG;
+    const float *b = xin + (static_cast<idx_t>(y0) * W + x1) * xp + xg * CG;
+    const float *d = xin + (static_cast<idx_t>(y1) * W + x0) * xp + xg * CG;
+    const float *e = xin + (static_cast<idx_t>(y1) * W + x1) * xp + xg * CG;
+    float va[CG], vb[CG], vd[CG], ve[CG];
+    if (VEC_X && CG == 3) {
+      // every corner pointer has the parity of xg * 3 (even pitch, 8-byte aligned base): odd -> [4 B][8 B], even -> [8 B][4 B]
+      const bool odd = (xg & 1) != 0;
+      const int o8 = odd ? 1 : 0, o4 = odd ? 0 : 2;
+      auto gather3 = [&](const float *q, float (&v)[CG]) {
+        const float2 w2 = __ldg(reinterpret_cast<const float2 *>(q + o8));
+        const float w1 = __ldg(q + o4);
+        v[0] = odd ? w1 : w2.x;
+        v[1] = odd ? w2.x : w2.y;
+        v[CG - 1] = odd ? w2.y : w1;
+      };
+      gather3(a, va); gather3(b, vb); gather3(d, vd); gather3(e, ve);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CG; ++j) { va[j] = a[j]; vb[j] = b[j]; vd[j] = d[j]; ve[j] = e[j]; }
+    }
 #pragma unroll
     for (int j = 0; j < CG; ++j) {
-      const float v = bilerp(a[j], b[j], d[j], e[j], wx, wy) * mk;
+      const float v = bilerp(va[j], vb[j], vd[j], ve[j], wx, wy) * mk;
 #pragma unroll
-      for (int k = 0; k < CG; ++k) acc[k] = fmaf(fw[(g * CG + k) * (O * CG) + t * CG + j], v, acc[k]);
+      for (int k = 0; k < CG; ++k) acc[k] = fmaf(wsrc[(g * CG + k) * (O * CG) + t * CG + j], v, acc[k]);
     }
   }
 #pragma unroll
@@ -1017,14 +1056,21 @@ extern "C" int32_t lssvc_offset_diversity(const lssvc_view *x, const lssvc_view 
     LSSVC_LAUNCHED();
     return LSSVC_OK;
   }
-  if (vec_off)
-    offset_diversity_kernel<3, 2, true><<<blocks_for(total), TPB, 0, lssvc::as_stream(stream)>>>(
-        x->ptr, x->pitch, off->ptr, off->pitch, flow->ptr, flow->pitch, fusion_w, fusion_b, groups, magnitude, out->ptr,
-        out->pitch, x->H, x->W);
-  else
-    offset_diversity_kernel<3, 2, false><<<blocks_for(total), TPB, 0, lssvc::as_stream(stream)>>>(
-        x->ptr, x->pitch, off->ptr, off->pitch, flow->ptr, flow->pitch, fusion_w, fusion_b, groups, magnitude, out->ptr,
-        out->pitch, x->H, x->W);
+  // 8-byte gathers + shared-memory fusion weights (see the kernel); LSSVC_GATHER_LEGACY keeps the scalar version for A/B
+  const bool vec_x = !legacy && groups <= 16 && x->pitch % 2 == 0 && (reinterpret_cast<uintptr_t>(x->ptr) & 7) == 0;
+  const long long px = static_cast<long long>(x->H) * x->W;
+  const int max_pitch = std::max(std::max(x->pitch, out->pitch), std::max(off->pitch, flow->pitch));
+  const bool i32 = !legacy && px * max_pitch < (1ll << 31) && total < (1ll << 31);
+#define OD_LAUNCH(VO, VX, I3)                                                                                                \
+  offset_diversity_kernel<3, 2, VO, VX, I3><<<blocks_for(total), TPB, 0, lssvc::as_stream(stream)>>>(                        \
+      x->ptr, x->pitch, off->ptr, off->pitch, flow->ptr, flow->pitch, fusion_w, fusion_b, groups, magnitude, out->ptr,       \
+      out->pitch, x->H, x->W)
+  if (vec_off && vec_x && i32) OD_LAUNCH(true, true, true);
+  else if (vec_off && vec_x) OD_LAUNCH(true, true, false);
+  else if (vec_off) OD_LAUNCH(true, false, false);
+  else if (vec_x) OD_LAUNCH(false, true, false);
+  else OD_LAUNCH(false, false, false);
+#undef OD_LAUNCH
   LSSVC_LAUNCHED();
   return LSSVC_OK;
 }
