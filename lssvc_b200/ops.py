@@ -170,7 +170,7 @@ class PackedConv:
     """Weights of one Conv2d repacked for the kernels: [kh*kw][n_pad][cin_total] + bias[n_pad]."""
 
     __slots__ = ("weight", "bias", "kh", "kw", "stride", "pad", "cout", "n_pad", "cin_total", "src_c", "pixel_shuffle",
-                 "_h2", "exact_in", "coherent", "pair_tile")
+                 "_h2", "exact_in", "coherent", "pair_tile", "_host")
 
     def __init__(self, w, b, stride=1, pad=None, src_channels=None, pixel_shuffle=False, transposed=False, device=None,
                  exact_in=False, coherent=False, pair_tile=0):
@@ -214,7 +214,10 @@ class PackedConv:
             co += view
         bias = torch.zeros(n_pad)
         bias[:cout] = b
-        self.weight = packed.contiguous().to(device)
+        # the host copy stays until the split-fp16 image has been derived from it (weight_h2): packing a model used to issue
+        # ~5 000 tiny device launches on first use; now it is host arithmetic + one upload per tensor
+        self._host = packed.contiguous()
+        self.weight = self._host.to(device)
         self.bias = bias.to(device)
         self.kh, self.kw, self.stride = kh, kw, stride
         self.pad = kh // 2 if pad is None else pad
@@ -229,7 +232,7 @@ class PackedConv:
         fp16 for every weight that matters; acc_scale = 2^-shift undoes it on the fp32 accumulator (exact).
         Each source's channels start at a multiple of 16 (the MMA's K step); pad columns are zero."""
         if self._h2 is None:
-            w = self.weight
+            w = self._host if self._host is not None else self.weight.cpu()      # host arithmetic (IEEE: same bits as on the device)
             taps, n_pad, _ = w.shape
             m = float(w.abs().max())
             shift = 0 if m == 0.0 else 13 - int(math.floor(math.log2(m)))
@@ -254,7 +257,8 @@ class PackedConv:
                 packed[:, 1, :, co:co + c] = (blk - hi.to(torch.float32)).to(torch.float16)
                 ci += c
                 co += round_up(c, 16)
-            self._h2 = (packed.contiguous(), cin16, 2.0 ** -shift)
+            self._h2 = (packed.contiguous().to(self.weight.device), cin16, 2.0 ** -shift)
+            self._host = None
         return self._h2
 
 
