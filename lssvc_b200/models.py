@@ -5,8 +5,9 @@
   LSSVC_extend   src/models/LSSVC_net_extend.py:8  + real bitstreams (compress / decompress / update)
 
 Same constructors, `from_state_dict` / `load_dict`, `set_scale_information`, `forward` / `encode_decode` signatures
-and state_dict layout; tensors in and out are NCHW fp32 torch tensors, batch 1.  Everything between the input
-conversion and the output conversion runs in the kernels of liblssvc_b200.so; there is no PyTorch compute path.
+and state_dict layout; tensors in and out are NCHW fp32 torch tensors (a batch > 1 is coded item by item, estimate mode
+only, as in the reference).  Everything between the input conversion and the output conversion runs in the kernels of
+liblssvc_b200.so; there is no PyTorch compute path.
 """
 import math
 import os
@@ -61,6 +62,30 @@ def _force(model, key, out, mean=None, mask=None, q_view=None):
     got = torch.round(dst - m) if m is not None else dst
     model._force_flips[key] = int((got != ref).sum().item())
     dst.copy_(ref + m if m is not None else ref)
+
+
+def _merge_batch(results):
+    """Per-item results of a batch -> one result: tensors concatenated along the batch dimension, bit counts and times summed
+    (the reference sums its likelihoods over the whole batch: LSSVC_net.py:154-167, IntraSS.py:160), nested dicts merged likewise;
+    the NHWC hand-over of the DPB ("_native") is per frame and is dropped."""
+    out = {}
+    for k, v in results[0].items():
+        if k.startswith("_"):
+            continue
+        vs = [r[k] for r in results]
+        if isinstance(v, torch.Tensor):
+            out[k] = torch.cat(vs, dim=0)
+        elif isinstance(v, dict):
+            out[k] = _merge_batch(vs)
+        elif isinstance(v, (int, float)):
+            out[k] = sum(vs)
+        else:
+            out[k] = v
+    return out
+
+
+def _item(t, b):
+    return None if t is None else t[b:b + 1]
 
 
 class _Bits:
@@ -286,6 +311,12 @@ class IntraSS(Engine):
         """IntraSS.forward (IntraSS.py:137-172).  _async (runner.py): no host synchronisation — the bit counts stay on the
         device (result["_bits"]) and "bit_bl" / "bit_el" are None until the caller reads them."""
         self._require_cuda()
+        if x_bl.dim() == 4 and x_bl.shape[0] > 1:
+            # batch > 1 (estimate mode only, as in the reference): the items are independent frames, coded one after the other
+            if _write is not None or _async:
+                raise ValueError("IntraSS: bitstream / asynchronous coding takes one frame at a time (batch 1)")
+            return _merge_batch([self.forward(x_bl[b:b + 1], x_el[b:b + 1], train_with_recon, _native)
+                                 for b in range(x_bl.shape[0])])
         bits = _Bits(self.device)
         xb, xe = self.image_view(x_bl), self.image_view(x_el)
         # ---- base layer: IntraNoAR.get_layer_information (priors.py:368-388)
@@ -827,6 +858,14 @@ class LSSVC(Engine):
         self._require_cuda()
         dpb = _dpb if _dpb is not None else {"ref_frame_bl": ref_frame_bl, "ref_frame_el": ref_frame_el,
                                              "ref_feature_bl": ref_feature_bl, "ref_feature_el": ref_feature_el}
+        if x_bl.dim() == 4 and x_bl.shape[0] > 1:
+            # batch > 1 (estimate mode only, as in the reference): independent frames with their own DPB entries, one after the other
+            if _write is not None or _async:
+                raise ValueError("LSSVC: bitstream / asynchronous coding takes one frame at a time (batch 1)")
+            keys = ("ref_frame_bl", "ref_frame_el", "ref_feature_bl", "ref_feature_el")
+            return _merge_batch([self.forward_one_frame(x_bl[b:b + 1], x_el[b:b + 1], None, None, None, None,
+                                                        _dpb={k: _item(dpb.get(k), b) for k in keys})
+                                 for b in range(x_bl.shape[0])])
         if (self.use_graphs and _write is None and getattr(self, "_debug", None) is None and not getattr(self, "_force", None)
                 and ops.TRACE is None and not _lib.DRY_RUN):
             return self._forward_graphed(x_bl, x_el, dpb, _async)

@@ -104,3 +104,20 @@ def test_conv_head_supported_is_a_pure_host_predicate():
         d, keep = desc(*args)
         assert lib.lssvc_conv_head_supported(byref(d)) == want, args
     assert lib.lssvc_conv_head_supported(None) == 0
+
+
+def test_batch_two_shapes(dry_run):
+    """Batch > 1 (estimate mode): results are concatenated along the batch dimension, the DPB is split per item."""
+    from lssvc_b200 import IntraSS, LSSVC_extend
+    H = W = 128
+    net_i, net_p = IntraSS(seed=0), LSSVC_extend(seed=1)
+    for n in (net_i, net_p):
+        n.set_scale_information(2.0, (H, W), (0, 0, 0, 0))
+    x_bl, x_el = torch.rand(2, 3, H // 2, W // 2), torch.rand(2, 3, H, W)
+    r = net_i.encode_decode(x_bl, x_el, None, None, H // 2, W // 2, H, W)
+    assert r["x_hat_el"].shape == (2, 3, H, W) and r["x_hat_bl"].shape == (2, 3, H // 2, W // 2) and r["feature_el"].shape == (2, 64, H, W)
+    dpb = {"ref_frame_bl": r["x_hat_bl"], "ref_frame_el": r["x_hat_el"], "ref_feature_bl": None, "ref_feature_el": r["feature_el"]}
+    r = net_p.encode_decode(x_bl, x_el, dpb, None, None, W, H, W // 2, H // 2)
+    assert r["dpb"]["ref_feature_el"].shape == (2, 48, H, W) and r["dpb"]["ref_feature_bl"].shape == (2, 64, H // 2, W // 2)
+    assert r["mv_hat"].shape == (2, 2, H, W) and "_native" not in r["dpb"]
+    assert isinstance(r["bit_bl"], float) and isinstance(r["bit_el"], float)
