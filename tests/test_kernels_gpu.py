@@ -590,7 +590,7 @@ def test_gaussian_and_factorized(cuda_device):
 def test_entropy_epilogues(cuda_device, monkeypatch, shape):
     """LSSVC_EPI_LAPLACE / LSSVC_EPI_BITPARM: the convolution that produces (scale | mean) / z codes the latent in its own
     epilogue.  Against the same convolution followed by the stand-alone entropy kernel: parameters, quantised latent, symbols
-    and CDF rows bit for bit; bits to 1e-12 relative (only the order of the double sum differs)."""
+    and CDF rows bit for bit; bits to 1e-10 relative (only the order of the double-precision sum — atomics — differs)."""
     ops = _ops()
     from lssvc_b200 import entropy
     dev = cuda_device
@@ -626,7 +626,7 @@ def test_entropy_epilogues(cuda_device, monkeypatch, shape):
         a, b_ = run_laplace(True, C), run_laplace(False, C)
         for i in range(4):
             assert torch.equal(a[i], b_[i]), (C, i)
-        assert abs(a[4] - b_[4]) <= 1e-12 * abs(b_[4]) and b_[4] > 0
+        assert abs(a[4] - b_[4]) <= 1e-10 * abs(b_[4]) and b_[4] > 0
         # sanity against torch: symbols = round(y - mean)
         assert torch.equal(a[2].view(C, H, W).cpu(), torch.round(a[5][0] - a[0][0, C:].cpu()).int())
 
@@ -659,7 +659,7 @@ def test_entropy_epilogues(cuda_device, monkeypatch, shape):
     (fa, fbits), (fb, fbits_ref) = run_fourpart(True), run_fourpart(False)
     for i, (u, v) in enumerate(zip(fa, fb)):
         assert torch.equal(u, v), ("fourpart", i)
-    assert abs(fbits - fbits_ref) <= 1e-12 * abs(fbits_ref) and fbits_ref > 0
+    assert abs(fbits - fbits_ref) <= 1e-10 * abs(fbits_ref) and fbits_ref > 0
     assert torch.isfinite(fa[-3]).all() and float(fa[-3].abs().max()) > 0     # y_hat after step 3: every position coded
 
     def run_bitparm(fuse):
@@ -682,7 +682,7 @@ def test_entropy_epilogues(cuda_device, monkeypatch, shape):
     a, b_ = run_bitparm(True), run_bitparm(False)
     assert torch.equal(a[0], b_[0]) and torch.equal(a[1], b_[1])
     assert torch.equal(a[0], torch.round(a[0])) and float(a[0].abs().max()) > 0
-    assert abs(a[2] - b_[2]) <= 1e-12 * abs(b_[2]) and b_[2] > 0
+    assert abs(a[2] - b_[2]) <= 1e-10 * abs(b_[2]) and b_[2] > 0
 
 
 def test_layout_roundtrip(cuda_device):
