@@ -7,14 +7,15 @@
 // P-frame.  Their arithmetic is tiny (1152-1568 FMA per pixel): as a register-blocked direct convolution they are bound by
 // the fp32 FMA rate / the read of their input instead.
 //
-// One CTA = 4 warps = a 64 x 16 pixel tile.  Input channels are walked in chunks of 8; a chunk's halo tile
-// ((16 + k - 1) x (64 + k - 1) pixels) is copied with cp.async (zero fill outside the image = the conv's padding) into
-// shared memory as [quad of 4 channels][row][column parity][column / 2] float4, so that the lanes of a warp, which own
-// the pixel pairs (2 lane, 2 lane + 1), read consecutive float4 for every window column: conflict-free LDS.128.
-// A thread owns 2 (x) x 4 (y) pixels x Cout accumulators and streams the input rows of its strip once: row ir is
-// loaded (k + 1 float4 per channel quad) and added into every output row ir - r it belongs to.  Weights sit in shared
-// memory as [tap][quad][cout] float4 (broadcast reads); for 3x3 with Cout = 2 the 18 float4 of a quad are held in
-// registers.  Several CTAs per SM overlap one CTA's fill with another's arithmetic.
+// One CTA = 4 warps = a 64 x 16 pixel tile.  Input channels are walked one quad (4 channels) at a time; a quad's halo tile
+// ((16 + k - 1) x (64 + k - 1) pixels) is copied with cp.async (zero fill outside the image = the conv's padding) into one
+// of TWO shared-memory buffers laid out [row][column parity][column / 2] float4, so that the lanes of a warp, which own the
+// pixel pairs (2 lane, 2 lane + 1), read consecutive float4 for every window column: conflict-free LDS.128; the copy of
+// quad q + 1 is in flight while quad q is computed (thread x < 64 + k - 1 owns halo column x and walks its rows with a running
+// pointer: ~3 instructions per copy).  A thread owns 2 (x) x 4 (y) pixels x Cout accumulators and streams the input rows of
+// its strip once: row ir is loaded (k + 1 float4) and added into every output row ir - r it belongs to.  Weights sit in
+// shared memory as [tap][quad][cout] float4 (broadcast reads); for 3x3 with Cout = 2 the 18 float4 of a quad are held in
+// registers.  3-4 CTAs per SM.  Measured variants and what bounds the kernel: DESIGN.md 3.2, profiles/r2_ab_results.txt.
 #include <stdlib.h>
 
 #include "common.cuh"
