@@ -76,3 +76,38 @@ def test_interlayer_padding_matches_survey_sizes():
     assert synth.interlayer_padding(1080, 1920)["LR_padded_size"] == (576, 960)
     assert synth.interlayer_padding(2160, 3840)["HR_padded_size"] == (2176, 3840)
     assert synth.interlayer_padding(2160, 3840)["LR_padded_size"] == (1088, 1920)
+
+
+def test_oracle_pad_size_reproduces_reference_golden():
+    """Non-zero pad_size (get_depadded_feature, LSSVC_net.py:271-282 / 453-456, IntraSS.py:124-147): the base layer is coded on a
+    frame with 64 more padding pixels than the enhancement layer's size / 2 and cropped by pad_size = (0, -64, 0, -64) before the
+    inter-layer resamplers.  Fixture: tools/make_golden_padsize.py (reference == oracle bit for bit there)."""
+    g = torch.load(os.path.join(GOLD, "padsize_128.pt"))
+    torch.set_num_threads(8)
+    H, W, PAD = g["H"], g["W"], tuple(g["pad_size"])
+    sd_i = nets.ParamBag(nets.intra_ss_spec(), seed=0, gains=nets.model_gains("I")).state_dict()
+    sd_p = nets.ParamBag(nets.lssvc_spec(), seed=1, gains=nets.model_gains("P")).state_dict()
+    frames = [(torch.nn.functional.pad(b, (0, 64, 0, 64), mode="replicate"), e) for b, e in synth.make_sequence(H, W, 2, seed=g["seed"])]
+    with torch.no_grad():
+        o = orc.intra_ss(sd_i, *frames[0], (H, W), PAD)
+        f = g["frames"][0]
+        assert tuple(o["x_hat_bl"].shape[2:]) == (128, 128) and tuple(o["x_hat_el"].shape[2:]) == (H, W)
+        for k in ("bit_bl", "bit_el"):
+            assert abs(o[k] - f[k]) / f[k] < 1e-4
+        assert (_sub(o["x_hat_bl"], 4) - f["x_hat_bl"]).abs().max() < 1e-4
+        assert (_sub(o["x_hat_el"]) - f["x_hat_el"]).abs().max() < 1e-4
+        assert (_sub(o["feature_el"]) - f["feature_el"]).abs().max() < 1e-3
+        # a different pad_size must give a different enhancement layer (the argument is not ignored) ...
+        o0 = orc.intra_ss(sd_i, frames[0][0][:, :, :64, :64], frames[0][1], (H, W))
+        assert (o0["x_hat_el"] - o["x_hat_el"]).abs().max() > 1e-3
+        dpb = {"ref_frame_bl": o["x_hat_bl"].clamp(0, 1), "ref_frame_el": o["x_hat_el"].clamp(0, 1), "ref_feature_bl": None,
+               "ref_feature_el": o["feature_el"]}
+        o = orc.lssvc(sd_p, *frames[1], dpb, (H, W), 2.0, PAD)
+        f = g["frames"][1]
+        for k in ("bit_bl", "bit_el"):
+            assert abs(o[k] - f[k]) / f[k] < 1e-4
+        assert (_sub(o["dpb"]["ref_frame_bl"], 4) - f["ref_frame_bl"]).abs().max() < 1e-4
+        assert (_sub(o["dpb"]["ref_frame_el"]) - f["ref_frame_el"]).abs().max() < 1e-4
+        assert (_sub(o["dpb"]["ref_feature_el"]) - f["ref_feature_el"]).abs().max() < 1e-3
+        assert (_sub(o["mv_hat"]) - f["mv_hat"]).abs().max() < 1e-3
+        assert (o["four_part"]["y_q"] == f["sym_el"].float()).float().mean() > 0.999
